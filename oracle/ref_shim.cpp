@@ -18,6 +18,7 @@
 #include <vector>
 #include <chrono>
 #include <unistd.h>
+#include <cstdlib>
 #include <thread>
 #include <atomic>
 
@@ -78,6 +79,13 @@ extern "C" {
 
 int ref_create(ref_ctx** out) {
     *out = new ref_ctx();
+    // the reference chats on std::cerr (ribbon-count warnings, "Collision possible ..."); keep
+    // test and bench logs readable unless asked otherwise.  The ctx is never freed before exit in
+    // practice; ref_destroy restores the buffer.
+    if (!getenv("PPE_REF_VERBOSE")) {
+        static NullBuf quiet;
+        std::cerr.rdbuf(&quiet);
+    }
     (*out)->config.setMap(std::make_shared<Map>());
     (*out)->config.setNowFunction([]() -> double {
         struct timespec t; clock_gettime(CLOCK_REALTIME, &t);

@@ -1,0 +1,551 @@
+// ppe_capi.cu -- the C ABI of include/ppe.h: context, HBM-resident world state, batch calls.
+//
+// Host side of the engine.  Loop invariants that the reference recomputes per sample point with
+// the host libm (cos/sin of obstacle yaws, covariance inverse, normaliser) are computed here, once,
+// with the same host libm; everything per edge and per sample runs in the kernels of
+// ppe_kernels.cu.  There is no CPU evaluation path: without a usable CUDA device ppe_create fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "ppe.h"
+#include "ppe_kernels.cuh"
+
+using namespace ppe;
+
+struct ppe_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    ppe_config cfg{};
+    bool have_cfg = false;
+
+    // static map
+    uint32_t* d_map = nullptr;
+    int map_kind = kMapNone, rows = 0, cols = 0, stride_words = 0;
+    double resolution = 1;
+
+    // dynamic obstacles
+    ObstacleD* d_obs = nullptr;
+    int obs_kind = kObsNone, n_obs = 0;
+
+    // interned ribbon sets: host mirror + device pool (uploaded lazily before a batch)
+    std::vector<double> h_ribbons; // 4 doubles per ribbon
+    std::vector<int> h_off, h_cnt;
+    std::vector<double> h_cct;
+    bool sets_dirty = true;
+    int max_set = 0;
+    double4* d_ribbons = nullptr;
+    int* d_off = nullptr;
+    int* d_cnt = nullptr;
+    double* d_cct = nullptr;
+    size_t cap_ribbons = 0, cap_sets = 0;
+
+    // grow-only batch buffers for the host-pointer entry points
+    ppe_edge* d_edges = nullptr;
+    ppe_edge_result* d_results = nullptr;
+    size_t cap_edges = 0, cap_results = 0, cap_dubi = 0;
+    double* d_dub = nullptr; // q0 q1 rho param length
+    int32_t* d_dubi = nullptr; // type err
+    size_t cap_dub = 0;
+
+    // ribbons-after pool
+    double4* d_out_ribbons = nullptr;
+    unsigned long long* d_out_count = nullptr;
+    size_t out_cap = 0;
+
+    unsigned long long* d_work = nullptr;
+    BestD* d_block_best = nullptr;
+    BestD* d_best = nullptr;
+    int max_blocks = 0;
+
+    // bookkeeping of the last true-cost batch (for ppe_get_ribbons_after / ppe_best)
+    std::vector<int64_t> last_off;
+    std::vector<int32_t> last_n, last_set, last_changed;
+    std::vector<double> h_out_ribbons;
+    bool out_downloaded = false;
+    unsigned long long last_out_count = 0;
+    bool have_batch = false;
+
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(ppe_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define PPE_CUDA(ctx, call)                                                   \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return fail((ctx), PPE_ERR_CUDA, #call, e_);   \
+    } while (0)
+
+template <typename T>
+int grow(ppe_ctx* ctx, T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return PPE_OK;
+    size_t ncap = *cap ? *cap : 1024;
+    while (ncap < need) ncap *= 2;
+    if (*p) PPE_CUDA(ctx, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    PPE_CUDA(ctx, cudaMalloc((void**)p, ncap * sizeof(T)));
+    *cap = ncap;
+    return PPE_OK;
+}
+
+int ribbon_cap_for(int max_set) {
+    int cap = ((max_set + 32 + 31) / 32) * 32; // head-room for splits (a split adds one ribbon)
+    if (cap < 32) cap = 32;
+    return cap;
+}
+
+int upload_sets(ppe_ctx* ctx) {
+    if (!ctx->sets_dirty) return PPE_OK;
+    const size_t nr = ctx->h_ribbons.size() / 4, ns = ctx->h_cnt.size();
+    if (nr + 1 > ctx->cap_ribbons) {
+        if (ctx->d_ribbons) PPE_CUDA(ctx, cudaFree(ctx->d_ribbons));
+        ctx->d_ribbons = nullptr;
+        size_t c = ctx->cap_ribbons ? ctx->cap_ribbons : 1024;
+        while (c < nr + 1) c *= 2;
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_ribbons, c * sizeof(double4)));
+        ctx->cap_ribbons = c;
+    }
+    if (ns + 1 > ctx->cap_sets) {
+        if (ctx->d_off) PPE_CUDA(ctx, cudaFree(ctx->d_off));
+        if (ctx->d_cnt) PPE_CUDA(ctx, cudaFree(ctx->d_cnt));
+        if (ctx->d_cct) PPE_CUDA(ctx, cudaFree(ctx->d_cct));
+        ctx->d_off = ctx->d_cnt = nullptr;
+        ctx->d_cct = nullptr;
+        size_t c = ctx->cap_sets ? ctx->cap_sets : 64;
+        while (c < ns + 1) c *= 2;
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_off, c * sizeof(int)));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_cnt, c * sizeof(int)));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_cct, c * sizeof(double)));
+        ctx->cap_sets = c;
+    }
+    if (nr) PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_ribbons, ctx->h_ribbons.data(), nr * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (ns) {
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_off, ctx->h_off.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cnt, ctx->h_cnt.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cct, ctx->h_cct.data(), ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->sets_dirty = false;
+    return PPE_OK;
+}
+
+int ensure_pool(ppe_ctx* ctx, size_t want) {
+    if (ctx->d_out_ribbons && ctx->out_cap >= want) return PPE_OK;
+    if (ctx->d_out_ribbons) PPE_CUDA(ctx, cudaFree(ctx->d_out_ribbons));
+    ctx->d_out_ribbons = nullptr;
+    ctx->out_cap = 0;
+    PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_out_ribbons, want * sizeof(double4)));
+    ctx->out_cap = want;
+    return PPE_OK;
+}
+
+int make_world(ppe_ctx* ctx, WorldD* w) {
+    if (!ctx->have_cfg) return fail(ctx, PPE_ERR_STATE, "ppe_set_config must be called before a batch");
+    int rc = upload_sets(ctx);
+    if (rc != PPE_OK) return rc;
+    if (!ctx->d_out_ribbons) {
+        size_t want = (size_t)1 << 22; // 4 Mi ribbons = 128 MiB; grows on demand
+        const char* env = getenv("PPE_RIBBON_POOL");
+        if (env && atoll(env) > 0) want = (size_t)atoll(env);
+        rc = ensure_pool(ctx, want);
+        if (rc != PPE_OK) return rc;
+    }
+    memset(w, 0, sizeof *w);
+    w->cfg = ctx->cfg;
+    w->dt = ctx->cfg.collision_checking_increment / ctx->cfg.max_speed;
+    w->horizon_end = ctx->cfg.time_horizon + 1e-12 + ctx->cfg.start_state_time;
+    w->map_bits = ctx->d_map;
+    w->map_kind = ctx->map_kind;
+    w->rows = ctx->rows; w->cols = ctx->cols; w->stride_words = ctx->stride_words;
+    w->resolution = ctx->resolution;
+    w->obstacles = ctx->d_obs;
+    w->obs_kind = ctx->n_obs > 0 ? ctx->obs_kind : kObsNone;
+    w->n_obs = ctx->obs_kind == kObsNone ? 0 : ctx->n_obs;
+    w->ribbons = ctx->d_ribbons;
+    w->set_offset = ctx->d_off;
+    w->set_count = ctx->d_cnt;
+    w->set_cct = ctx->d_cct;
+    w->n_sets = (int)ctx->h_cnt.size();
+    w->ribbon_cap = ribbon_cap_for(ctx->max_set);
+    w->out_ribbons = ctx->d_out_ribbons;
+    w->out_count = ctx->d_out_count;
+    w->out_cap = ctx->out_cap;
+    if (true_cost_smem_bytes(w->ribbon_cap, w->n_obs) > 200 * 1024)
+        return fail(ctx, PPE_ERR_CAPACITY, "ribbon sets / obstacle list too large for the per-CTA shared-memory working set");
+    return PPE_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int ppe_abi_version(void) { return PPE_ABI_VERSION; }
+int ppe_abi_sizeof_config(void) { return (int)sizeof(ppe_config); }
+int ppe_abi_sizeof_edge(void) { return (int)sizeof(ppe_edge); }
+int ppe_abi_sizeof_edge_result(void) { return (int)sizeof(ppe_edge_result); }
+
+int ppe_create(int device, ppe_ctx** out) {
+    if (!out) return PPE_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return PPE_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PPE_ERR_NO_DEVICE;
+    if (prop.major < 10) return PPE_ERR_NO_DEVICE; // sm_100a SASS only; no other code path is shipped
+    if (cudaSetDevice(device) != cudaSuccess) return PPE_ERR_NO_DEVICE;
+    ppe_ctx* ctx = new ppe_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PPE_ERR_CUDA; }
+    ctx->max_blocks = ctx->sm_count * 32;
+    bool ok = cudaMalloc((void**)&ctx->d_work, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_out_count, sizeof(unsigned long long)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_block_best, (size_t)ctx->max_blocks * sizeof(BestD)) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_best, sizeof(BestD)) == cudaSuccess;
+    if (!ok) { ppe_destroy(ctx); return PPE_ERR_CUDA; }
+    *out = ctx;
+    return PPE_OK;
+}
+
+void ppe_destroy(ppe_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_map); cudaFree(ctx->d_obs);
+    cudaFree(ctx->d_ribbons); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct);
+    cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
+    cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ppe_last_error(const ppe_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ppe_set_config(ppe_ctx* ctx, const ppe_config* cfg) {
+    if (!ctx || !cfg) return PPE_ERR_INVALID;
+    if (!(cfg->max_speed > 0) || !(cfg->collision_checking_increment > 0) || !(cfg->ribbon_width > 0) ||
+        !(cfg->turning_radius > 0) || !(cfg->coverage_turning_radius > 0))
+        return fail(ctx, PPE_ERR_INVALID, "config: speeds, radii, increment and ribbon width must be positive");
+    ctx->cfg = *cfg;
+    ctx->have_cfg = true;
+    return PPE_OK;
+}
+
+int ppe_set_map_none(ppe_ctx* ctx) {
+    if (!ctx) return PPE_ERR_INVALID;
+    ctx->map_kind = kMapNone;
+    return PPE_OK;
+}
+
+int ppe_set_map_bitmap(ppe_ctx* ctx, const uint8_t* bits, int rows, int cols, int row_stride_bytes, double resolution) {
+    if (!ctx || !bits || rows <= 0 || cols <= 0 || row_stride_bytes * 8 < cols || !(resolution > 0))
+        return fail(ctx, PPE_ERR_INVALID, "ppe_set_map_bitmap: bad arguments");
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    // repack rows to whole 32-bit words so one lane-load serves 32 cells
+    const int words = (cols + 31) / 32;
+    std::vector<uint32_t> packed((size_t)rows * words, 0u);
+    for (int r = 0; r < rows; r++) {
+        const uint8_t* src = bits + (size_t)r * row_stride_bytes;
+        uint32_t* dst = packed.data() + (size_t)r * words;
+        const int nbytes = (cols + 7) / 8;
+        for (int b = 0; b < nbytes; b++) dst[b >> 2] |= (uint32_t)src[b] << (8 * (b & 3));
+        // clear padding bits past `cols`
+        if (cols & 31) dst[words - 1] &= (1u << (cols & 31)) - 1u;
+    }
+    if (ctx->d_map) PPE_CUDA(ctx, cudaFree(ctx->d_map));
+    ctx->d_map = nullptr;
+    PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_map, packed.size() * sizeof(uint32_t)));
+    PPE_CUDA(ctx, cudaMemcpy(ctx->d_map, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->map_kind = kMapBitmap;
+    ctx->rows = rows; ctx->cols = cols; ctx->stride_words = words; ctx->resolution = resolution;
+    return PPE_OK;
+}
+
+int ppe_set_obstacles_none(ppe_ctx* ctx) {
+    if (!ctx) return PPE_ERR_INVALID;
+    ctx->obs_kind = kObsNone;
+    ctx->n_obs = 0;
+    return PPE_OK;
+}
+
+static int upload_obstacles(ppe_ctx* ctx, const std::vector<ObstacleD>& h, int kind) {
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->d_obs) PPE_CUDA(ctx, cudaFree(ctx->d_obs));
+    ctx->d_obs = nullptr;
+    if (!h.empty()) {
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_obs, h.size() * sizeof(ObstacleD)));
+        PPE_CUDA(ctx, cudaMemcpy(ctx->d_obs, h.data(), h.size() * sizeof(ObstacleD), cudaMemcpyHostToDevice));
+    }
+    ctx->obs_kind = kind;
+    ctx->n_obs = (int)h.size();
+    return PPE_OK;
+}
+
+int ppe_set_obstacles_binary(ppe_ctx* ctx, int n, const double* x, const double* y, const double* yaw,
+                             const double* speed, const double* time, const double* width, const double* length) {
+    if (!ctx || n < 0 || (n > 0 && (!x || !y || !yaw || !speed || !time || !width || !length)))
+        return fail(ctx, PPE_ERR_INVALID, "ppe_set_obstacles_binary: bad arguments");
+    std::vector<ObstacleD> h((size_t)n);
+    for (int i = 0; i < n; i++) {
+        ObstacleD& o = h[i];
+        memset(&o, 0, sizeof o);
+        o.X = x[i]; o.Y = y[i]; o.Time = time[i]; o.Speed = speed[i];
+        o.cosYaw = cos(yaw[i]); o.sinYaw = sin(yaw[i]);
+        o.a = (length[i] + 2) / 2; // strict: Length += 2, then `fabs(rotatedX) < Length / 2`
+        o.b = (width[i] + 2) / 2;
+    }
+    return upload_obstacles(ctx, h, kObsBinary);
+}
+
+int ppe_set_obstacles_gaussian(ppe_ctx* ctx, int n, const double* x, const double* y, const double* yaw,
+                               const double* speed, const double* time, const double* cov) {
+    if (!ctx || n < 0 || (n > 0 && (!x || !y || !yaw || !speed || !time)))
+        return fail(ctx, PPE_ERR_INVALID, "ppe_set_obstacles_gaussian: bad arguments");
+    std::vector<ObstacleD> h((size_t)n);
+    for (int i = 0; i < n; i++) {
+        ObstacleD& o = h[i];
+        memset(&o, 0, sizeof o);
+        o.X = x[i]; o.Y = y[i]; o.Time = time[i]; o.Speed = speed[i];
+        o.cosYaw = cos(yaw[i]); o.sinYaw = sin(yaw[i]);
+        // default covariance of GaussianDynamicObstaclesManager::Obstacle (Gaussian...h:24-25)
+        const double c00 = cov ? cov[4 * i] : 30, c01 = cov ? cov[4 * i + 1] : 10, c10 = cov ? cov[4 * i + 2] : 10,
+                     c11 = cov ? cov[4 * i + 3] : 30;
+        // Obstacle::pdf (Gaussian...h:39-44): 2x2 inverse and determinant in Eigen's closed form
+        const double det = c00 * c11 - c10 * c01;
+        const double invdet = 1.0 / det;
+        o.a = c11 * invdet;   // i00
+        o.b = -c10 * invdet;  // i10
+        o.c = -c01 * invdet;  // i01
+        o.d = c00 * invdet;   // i11
+        const double twoPi = 2 * M_PI;
+        o.norm = 1.0 / twoPi / sqrt(det);
+    }
+    return upload_obstacles(ctx, h, kObsGaussian);
+}
+
+int ppe_put_ribbon_set(ppe_ctx* ctx, int n, const double* xyxy, double coverage_completed_time, int32_t* set_id) {
+    if (!ctx || n < 0 || (n > 0 && !xyxy) || !set_id) return fail(ctx, PPE_ERR_INVALID, "ppe_put_ribbon_set: bad arguments");
+    if (!ctx->have_cfg) return fail(ctx, PPE_ERR_STATE, "ppe_set_config must precede ppe_put_ribbon_set (ribbon width)");
+    const double W = ctx->cfg.ribbon_width;
+    const int off = (int)(ctx->h_ribbons.size() / 4);
+    int kept = 0;
+    for (int i = 0; i < n; i++) {
+        const double sx = xyxy[4 * i], sy = xyxy[4 * i + 1], ex = xyxy[4 * i + 2], ey = xyxy[4 * i + 3];
+        // RibbonManager::add drops ribbons that are already covered (RibbonManager.cpp:7-12,154-158)
+        const double sq = (ex - sx) * (ex - sx) + (ey - sy) * (ey - sy);
+        const double minLength = 2 * W;
+        if (sq < minLength * minLength / 1) continue;
+        ctx->h_ribbons.push_back(sx); ctx->h_ribbons.push_back(sy);
+        ctx->h_ribbons.push_back(ex); ctx->h_ribbons.push_back(ey);
+        kept++;
+    }
+    if (ribbon_cap_for(kept) > 512) {
+        ctx->h_ribbons.resize((size_t)off * 4);
+        return fail(ctx, PPE_ERR_CAPACITY, "ribbon set larger than the per-edge device working set (480 ribbons)");
+    }
+    ctx->h_off.push_back(off);
+    ctx->h_cnt.push_back(kept);
+    ctx->h_cct.push_back(coverage_completed_time);
+    if (kept > ctx->max_set) ctx->max_set = kept;
+    ctx->sets_dirty = true;
+    *set_id = (int32_t)ctx->h_cnt.size() - 1;
+    return PPE_OK;
+}
+
+int ppe_clear_ribbon_sets(ppe_ctx* ctx) {
+    if (!ctx) return PPE_ERR_INVALID;
+    ctx->h_ribbons.clear(); ctx->h_off.clear(); ctx->h_cnt.clear(); ctx->h_cct.clear();
+    ctx->max_set = 0;
+    ctx->sets_dirty = true;
+    ctx->have_batch = false;
+    return PPE_OK;
+}
+
+// ---- K1 ------------------------------------------------------------------------------------------
+int ppe_dubins_batch_device(ppe_ctx* ctx, int64_t n, const double* d_q0, const double* d_q1, const double* d_rho,
+                            int32_t* d_type, double* d_param, double* d_length, int32_t* d_err, void* stream) {
+    if (!ctx || n < 0) return PPE_ERR_INVALID;
+    if (n == 0) return PPE_OK;
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    PPE_CUDA(ctx, launch_dubins_batch(n, d_q0, d_q1, d_rho, d_type, d_param, d_length, d_err, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return PPE_OK;
+}
+
+int ppe_dubins_batch(ppe_ctx* ctx, int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type,
+                     double* param, double* length, int32_t* err) {
+    if (!ctx || n < 0 || (n > 0 && (!q0 || !q1 || !rho || !type || !param || !length || !err)))
+        return fail(ctx, PPE_ERR_INVALID, "ppe_dubins_batch: bad arguments");
+    if (n == 0) return PPE_OK;
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    // layout: q0[3n] q1[3n] rho[n] param[3n] length[n]
+    int rc = grow(ctx, &ctx->d_dub, &ctx->cap_dub, (size_t)n * 11);
+    if (rc != PPE_OK) return rc;
+    rc = grow(ctx, &ctx->d_dubi, &ctx->cap_dubi, (size_t)n * 2);
+    if (rc != PPE_OK) return rc;
+    double* dq0 = ctx->d_dub;
+    double* dq1 = dq0 + 3 * n;
+    double* drho = dq1 + 3 * n;
+    double* dpar = drho + n;
+    double* dlen = dpar + 3 * n;
+    int32_t* dtype = ctx->d_dubi;
+    int32_t* derr = dtype + n;
+    cudaStream_t s = ctx->stream;
+    PPE_CUDA(ctx, cudaMemcpyAsync(dq0, q0, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    PPE_CUDA(ctx, cudaMemcpyAsync(dq1, q1, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    PPE_CUDA(ctx, cudaMemcpyAsync(drho, rho, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = ppe_dubins_batch_device(ctx, n, dq0, dq1, drho, dtype, dpar, dlen, derr, s);
+    if (rc != PPE_OK) return rc;
+    PPE_CUDA(ctx, cudaMemcpyAsync(param, dpar, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PPE_CUDA(ctx, cudaMemcpyAsync(length, dlen, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    PPE_CUDA(ctx, cudaMemcpyAsync(type, dtype, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    PPE_CUDA(ctx, cudaMemcpyAsync(err, derr, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    PPE_CUDA(ctx, cudaStreamSynchronize(s));
+    return PPE_OK;
+}
+
+// ---- K2 / K3 ----------------------------------------------------------------------------------------
+int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges, ppe_edge_result* d_results, void* stream) {
+    if (!ctx || n < 0) return PPE_ERR_INVALID;
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    WorldD w;
+    int rc = make_world(ctx, &w);
+    if (rc != PPE_OK) return rc;
+    ctx->have_batch = false;
+    ctx->out_downloaded = false;
+    if (n == 0) return PPE_OK;
+    int launches = 0;
+    PPE_CUDA(ctx, launch_true_cost_batch(w, n, d_edges, d_results, ctx->d_work, ctx->d_block_best, ctx->max_blocks,
+                                         ctx->d_best, ctx->sm_count, (cudaStream_t)stream, &launches));
+    ctx->launches += launches;
+    return PPE_OK;
+}
+
+int ppe_best_device(ppe_ctx* ctx, double* f, int64_t* edge_index, void* stream) {
+    if (!ctx || !f || !edge_index) return PPE_ERR_INVALID;
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    BestD b;
+    PPE_CUDA(ctx, cudaMemcpyAsync(&b, ctx->d_best, sizeof b, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    PPE_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    *f = b.idx >= 0 ? b.f : INFINITY;
+    *edge_index = b.idx;
+    return PPE_OK;
+}
+
+int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge_result* results) {
+    if (!ctx || n < 0 || (n > 0 && (!edges || !results))) return fail(ctx, PPE_ERR_INVALID, "ppe_true_cost_batch: bad arguments");
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) { ctx->have_batch = false; return PPE_OK; }
+    {
+        int rc = grow(ctx, &ctx->d_edges, &ctx->cap_edges, (size_t)n);
+        if (rc != PPE_OK) return rc;
+        rc = grow(ctx, &ctx->d_results, &ctx->cap_results, (size_t)n);
+        if (rc != PPE_OK) return rc;
+    }
+    cudaStream_t s = ctx->stream;
+    PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_edges, edges, (size_t)n * sizeof(ppe_edge), cudaMemcpyHostToDevice, s));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int rc = ppe_true_cost_batch_device(ctx, n, ctx->d_edges, ctx->d_results, s);
+        if (rc != PPE_OK) return rc;
+        PPE_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results, (size_t)n * sizeof(ppe_edge_result), cudaMemcpyDeviceToHost, s));
+        PPE_CUDA(ctx, cudaMemcpyAsync(&ctx->last_out_count, ctx->d_out_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        PPE_CUDA(ctx, cudaStreamSynchronize(s));
+        if (ctx->last_out_count <= ctx->out_cap) break;
+        // the ribbons-after pool was too small for this batch: grow it and run the batch again
+        rc = ensure_pool(ctx, (size_t)(ctx->last_out_count + ctx->last_out_count / 4 + 1024));
+        if (rc != PPE_OK) return rc;
+    }
+    ctx->last_off.resize((size_t)n); ctx->last_n.resize((size_t)n); ctx->last_set.resize((size_t)n); ctx->last_changed.resize((size_t)n);
+    for (int64_t i = 0; i < n; i++) {
+        ctx->last_off[i] = results[i].ribbons_offset;
+        ctx->last_n[i] = results[i].n_ribbons_after;
+        ctx->last_set[i] = edges[i].ribbon_set;
+        ctx->last_changed[i] = results[i].ribbons_changed;
+    }
+    ctx->have_batch = true;
+    ctx->out_downloaded = false;
+    return PPE_OK;
+}
+
+int ppe_get_ribbons_after(ppe_ctx* ctx, int64_t i, double* xyxy, int cap) {
+    if (!ctx || !ctx->have_batch || i < 0 || (size_t)i >= ctx->last_n.size() || (cap > 0 && !xyxy))
+        return fail(ctx, PPE_ERR_INVALID, "ppe_get_ribbons_after: no such edge in the last ppe_true_cost_batch");
+    if (!ctx->last_changed[i]) {
+        // identical to the parent's interned set
+        const int set = ctx->last_set[i];
+        if (set < 0 || (size_t)set >= ctx->h_cnt.size()) return fail(ctx, PPE_ERR_INVALID, "unknown ribbon set");
+        const int n = ctx->h_cnt[set];
+        const double* src = ctx->h_ribbons.data() + (size_t)ctx->h_off[set] * 4;
+        for (int k = 0; k < n && k < cap; k++) memcpy(xyxy + 4 * k, src + 4 * k, 4 * sizeof(double));
+        return n;
+    }
+    if (ctx->last_off[i] < 0) return fail(ctx, PPE_ERR_CAPACITY, "ribbons-after of this edge were not materialised");
+    if (!ctx->out_downloaded) {
+        PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+        const size_t cnt = (size_t)(ctx->last_out_count < ctx->out_cap ? ctx->last_out_count : ctx->out_cap);
+        ctx->h_out_ribbons.resize(cnt * 4);
+        if (cnt) PPE_CUDA(ctx, cudaMemcpy(ctx->h_out_ribbons.data(), ctx->d_out_ribbons, cnt * sizeof(double4), cudaMemcpyDeviceToHost));
+        ctx->out_downloaded = true;
+    }
+    const int n = ctx->last_n[i];
+    const double* src = ctx->h_out_ribbons.data() + (size_t)ctx->last_off[i] * 4;
+    for (int k = 0; k < n && k < cap; k++) memcpy(xyxy + 4 * k, src + 4 * k, 4 * sizeof(double));
+    return n;
+}
+
+int ppe_best(ppe_ctx* ctx, double* f, int64_t* edge_index) {
+    if (!ctx || !ctx->have_batch) return fail(ctx, PPE_ERR_STATE, "ppe_best: no batch has been evaluated");
+    return ppe_best_device(ctx, f, edge_index, ctx->stream);
+}
+
+int64_t ppe_launch_count(const ppe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ppe_measure_fp64_peak(ppe_ctx* ctx, double* tflops, void* stream) {
+    if (!ctx || !tflops) return PPE_ERR_INVALID;
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    double* d_out = nullptr;
+    PPE_CUDA(ctx, cudaMalloc((void**)&d_out, sizeof(double)));
+    cudaEvent_t a, b;
+    PPE_CUDA(ctx, cudaEventCreate(&a));
+    PPE_CUDA(ctx, cudaEventCreate(&b));
+    const int blocks = ctx->sm_count * 8, iters = 1 << 15;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        PPE_CUDA(ctx, cudaEventRecord(a, s));
+        PPE_CUDA(ctx, launch_fp64_peak(d_out, blocks, iters, s));
+        PPE_CUDA(ctx, cudaEventRecord(b, s));
+        PPE_CUDA(ctx, cudaEventSynchronize(b));
+        float ms = 0;
+        PPE_CUDA(ctx, cudaEventElapsedTime(&ms, a, b));
+        const double flops = (double)blocks * 256.0 * 8.0 * (double)iters * 2.0;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    ctx->launches += 4;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d_out);
+    *tflops = best;
+    return PPE_OK;
+}
+
+} // extern "C"

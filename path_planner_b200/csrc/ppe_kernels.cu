@@ -1,0 +1,707 @@
+// ppe_kernels.cu -- hand-written sm_100a kernels of the batched Dubins edge-evaluation engine.
+//
+//   K1 k1_dubins_batch   one thread = one (q0, q1, rho) triple: shortest Dubins word, branch-free
+//                        over the six words, fp64.       Replaces Edge::computeApproxCost ->
+//                        DubinsWrapper::set -> dubins_shortest_path (Edge.cpp:11-20,
+//                        DubinsWrapper.cpp:9-17).
+//   K2 k2_true_cost      one warp = one edge; lanes = consecutive sample points of the path.
+//                        Replaces Edge::computeTrueCost (Edge.cpp:68-206) including the Dubins
+//                        solve for path-less edges, Map/GridWorldMap::isBlocked, Binary/Gaussian
+//                        collisionExists, the RibbonManager cover state machine, the truncated end
+//                        state, g (Vertex.cpp:102-104) and h = MaxDistance (RibbonManager.cpp:234-248).
+//   K3 best-f epilogue   fused into K2 (per-warp running best, block reduce) + k3_best_final.
+//
+// No tensor cores: this is branchy fp64 transcendental + bit-gather work.  Compiled with
+// -fmad=false: the x86-64 reference build has no FMA contraction and discrete outcomes (word
+// choice, cell index, ribbon containment, sample count) must not flip.
+#include <float.h>
+
+#include "ppe_kernels.cuh"
+#include "ppe_math.cuh"
+
+namespace ppe {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kBlockThreads = kWarpsPerBlock * 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kSkipCap = 1 << 28;
+constexpr int kMaxSamples = 1 << 22;
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(kFull, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, d));
+    return v;
+}
+
+__device__ __forceinline__ RibbonD load_ribbon(const double4* p) {
+    const double4 v = *p;
+    RibbonD r;
+    r.sx = v.x; r.sy = v.y; r.ex = v.z; r.ey = v.w;
+    return r;
+}
+
+__device__ __forceinline__ double4 pack_ribbon(double sx, double sy, double ex, double ey) {
+    return make_double4(sx, sy, ex, ey);
+}
+
+// Map::isBlocked (Map.cpp:4-6) / GridWorldMap::isBlocked (GridWorldMap.cpp:84-93).  The bitmap
+// (<= 2 MiB at 4096^2) stays L2/L1 resident; consecutive lanes are consecutive 0.05 m samples, so
+// a warp's 32 lookups fall into one or two 32-byte sectors.
+__device__ __forceinline__ bool map_blocked(const WorldD& w, double x, double y) {
+    if (w.map_kind == kMapNone) return false;
+    if (x < 0 || x / w.resolution >= (double)w.cols) return true;
+    if (y < 0 || y / w.resolution >= (double)w.rows) return true;
+    const unsigned long long r = (unsigned long long)(y / w.resolution);
+    const unsigned long long c = (unsigned long long)(x / w.resolution);
+    const uint32_t word = __ldg(&w.map_bits[r * (unsigned long long)w.stride_words + (c >> 5)]);
+    return (word >> (c & 31)) & 1u;
+}
+
+// BinaryDynamicObstaclesManager::collisionExists (Binary...cpp:4-22) and
+// GaussianDynamicObstaclesManager::collisionExists (Gaussian...cpp:3-13), strict = true.
+// Obstacles are staged in shared memory once per CTA; every lane walks them in container order so
+// the per-sample sum has the reference's summation order.
+__device__ __forceinline__ double collision_exists(int kind, int n_obs, const ObstacleD* __restrict__ obs, double x,
+                                                   double y, double time) {
+    double sum = 0;
+    if (kind == kObsBinary) {
+        for (int i = 0; i < n_obs; i++) {
+            const ObstacleD& o = obs[i];
+            const double dtm = time - o.Time;
+            const double dx = o.Speed * dtm * o.cosYaw;
+            const double dy = o.Speed * dtm * o.sinYaw;
+            const double X = o.X + dx, Y = o.Y + dy;
+            const double tx = x - X, ty = y - Y;
+            const double rx = tx * o.cosYaw - ty * o.sinYaw;
+            const double ry = tx * o.sinYaw + ty * o.cosYaw;
+            if (fabs(rx) < o.a && fabs(ry) < o.b) sum += 1.0;
+        }
+        return sum;
+    }
+    for (int i = 0; i < n_obs; i++) {
+        const ObstacleD& o = obs[i];
+        const double dtm = time - o.Time;
+        const double dx = o.Speed * dtm * o.cosYaw;
+        const double dy = o.Speed * dtm * o.sinYaw;
+        const double X = o.X + dx, Y = o.Y + dy;
+        const double d0 = x - X, d1 = y - Y;
+        const double r0 = d0 * o.a + d1 * o.b;  // (v^T Sigma^-1)_0 = v0*i00 + v1*i10
+        const double r1 = d0 * o.c + d1 * o.d;  // (v^T Sigma^-1)_1 = v0*i01 + v1*i11
+        const double quadform = r0 * d0 + r1 * d1;
+        sum += o.norm * exp(-0.5 * quadform);
+    }
+    if (sum < 1e-5) return 0;
+    return sum;
+}
+
+// RibbonManager::minDistanceFrom (RibbonManager.cpp:142-152): lanes over ribbons.
+__device__ __forceinline__ double warp_min_distance_from(const double4* cur, int nr, double x, double y, double W,
+                                                         int lane) {
+    if (nr == 0) return 0;
+    double mn = DBL_MAX;
+    bool inside = false;
+    for (int r = lane; r < nr; r += 32) {
+        const RibbonD rb = load_ribbon(cur + r);
+        double px, py;
+        ribbon_projection(rb, x, y, &px, &py);
+        if (ribbon_contains(rb, x, y, px, py, false, W)) inside = true;
+        const double dStart = point_distance(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart);
+    }
+    if (__any_sync(kFull, inside)) return 0;
+    return warp_min(mn);
+}
+
+// RibbonManager::cover(x, y, strict = true) (RibbonManager.cpp:14-22 with Ribbon::split,
+// Ribbon.cpp:9-17 and add, RibbonManager.cpp:154-158): every ribbon is split independently; list
+// order is kept by a warp prefix sum over the 0/1/2 pieces each ribbon leaves behind.  Writes the
+// new list into `alt`; the caller swaps the buffers when something changed.
+__device__ __forceinline__ int warp_cover(const double4* cur, double4* alt, int nr, int cap, double x, double y,
+                                          double W, int lane, bool* changed, bool* overflow) {
+    int out_base = 0;
+    bool any_change = false;
+    for (int base = 0; base < nr; base += 32) {
+        const int r = base + lane;
+        const bool active = r < nr;
+        RibbonD rb = {0, 0, 0, 0};
+        bool contained = false;
+        double px = 0, py = 0;
+        if (active) {
+            rb = load_ribbon(cur + r);
+            ribbon_projection(rb, x, y, &px, &py);
+            contained = ribbon_contains(rb, x, y, px, py, true, W);
+        }
+        RibbonD piece = {0, 0, 0, 0};
+        RibbonD rest = rb;
+        if (contained) {
+            piece.sx = rb.sx; piece.sy = rb.sy; piece.ex = px; piece.ey = py;
+            rest.sx = px; rest.sy = py;
+        }
+        const bool keep_piece = active && contained && !ribbon_covered(piece, true, W);
+        const bool keep_rest = active && !ribbon_covered(rest, true, W);
+        const int cnt = (keep_piece ? 1 : 0) + (keep_rest ? 1 : 0);
+        const int incl = warp_incl_scan(cnt, lane);
+        int off = out_base + incl - cnt;
+        if (keep_piece) {
+            if (off < cap) alt[off] = pack_ribbon(piece.sx, piece.sy, piece.ex, piece.ey);
+            off++;
+        }
+        if (keep_rest) {
+            if (off < cap) alt[off] = pack_ribbon(rest.sx, rest.sy, rest.ex, rest.ey);
+        }
+        const bool ch = active && (contained ? (keep_piece || !keep_rest || px != rb.sx || py != rb.sy) : !keep_rest);
+        any_change |= __any_sync(kFull, ch);
+        out_base += __shfl_sync(kFull, incl, 31);
+    }
+    __syncwarp();
+    if (out_base > cap) *overflow = true;
+    *changed = any_change;
+    return any_change ? (out_base > cap ? cap : out_base) : nr;
+}
+
+// RibbonManager::maxDistance (RibbonManager.cpp:234-248); `scratch` holds >= nr doubles.
+__device__ __forceinline__ double warp_max_distance(const double4* cur, int nr, double x, double y, double W,
+                                                    int lane, double* scratch) {
+    double mn = DBL_MAX, mx = 0;
+    for (int r = lane; r < nr; r += 32) {
+        const RibbonD rb = load_ribbon(cur + r);
+        scratch[r] = sqrt(ribbon_sqlen(rb)) - 2 * W;
+        const double dStart = point_distance(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart);
+        mx = fmax(fmax(mx, dEnd), dStart);
+    }
+    __syncwarp();
+    double sumLength = 0;
+    for (int r = 0; r < nr; r++) sumLength += scratch[r]; // list order, as the reference sums
+    __syncwarp();
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    return fmax(sumLength + mn, mx);
+}
+
+struct EdgeOut {
+    double true_cost, collision_penalty, approx_cost;
+    double ex, ey, eh, es, et;
+    double g, h, cct;
+    DubinsPathD path;
+    double w_speed, w_start, w_end;
+    long long ribbons_offset;
+    int infeasible, status, n_samples, n_checkpoints, n_ribbons_after, ribbons_changed;
+};
+
+__device__ __forceinline__ void write_result(ppe_edge_result* r, const EdgeOut& o) {
+    r->true_cost = o.true_cost;
+    r->collision_penalty = o.collision_penalty;
+    r->approx_cost = o.approx_cost;
+    r->end[0] = o.ex; r->end[1] = o.ey; r->end[2] = o.eh; r->end[3] = o.es; r->end[4] = o.et;
+    r->g = o.g;
+    r->h = o.h;
+    r->coverage_completed_time = o.cct;
+    r->path_qi[0] = o.path.qi[0]; r->path_qi[1] = o.path.qi[1]; r->path_qi[2] = o.path.qi[2];
+    r->path_param[0] = o.path.param[0]; r->path_param[1] = o.path.param[1]; r->path_param[2] = o.path.param[2];
+    r->path_rho = o.path.rho;
+    r->w_speed = o.w_speed;
+    r->w_start_time = o.w_start;
+    r->w_end_time = o.w_end;
+    r->ribbons_offset = o.ribbons_offset;
+    r->path_type = o.path.type;
+    r->infeasible = o.infeasible;
+    r->status = o.status;
+    r->n_samples = o.n_samples;
+    r->n_checkpoints = o.n_checkpoints;
+    r->n_ribbons_after = o.n_ribbons_after;
+    r->ribbons_changed = o.ribbons_changed;
+    r->reserved = 0;
+}
+
+// One edge, one warp.  All lanes hold identical copies of the per-edge scalars; lane i of a chunk
+// owns sample index base + i.
+__device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge, ppe_edge_result* __restrict__ result,
+                             const ObstacleD* s_obs, double4* bufA, double4* bufB, int lane, double* out_f) {
+    const ppe_config& cfg = w.cfg;
+    const double W = cfg.ribbon_width;
+    const double inc = cfg.collision_checking_increment;
+    const int cap = w.ribbon_cap;
+
+    EdgeOut o;
+    o.true_cost = 0; o.collision_penalty = 0; o.approx_cost = 0;
+    o.ex = o.ey = o.eh = o.es = o.et = 0;
+    o.g = 0; o.h = 0; o.cct = 0;
+    o.path.qi[0] = o.path.qi[1] = o.path.qi[2] = 0;
+    o.path.param[0] = o.path.param[1] = o.path.param[2] = 0;
+    o.path.rho = 0; o.path.type = 0;
+    o.w_speed = o.w_start = o.w_end = 0;
+    o.ribbons_offset = -1;
+    o.infeasible = 0; o.status = PPE_EDGE_OK; o.n_samples = 0; o.n_checkpoints = 0;
+    o.n_ribbons_after = 0; o.ribbons_changed = 0;
+    *out_f = INFINITY;
+
+    const double src_x = edge->src[0], src_y = edge->src[1], src_h = edge->src[2], src_speed = edge->src[3],
+                 src_t = edge->src[4];
+    const double src_g = edge->src_g;
+    const bool has_path = edge->has_path != 0;
+    const bool cov = edge->coverage_allowed != 0;
+    const int set = edge->ribbon_set;
+
+    // v->m_RibbonManager = start->m_RibbonManager (Vertex.cpp:24,32): parent's ribbons -> shared memory
+    int nr = 0;
+    double cct = -1;
+    if (set >= 0 && set < w.n_sets) {
+        nr = w.set_count[set];
+        cct = w.set_cct[set];
+        const double4* src_ribbons = w.ribbons + w.set_offset[set];
+        if (nr > cap) { o.status = PPE_EDGE_ERR_RIBBON_CAPACITY; nr = 0; }
+        for (int r = lane; r < nr; r += 32) bufA[r] = src_ribbons[r];
+    } else {
+        o.status = PPE_EDGE_ERR_RIBBON_CAPACITY;
+    }
+    __syncwarp();
+    if (o.status != PPE_EDGE_OK) {
+        if (lane == 0) write_result(result, o);
+        return;
+    }
+    double4* cur = bufA;
+    double4* alt = bufB;
+    bool modified = false;
+    bool overflow = false;
+
+    // ---- wrapper / path (Edge.cpp:73-85, Edge::setEnd :208-215, DubinsWrapper.cpp:9-17,84-93) ----------
+    DubinsPathD path;
+    path.qi[0] = path.qi[1] = path.qi[2] = 0;
+    path.param[0] = path.param[1] = path.param[2] = 0;
+    path.rho = 0; path.type = 0;
+    PathSampler smp;
+    double w_speed = 0, w_start = -1, w_end = -1;
+    bool w_init = false;
+    double ex, ey, eh, es; // end()->state() pose
+    double approx = -1;
+    bool sample_fault = false; // both dubins_path_sample attempts failed somewhere (stale-pose case)
+
+    if (has_path) {
+        path.qi[0] = edge->path_qi[0]; path.qi[1] = edge->path_qi[1]; path.qi[2] = edge->path_qi[2];
+        path.param[0] = edge->path_param[0]; path.param[1] = edge->path_param[1]; path.param[2] = edge->path_param[2];
+        path.rho = edge->path_rho; path.type = edge->path_type;
+        w_speed = edge->w_speed;
+        w_start = edge->w_start_time;
+        w_init = w_start >= 0;
+        sampler_init(&smp, path);
+        w_end = w_start + smp.length / w_speed;
+        if (edge->w_end_time < w_end) w_end = edge->w_end_time;
+        if (!w_init || !(w_start <= w_end)) {
+            o.status = PPE_EDGE_ERR_END_SAMPLE;
+            if (lane == 0) write_result(result, o);
+            return;
+        }
+        ex = 0; ey = 0; eh = 0;
+        if (!wrapper_sample_pose(smp, w_start, w_speed, w_end, &ex, &ey, &eh)) {
+            eh = heading_to_yaw(eh);
+            sample_fault = true;
+        }
+        es = w_speed;
+        approx = (w_end - src_t) * cfg.time_penalty_factor;
+    } else {
+        ex = edge->dst[0]; ey = edge->dst[1]; eh = edge->dst[2]; es = edge->dst[3];
+    }
+    const double speed = es;
+    const double rho = cov ? cfg.coverage_turning_radius : cfg.turning_radius;
+    if (approx == -1 || path.rho != rho) {
+        if (src_x == ex && src_y == ey && src_h == eh) {
+            approx = 0; // co-located (State::isCoLocated, State.cpp:87-91): wrapper untouched
+        } else {
+            const double q1[3] = {src_x, src_y, heading_to_yaw(src_h)};
+            const double q2[3] = {ex, ey, heading_to_yaw(eh)};
+            dubins_shortest_path(&path, q1, q2, rho); // return code ignored, as DubinsWrapper.cpp:13 does
+            sampler_init(&smp, path);
+            w_speed = src_speed;
+            w_start = src_t;
+            w_init = w_start >= 0;
+            w_end = w_start + smp.length / w_speed;
+            approx = smp.length / speed * cfg.time_penalty_factor;
+        }
+    }
+    if (w_speed != speed) {
+        if (!w_init) { // setSpeed -> setEndTime -> length() throws on an unset wrapper
+            o.status = PPE_EDGE_ERR_NO_PATH;
+            if (lane == 0) write_result(result, o);
+            return;
+        }
+        w_speed = speed;
+        w_end = w_start + smp.length / w_speed;
+    }
+    if (approx < 0) {
+        o.status = PPE_EDGE_ERR_NO_PATH;
+        if (lane == 0) write_result(result, o);
+        return;
+    }
+
+    // ---- the sampling loop (Edge.cpp:86-175) ---------------------------------------------------------------
+    double endTime = fmin(w.horizon_end, w_end);
+    int ribbonsDoneTime = -1;
+    const bool startedDone = (nr == 0);
+    double penalty = 0;
+    bool infeasible = false;
+    if (src_t >= endTime) infeasible = true;
+    const double dt = w.dt;
+    const double t0 = src_t + fmod(src_t - cfg.start_state_time, dt);
+
+    int next_cp = 0;             // sample index of the next ribbon check-point (toCoverDistance starts at 0)
+    double carry_x = src_x, carry_y = src_y, carry_h = src_h; // pose of sample base-1 (`intermediate` before the chunk)
+    double P_x = src_x, P_y = src_y, P_h = src_h, lastHeading = src_h, t_exit = t0;
+    int n_samples = 0, n_cp = 0;
+
+    const double span = (endTime - t0) / dt;
+    const bool loop_ok = (dt > 0) && (span < (double)kMaxSamples || !(t0 < endTime));
+    if (!loop_ok) {
+        o.status = PPE_EDGE_ERR_END_SAMPLE;
+        if (lane == 0) write_result(result, o);
+        return;
+    }
+
+    TimeWalker tw;
+    tw.init(t0, dt);
+
+    for (int base = 0;; base += 32) {
+        const int i = base + lane;
+        const double t_i = tw.at(i);
+        bool valid = t_i < endTime;
+        double x = 0, y = 0, hd = 0;
+        bool in_time = true, sample_ok = true, blocked = false;
+        if (valid) {
+            in_time = (w_start <= t_i) && (w_end >= t_i); // DubinsWrapper::containsTime
+            if (in_time) {
+                sample_ok = wrapper_sample_pose(smp, w_start, w_speed, t_i, &x, &y, &hd);
+                if (sample_ok) blocked = map_blocked(w, x, y);
+            }
+        }
+        const unsigned m_valid = __ballot_sync(kFull, valid);
+        const unsigned m_stop = __ballot_sync(kFull, valid && (!in_time || blocked));
+        if (__any_sync(kFull, valid && in_time && !sample_ok)) sample_fault = true;
+        int nvalid = __popc(m_valid); // valid lanes form a prefix (times increase)
+        const int fstop = m_stop ? (__ffs(m_stop) - 1) : 32;
+        int limit = nvalid < fstop ? nvalid : fstop; // lanes [0, limit) execute the full loop body
+
+        // -- ribbon check-points inside this chunk, in order (Edge.cpp:153-172)
+        while (next_cp < base + limit) {
+            const int l = next_cp - base;
+            const double cx = __shfl_sync(kFull, x, l);
+            const double cy = __shfl_sync(kFull, y, l);
+            const double ch = __shfl_sync(kFull, hd, l);
+            const double ct = __shfl_sync(kFull, t_i, l);
+            const double ph_prev = __shfl_sync(kFull, hd, l > 0 ? l - 1 : 0);
+            const double ph = l > 0 ? ph_prev : carry_h;
+            n_cp++;
+            const double toCover = warp_min_distance_from(cur, nr, cx, cy, W, lane);
+            if (cov || ph == ch) {
+                bool changed = false;
+                const int nn = warp_cover(cur, alt, nr, cap, cx, cy, W, lane, &changed, &overflow);
+                if (changed) {
+                    double4* tmp = cur; cur = alt; alt = tmp;
+                    nr = nn;
+                    modified = true;
+                }
+            }
+            if (nr == 0) {
+                if (cct == -1) cct = ct;
+                ribbonsDoneTime = (int)ct;
+                endTime = fmin(endTime, cct + cfg.time_minimum);
+                valid = t_i < endTime;
+                nvalid = __popc(__ballot_sync(kFull, valid));
+                limit = nvalid < fstop ? nvalid : fstop;
+                if (limit < l + 1) limit = l + 1; // the check-point's own iteration has already run
+            }
+            next_cp = next_cp + 1 + skip_count(toCover, inc, kSkipCap);
+        }
+
+        // -- dynamic-obstacle penalty of the executed iterations (Edge.cpp:150-151), in sample order
+        if (w.obs_kind != kObsNone && w.n_obs > 0) {
+            double p = 0;
+            if (lane < limit) p = collision_exists(w.obs_kind, w.n_obs, s_obs, x, y, t_i) * cfg.collision_penalty_factor;
+            if (__any_sync(kFull, p != 0)) {
+                for (int k = 0; k < limit; k++) penalty += __shfl_sync(kFull, p, k);
+            }
+        }
+
+        n_samples += limit;
+        if (limit < 32) {
+            // the loop ends inside this chunk
+            // the iteration at lane `limit` was entered and broke out only if that lane is still inside
+            // the (possibly truncated) end time
+            const bool stop_lane_valid = __shfl_sync(kFull, (int)valid, limit) != 0;
+            const bool stopped = (fstop == limit) && ((m_stop >> fstop) & 1u) && stop_lane_valid;
+            const int lp = limit > 0 ? limit - 1 : 0;
+            const double px = __shfl_sync(kFull, x, lp), py = __shfl_sync(kFull, y, lp), ph = __shfl_sync(kFull, hd, lp);
+            const double prev_x = limit > 0 ? px : carry_x, prev_y = limit > 0 ? py : carry_y,
+                         prev_h = limit > 0 ? ph : carry_h;
+            const double sx_ = __shfl_sync(kFull, x, limit), sy_ = __shfl_sync(kFull, y, limit),
+                         sh_ = __shfl_sync(kFull, hd, limit);
+            const bool stop_blocked = __shfl_sync(kFull, (int)blocked, limit) != 0;
+            t_exit = __shfl_sync(kFull, t_i, limit);
+            lastHeading = prev_h;
+            if (stopped) {
+                infeasible = true;
+                n_samples += 1; // the breaking iteration was entered
+                if (stop_blocked) { P_x = sx_; P_y = sy_; P_h = sh_; } // `intermediate` holds the blocked sample
+                else { P_x = prev_x; P_y = prev_y; P_h = prev_h; }     // sample() threw before touching it
+            } else {
+                P_x = prev_x; P_y = prev_y; P_h = prev_h;
+            }
+            break;
+        }
+        carry_x = __shfl_sync(kFull, x, 31);
+        carry_y = __shfl_sync(kFull, y, 31);
+        carry_h = __shfl_sync(kFull, hd, 31);
+        if (base > kMaxSamples) { o.status = PPE_EDGE_ERR_END_SAMPLE; break; }
+    }
+
+    // ---- tail (Edge.cpp:176-203) ------------------------------------------------------------------------------
+    o.infeasible = infeasible ? 1 : 0;
+    o.n_samples = n_samples;
+    if (!((w_start <= endTime) && (w_end >= endTime)) || o.status != PPE_EDGE_OK) {
+        // m_DubinsWrapper.sample(end()->state()) throws out of computeTrueCost (DubinsWrapper.cpp:30-35)
+        o.status = PPE_EDGE_ERR_END_SAMPLE;
+        if (lane == 0) write_result(result, o);
+        return;
+    }
+    if (!wrapper_sample_pose(smp, w_start, w_speed, endTime, &ex, &ey, &eh)) {
+        eh = heading_to_yaw(eh);
+        sample_fault = true;
+    }
+    es = w_speed;
+    w_end = endTime; // updateEndTime
+    double t_done = t_exit;
+    if (cov || lastHeading == P_h) {
+        bool changed = false;
+        const int nn = warp_cover(cur, alt, nr, cap, P_x, P_y, W, lane, &changed, &overflow);
+        if (changed) {
+            double4* tmp = cur; cur = alt; alt = tmp;
+            nr = nn;
+            modified = true;
+        }
+    }
+    if (nr == 0) {
+        if (cct == -1) cct = t_done;
+        ribbonsDoneTime = (int)t_done;
+    }
+    const double netTime = endTime - src_t;
+    double T = fmax(netTime - (nr == 0 ? (endTime - (double)ribbonsDoneTime) : 0.0), 0.0);
+    if (startedDone) T = 0;
+    o.collision_penalty = penalty;
+    o.true_cost = T * cfg.time_penalty_factor + penalty;
+    o.approx_cost = approx;
+    o.ex = ex; o.ey = ey; o.eh = eh; o.es = es; o.et = endTime;
+    o.g = src_g + o.true_cost;                                  // Vertex::setCurrentCost
+    if (cfg.heuristic == PPE_H_MAX_DISTANCE) {                  // Vertex::computeApproxToGo
+        const double d = nr == 0 ? 0.0 : warp_max_distance(cur, nr, ex, ey, W, lane, (double*)alt);
+        o.h = d / cfg.max_speed * cfg.time_penalty_factor;
+    } else {
+        o.h = -1;
+    }
+    o.cct = cct;
+    o.path = path;
+    o.w_speed = w_speed; o.w_start = w_start; o.w_end = w_end;
+    o.n_checkpoints = n_cp;
+    o.n_ribbons_after = nr;
+    o.ribbons_changed = modified ? 1 : 0;
+    if (overflow) o.status = PPE_EDGE_ERR_RIBBON_CAPACITY;
+    else if (sample_fault) o.status = PPE_EDGE_ERR_END_SAMPLE;
+
+    // ribbons-after: only edges that changed their parent's set materialise a list
+    if (modified && !overflow) {
+        unsigned long long off = 0;
+        if (lane == 0) off = atomicAdd(w.out_count, (unsigned long long)nr);
+        off = __shfl_sync(kFull, off, 0);
+        if (off + (unsigned long long)nr <= w.out_cap) {
+            for (int r = lane; r < nr; r += 32) w.out_ribbons[off + r] = cur[r];
+            o.ribbons_offset = (long long)off;
+        } else {
+            o.status = PPE_EDGE_ERR_RIBBON_CAPACITY;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) write_result(result, o);
+    if (!infeasible && o.status == PPE_EDGE_OK && o.h >= 0) *out_f = o.g + o.h;
+}
+
+__global__ void __launch_bounds__(kBlockThreads)
+k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edges, ppe_edge_result* __restrict__ results,
+             unsigned long long* work_counter, BestD* block_best) {
+    extern __shared__ double4 smem4[];
+    ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
+    double4* s_rib = smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4));
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double4* bufA = s_rib + (size_t)warp * 2 * w.ribbon_cap;
+    double4* bufB = bufA + w.ribbon_cap;
+
+    {
+        const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
+        double* dst = reinterpret_cast<double*>(s_obs);
+        const double* src = reinterpret_cast<const double*>(w.obstacles);
+        for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    double best_f = INFINITY;
+    long long best_idx = -1;
+    for (;;) {
+        unsigned long long ei = 0;
+        if (lane == 0) ei = atomicAdd(work_counter, 1ULL);
+        ei = __shfl_sync(kFull, ei, 0);
+        if (ei >= (unsigned long long)n) break;
+        double f;
+        process_edge(w, edges + ei, results + ei, s_obs, bufA, bufB, lane, &f);
+        if (f < best_f || (f == best_f && (long long)ei < best_idx)) { best_f = f; best_idx = (long long)ei; }
+        __syncwarp();
+    }
+
+    // K3 epilogue: block-level best (f, edge index); ties go to the smaller index
+    __shared__ double s_f[kWarpsPerBlock];
+    __shared__ long long s_i[kWarpsPerBlock];
+    if (lane == 0) { s_f[warp] = best_f; s_i[warp] = best_idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double bf = INFINITY;
+        long long bi = -1;
+        for (int k = 0; k < kWarpsPerBlock; k++) {
+            if (s_i[k] >= 0 && (s_f[k] < bf || (s_f[k] == bf && s_i[k] < bi) || bi < 0)) { bf = s_f[k]; bi = s_i[k]; }
+        }
+        block_best[blockIdx.x].f = bf;
+        block_best[blockIdx.x].idx = bi;
+    }
+}
+
+__global__ void k3_best_final(const BestD* block_best, int nblocks, BestD* out) {
+    __shared__ double s_f[256];
+    __shared__ long long s_i[256];
+    double bf = INFINITY;
+    long long bi = -1;
+    for (int k = threadIdx.x; k < nblocks; k += blockDim.x) {
+        const BestD b = block_best[k];
+        if (b.idx >= 0 && (bi < 0 || b.f < bf || (b.f == bf && b.idx < bi))) { bf = b.f; bi = b.idx; }
+    }
+    s_f[threadIdx.x] = bf;
+    s_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const double of = s_f[threadIdx.x + s];
+            const long long oi = s_i[threadIdx.x + s];
+            if (oi >= 0 && (s_i[threadIdx.x] < 0 || of < s_f[threadIdx.x] || (of == s_f[threadIdx.x] && oi < s_i[threadIdx.x]))) {
+                s_f[threadIdx.x] = of;
+                s_i[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out->f = s_f[0]; out->idx = s_i[0]; }
+}
+
+// K1: one thread per Dubins solve
+__global__ void __launch_bounds__(128)
+k1_dubins_batch(const long long n, const double* __restrict__ q0, const double* __restrict__ q1,
+                const double* __restrict__ rho, int32_t* __restrict__ type, double* __restrict__ param,
+                double* __restrict__ length, int32_t* __restrict__ err) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a[3] = {q0[3 * i], q0[3 * i + 1], q0[3 * i + 2]};
+    const double b[3] = {q1[3 * i], q1[3 * i + 1], q1[3 * i + 2]};
+    DubinsPathD p;
+    p.param[0] = p.param[1] = p.param[2] = 0;
+    p.type = 0;
+    const int e = dubins_shortest_path(&p, a, b, rho[i]);
+    type[i] = p.type;
+    param[3 * i] = p.param[0];
+    param[3 * i + 1] = p.param[1];
+    param[3 * i + 2] = p.param[2];
+    length[i] = e == kEdubOk ? dubins_path_length(p) : 0.0;
+    err[i] = e;
+}
+
+// FP64 FMA throughput probe: the roofline denominator for K2 (MEASURED_PEAKS.json has no fp64 entry)
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+        a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;
+}
+
+} // namespace
+
+int true_cost_block_threads() { return kBlockThreads; }
+
+size_t true_cost_smem_bytes(int ribbon_cap, int n_obs) {
+    return (size_t)n_obs * sizeof(ObstacleD) + (size_t)kWarpsPerBlock * 2 * (size_t)ribbon_cap * sizeof(double4);
+}
+
+cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type,
+                                double* param, double* length, int32_t* err, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int threads = 128;
+    const long long blocks = (n + threads - 1) / threads;
+    k1_dubins_batch<<<(unsigned)blocks, threads, 0, stream>>>(n, q0, q1, rho, type, param, length, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edge* edges, ppe_edge_result* results,
+                                   unsigned long long* work_counter, BestD* block_best, int max_blocks, BestD* best,
+                                   int sm_count, cudaStream_t stream, int* launches) {
+    const size_t smem = true_cost_smem_bytes(world.ribbon_cap, world.n_obs);
+    static size_t configured = 0;
+    cudaError_t e;
+    if (smem > configured) {
+        e = cudaFuncSetAttribute(k2_true_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_true_cost, kBlockThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    // persistent grid: a multiple of the SM count, never more warps than edges
+    long long blocks = (long long)sm_count * per_sm;
+    const long long needed = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (blocks > needed) blocks = needed;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(world.out_count, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    k2_true_cost<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(world, (long long)n, edges, results, work_counter,
+                                                                   block_best);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k3_best_final<<<1, 256, 0, stream>>>(block_best, (int)blocks, best);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t stream) {
+    k_fp64_peak<<<blocks, 256, 0, stream>>>(out, iters);
+    return cudaGetLastError();
+}
+
+} // namespace ppe

@@ -1,0 +1,68 @@
+// ppe_kernels.cuh -- device-side world description and kernel launch prototypes (internal).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ppe.h"
+
+namespace ppe {
+
+// Dynamic obstacle with the loop invariants hoisted on the host (the reference recomputes
+// cos/sin(Yaw), Width+2, the covariance inverse and the normaliser for every sample point:
+// BinaryDynamicObstaclesManager.cpp:8-20, GaussianDynamicObstaclesManager.h:31-44).
+struct ObstacleD {
+    double X, Y, Time, Speed;
+    double cosYaw, sinYaw;
+    // binary: a = (Length+2)/2, b = (Width+2)/2 (strict inflation, Binary...cpp:9-12,18)
+    // gaussian: a..d = inverse covariance i00, i10, i01, i11; norm = 1/(2 pi)/sqrt(det)
+    double a, b, c, d;
+    double norm;
+    double pad;
+};
+static_assert(sizeof(ObstacleD) == 96, "ObstacleD layout");
+
+enum { kMapNone = 0, kMapBitmap = 1 };
+enum { kObsNone = 0, kObsBinary = 1, kObsGaussian = 2 };
+
+// Read-only world state resident in HBM for the lifetime of a plan.
+struct WorldD {
+    ppe_config cfg;
+    double dt;            // collisionCheckingIncrement / maxSpeed        (Edge.cpp:114)
+    double horizon_end;   // timeHorizon + 1e-12 + startStateTime        (Edge.cpp:90)
+    // static map: rows x stride_words 32-bit words, bit c of row r = blocked[r][c]
+    const uint32_t* map_bits;
+    int map_kind, rows, cols, stride_words;
+    double resolution;
+    // dynamic obstacles
+    const ObstacleD* obstacles;
+    int obs_kind, n_obs;
+    // interned ribbon sets (RibbonManager state of parent vertices)
+    const double4* ribbons;     // pool: sx, sy, ex, ey
+    const int* set_offset;
+    const int* set_count;
+    const double* set_cct;      // coverageCompletedTime
+    int n_sets;
+    int ribbon_cap;             // per-warp working capacity (ribbons)
+    // ribbons-after output pool
+    double4* out_ribbons;
+    unsigned long long* out_count;
+    unsigned long long out_cap;
+};
+
+struct BestD {
+    double f;
+    long long idx;
+};
+
+// launchers (ppe_kernels.cu)
+cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type,
+                                double* param, double* length, int32_t* err, cudaStream_t stream);
+cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edge* edges, ppe_edge_result* results,
+                                   unsigned long long* work_counter, BestD* block_best, int max_blocks, BestD* best,
+                                   int sm_count, cudaStream_t stream, int* launches);
+cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t stream);
+size_t true_cost_smem_bytes(int ribbon_cap, int n_obs);
+int true_cost_block_threads();
+
+} // namespace ppe

@@ -1,0 +1,424 @@
+// ppe_math.cuh -- scalar building blocks of the edge engine, shared by every kernel.
+//
+// Everything here is plain IEEE fp64 arithmetic in the operation order of the reference (the
+// library is compiled with -fmad=false so nothing is contracted into FMAs the x86-64 reference
+// build does not have).  The functions are __host__ __device__ so that the host-side unit tests
+// (tests/host_helpers.cpp, built with g++) can pin the formulas against the oracle bit for bit
+// with glibc's libm; on the device the transcendental calls resolve to CUDA's libdevice.
+//
+// Reference anchors:
+//   dubins_curves (un-vendored; contract in SURVEY.md Appendix B): shortest path of the six words,
+//     path sampling -- called from DubinsWrapper.cpp:13,38-43.
+//   State::yaw / State::setYaw            path_planner_common/include/path_planner_common/State.h:51-65
+//   Edge::computeTrueCost time stepping   path_planner/src/planner/search/Edge.cpp:114-125,173
+//   toCoverDistance skip counter          Edge.cpp:153-154
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define PPE_HD __host__ __device__ __forceinline__
+#define PPE_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define PPE_HD inline
+#define PPE_HD_NOINLINE inline
+#endif
+
+namespace ppe {
+
+constexpr double kPi = 3.14159265358979323846;       // M_PI
+constexpr double kPi2 = 1.57079632679489661923;      // M_PI_2
+constexpr double kTwoPi = 2 * 3.14159265358979323846; // 2 * M_PI (exact doubling)
+
+// ---- bit helpers -----------------------------------------------------------------------------
+PPE_HD int64_t f64_bits(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(x);
+#else
+    int64_t b;
+    memcpy(&b, &x, sizeof b);
+    return b;
+#endif
+}
+PPE_HD double bits_f64(int64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(b);
+#else
+    double x;
+    memcpy(&x, &b, sizeof x);
+    return x;
+#endif
+}
+// unbiased exponent of a positive normal double
+PPE_HD int f64_exponent(double x) { return (int)((f64_bits(x) >> 52) & 0x7ff) - 1023; }
+// 2^e for -1022 <= e <= 1023
+PPE_HD double f64_pow2(int e) { return bits_f64((int64_t)(e + 1023) << 52); }
+
+PPE_HD void sincos_f64(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+
+// dubins.c: fmodr(theta, 2*M_PI)
+PPE_HD double mod2pi(double theta) { return theta - kTwoPi * floor(theta / kTwoPi); }
+
+// State::yaw(), State.h:51-55 (also the inverse map State::setYaw, State.h:62-65: the same formula)
+PPE_HD double heading_to_yaw(double heading) {
+    double h = kPi2 - heading;
+    if (h < 0) h += kTwoPi;
+    return h;
+}
+
+// ---- Dubins shortest path ----------------------------------------------------------------------
+struct DubinsPathD {
+    double qi[3];
+    double param[3];
+    double rho;
+    int type;
+};
+
+enum { kEdubOk = 0, kEdubCoconfigs = 1, kEdubParam = 2, kEdubBadRho = 3, kEdubNoPath = 4 };
+
+// All six words are evaluated unconditionally (no data-dependent branch per word: the feasibility
+// tests become selects), in enum order LSL, LSR, RSL, RSR, RLR, LRL with a strict `<` so ties go
+// to the earliest word.
+PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const double q1[3], double rho) {
+    if (rho <= 0.0) return kEdubBadRho;
+    const double dx = q1[0] - q0[0];
+    const double dy = q1[1] - q0[1];
+    const double D = sqrt(dx * dx + dy * dy);
+    const double d = D / rho;
+    double theta = 0;
+    if (d > 0) theta = mod2pi(atan2(dy, dx));
+    const double alpha = mod2pi(q0[2] - theta);
+    const double beta = mod2pi(q1[2] - theta);
+    double sa, ca, sb, cb;
+    sincos_f64(alpha, &sa, &ca);
+    sincos_f64(beta, &sb, &cb);
+    const double c_ab = cos(alpha - beta);
+    const double d_sq = d * d;
+
+    path->qi[0] = q0[0];
+    path->qi[1] = q0[1];
+    path->qi[2] = q0[2];
+    path->rho = rho;
+
+    double best_cost = INFINITY;
+    int best = -1;
+    double b0 = 0, b1 = 0, b2 = 0;
+
+#define PPE_TAKE(word, ok, t, p, q)                         \
+    {                                                       \
+        const double cost_ = (t) + (p) + (q);               \
+        if ((ok) && cost_ < best_cost) {                    \
+            best_cost = cost_; best = (word);               \
+            b0 = (t); b1 = (p); b2 = (q);                   \
+        }                                                   \
+    }
+
+    { // LSL
+        const double tmp0 = d + sa - sb;
+        const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sa - sb));
+        const double tmp1 = atan2((cb - ca), tmp0);
+        const double t = mod2pi(tmp1 - alpha);
+        const double p = sqrt(p_sq);
+        const double q = mod2pi(beta - tmp1);
+        PPE_TAKE(0, p_sq >= 0, t, p, q)
+    }
+    { // LSR
+        const double p_sq = -2 + (d_sq) + (2 * c_ab) + (2 * d * (sa + sb));
+        const double p = sqrt(p_sq);
+        const double tmp0 = atan2((-ca - cb), (d + sa + sb)) - atan2(-2.0, p);
+        const double t = mod2pi(tmp0 - alpha);
+        const double q = mod2pi(tmp0 - mod2pi(beta));
+        PPE_TAKE(1, p_sq >= 0, t, p, q)
+    }
+    { // RSL
+        const double p_sq = -2 + d_sq + (2 * c_ab) - (2 * d * (sa + sb));
+        const double p = sqrt(p_sq);
+        const double tmp0 = atan2((ca + cb), (d - sa - sb)) - atan2(2.0, p);
+        const double t = mod2pi(alpha - tmp0);
+        const double q = mod2pi(beta - tmp0);
+        PPE_TAKE(2, p_sq >= 0, t, p, q)
+    }
+    { // RSR
+        const double tmp0 = d - sa + sb;
+        const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sb - sa));
+        const double tmp1 = atan2((ca - cb), tmp0);
+        const double t = mod2pi(alpha - tmp1);
+        const double p = sqrt(p_sq);
+        const double q = mod2pi(tmp1 - beta);
+        PPE_TAKE(3, p_sq >= 0, t, p, q)
+    }
+    { // RLR
+        const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sa - sb)) / 8.;
+        const double phi = atan2(ca - cb, d - sa + sb);
+        const double p = mod2pi((2 * kPi) - acos(tmp0));
+        const double t = mod2pi(alpha - phi + mod2pi(p / 2.));
+        const double q = mod2pi(alpha - beta - t + mod2pi(p));
+        PPE_TAKE(4, fabs(tmp0) <= 1, t, p, q)
+    }
+    { // LRL
+        const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sb - sa)) / 8.;
+        const double phi = atan2(ca - cb, d + sa - sb);
+        const double p = mod2pi(2 * kPi - acos(tmp0));
+        const double t = mod2pi(-alpha - phi + p / 2.);
+        const double q = mod2pi(mod2pi(beta) - alpha - t + mod2pi(p));
+        PPE_TAKE(5, fabs(tmp0) <= 1, t, p, q)
+    }
+#undef PPE_TAKE
+    if (best < 0) return kEdubNoPath;
+    path->param[0] = b0;
+    path->param[1] = b1;
+    path->param[2] = b2;
+    path->type = best;
+    return kEdubOk;
+}
+
+PPE_HD double dubins_path_length(const DubinsPathD& p) {
+    double length = 0.;
+    length += p.param[0];
+    length += p.param[1];
+    length += p.param[2];
+    length = length * p.rho;
+    return length;
+}
+
+// ---- path sampler with the per-path loop invariants hoisted ---------------------------------------
+// dubins_path_sample walks all three segments on every call; the end configurations of segment 1
+// and 2 and the sin/cos of the three segment base angles depend on the path only, so they are
+// computed once per edge.  The per-sample remainder is one sincos (arcs) or none (straight).
+enum { kSegL = 0, kSegS = 1, kSegR = 2 };
+
+struct PathSampler {
+    double x0, y0, rho, length;
+    double p1, p12;           // param[0], param[0] + param[1]
+    double p2;                // param[1]
+    double bx[3], by[3], bth[3], bs[3], bc[3]; // base configuration of each segment (+ sin/cos of its angle)
+    int seg[3];
+};
+
+// one dubins_segment step from base configuration k by normalised length t
+PPE_HD void sampler_segment(const PathSampler& s, int k, double t, double* qx, double* qy, double* qth) {
+    const int type = s.seg[k];
+    double x, y, th;
+    if (type == kSegS) {
+        x = s.bc[k] * t;
+        y = s.bs[k] * t;
+        th = 0.0;
+    } else {
+        double sn, cs;
+        if (type == kSegL) {
+            sincos_f64(s.bth[k] + t, &sn, &cs);
+            x = +sn - s.bs[k];
+            y = -cs + s.bc[k];
+            th = t;
+        } else {
+            sincos_f64(s.bth[k] - t, &sn, &cs);
+            x = -sn + s.bs[k];
+            y = +cs - s.bc[k];
+            th = -t;
+        }
+    }
+    *qx = x + s.bx[k];
+    *qy = y + s.by[k];
+    *qth = th + s.bth[k];
+}
+
+PPE_HD void sampler_init(PathSampler* s, const DubinsPathD& p) {
+    // DIRDATA of dubins.c: L S L / L S R / R S L / R S R / R L R / L R L
+    const int t0 = (p.type == 0 || p.type == 1 || p.type == 5) ? kSegL : kSegR;
+    const int t1 = (p.type < 4) ? kSegS : (p.type == 4 ? kSegL : kSegR);
+    const int t2 = (p.type == 0 || p.type == 2 || p.type == 5) ? kSegL : kSegR;
+    s->seg[0] = t0; s->seg[1] = t1; s->seg[2] = t2;
+    s->x0 = p.qi[0]; s->y0 = p.qi[1]; s->rho = p.rho;
+    s->length = dubins_path_length(p);
+    s->p1 = p.param[0];
+    s->p2 = p.param[1];
+    s->p12 = p.param[0] + p.param[1];
+    s->bx[0] = 0.0; s->by[0] = 0.0; s->bth[0] = p.qi[2];
+    sincos_f64(s->bth[0], &s->bs[0], &s->bc[0]);
+    sampler_segment(*s, 0, p.param[0], &s->bx[1], &s->by[1], &s->bth[1]);
+    sincos_f64(s->bth[1], &s->bs[1], &s->bc[1]);
+    sampler_segment(*s, 1, p.param[1], &s->bx[2], &s->by[2], &s->bth[2]);
+    sincos_f64(s->bth[2], &s->bs[2], &s->bc[2]);
+}
+
+// dubins_path_sample(path, t, q): returns kEdubParam (q untouched) when t is outside [0, length]
+PPE_HD int sampler_sample(const PathSampler& s, double t, double* x, double* y, double* yaw) {
+    const double tprime = t / s.rho;
+    if (t < 0 || t > s.length) return kEdubParam;
+    double qx, qy, qth;
+    if (tprime < s.p1) {
+        sampler_segment(s, 0, tprime, &qx, &qy, &qth);
+    } else if (tprime < s.p12) {
+        sampler_segment(s, 1, tprime - s.p1, &qx, &qy, &qth);
+    } else {
+        sampler_segment(s, 2, tprime - s.p1 - s.p2, &qx, &qy, &qth);
+    }
+    *x = qx * s.rho + s.x0;
+    *y = qy * s.rho + s.y0;
+    *yaw = mod2pi(qth);
+    return kEdubOk;
+}
+
+// DubinsWrapper::sample body, DubinsWrapper.cpp:36-48: distance, EDUBPARAM retry at distance-1e-5,
+// yaw -> heading.  Returns false when both library calls fail (the reference then keeps the stale
+// pose; the engine reports that as a per-edge status instead).
+PPE_HD bool wrapper_sample_pose(const PathSampler& s, double w_start, double w_speed, double time, double* x,
+                                double* y, double* heading) {
+    const double distance = (time - w_start) * w_speed;
+    double yaw;
+    int err = sampler_sample(s, distance, x, y, &yaw);
+    if (err == kEdubParam) err = sampler_sample(s, distance - 1e-5, x, y, &yaw);
+    if (err != kEdubOk) return false;
+    double h = kPi2 - yaw;
+    if (h < 0) h += kTwoPi;
+    *heading = h;
+    return true;
+}
+
+// ---- exact replay of `t += dt` (Edge.cpp:173) without the serial dependency -------------------------
+// The sample times are produced by repeated floating-point addition, so t_i != t_0 + i*dt and the
+// sample COUNT depends on the accumulated rounding.  While t stays inside one binade [2^e, 2^(e+1))
+// every t is a multiple of u = ulp = 2^(e-52) and fl(t + dt) = t + D with D = dt rounded to a
+// multiple of u -- a constant, unless dt lies exactly half-way between two multiples (tie: the
+// rounding then depends on the parity of t; those binades are stepped one true addition at a
+// time).  Inside a binade t_i = t_s + (i - s) * D is exact.  A walker therefore hands every lane
+// its own t_i in O(#binades) work; binade crossings are done with one true addition.
+struct TimeWalker {
+    double dt;
+    double base, D;     // current run: t_i = base + (i - i0) * D for i0 <= i < i0 + cnt
+    int i0, cnt;
+    double t_next;      // first time after the current run (true fp addition)
+    int edt;
+
+    PPE_HD void build() {
+        // run starts at (i0, base)
+        const double t = base;
+        int n = 0;
+        D = 0.0;
+        const int64_t bits = f64_bits(t);
+        const int ebits = (int)((bits >> 52) & 0x7ff);
+        if (t > 0 && ebits != 0x7ff && ebits - 1023 > edt && ebits > 60) {
+            const int e = ebits - 1023;
+            const double u = f64_pow2(e - 52);
+            const double kq = floor(dt / u);          // exact: power-of-two scaling
+            const double r = dt - kq * u;             // exact remainder, 0 <= r < u
+            if (r != 0.5 * u) {                       // no tie: rounding is parity independent
+                const double Dd = kq * u + (r > 0.5 * u ? u : 0.0);
+                const double lim = f64_pow2(e + 1) - u; // steps with t_j + D <= lim cannot leave the binade
+                if (Dd > 0 && t + Dd <= lim) {
+                    const int64_t mt = (int64_t)((lim - t) / u);
+                    const int64_t mD = (int64_t)(Dd / u);
+                    int64_t nn = mt / mD;
+                    if (nn > 1000000) nn = 1000000;
+                    n = (int)nn;
+                    D = Dd;
+                }
+            }
+        }
+        cnt = n + 1;
+        t_next = (t + (double)n * D) + dt; // crossing / single step: one true addition
+    }
+
+    PPE_HD void init(double t0, double dt_) {
+        dt = dt_;
+        edt = (dt_ > 0) ? f64_exponent(dt_) : -2000;
+        i0 = 0;
+        base = t0;
+        build();
+    }
+
+    // t_i for non-decreasing i
+    PPE_HD double at(int i) {
+        while (i >= i0 + cnt) {
+            i0 += cnt;
+            base = t_next;
+            build();
+        }
+        return base + (double)(i - i0) * D;
+    }
+};
+
+// ---- exact replay of the toCoverDistance skip counter (Edge.cpp:153-154) ----------------------------
+// Number of loop iterations that take the `toCover > inc ? toCover -= inc` branch after a
+// check-point that set toCover = x, i.e. the count of successive fp subtractions until the value
+// is <= c.  Same binade argument as TimeWalker, walking downwards; capped at kmax.
+PPE_HD int skip_count(double x, double c, int kmax) {
+    int k = 0;
+    if (!(c > 0)) return (x > c) ? kmax : 0;
+    const int ec = f64_exponent(c);
+    while (x > c && k < kmax) {
+        const int64_t bits = f64_bits(x);
+        const int ebits = (int)((bits >> 52) & 0x7ff);
+        if (ebits == 0x7ff) return kmax; // inf / nan distance: never reaches the next check-point
+        const int e = ebits - 1023;
+        if (e >= ec + 1 && ebits > 60) {
+            const double u = f64_pow2(e - 52);
+            const double kq = floor(c / u);
+            const double r = c - kq * u;
+            if (r != 0.5 * u) {
+                const double D = kq * u + (r > 0.5 * u ? u : 0.0);
+                const double lo = f64_pow2(e) + u; // results >= lo stay in the binade (and > c)
+                if (D > 0 && x - D >= lo) {
+                    const int64_t mx = (int64_t)((x - lo) / u);
+                    const int64_t mD = (int64_t)(D / u);
+                    int64_t n = mx / mD;
+                    if (n > (int64_t)(kmax - k)) n = kmax - k;
+                    x = x - (double)n * D;
+                    k += (int)n;
+                    continue;
+                }
+            }
+        }
+        x = x - c; // one true subtraction
+        k++;
+    }
+    return k;
+}
+
+// ---- Ribbon primitives (Ribbon.h / Ribbon.cpp) -------------------------------------------------------
+struct RibbonD {
+    double sx, sy, ex, ey;
+};
+
+PPE_HD double ribbon_sqlen(const RibbonD& r) { // Ribbon.h:134-136
+    return (r.ex - r.sx) * (r.ex - r.sx) + (r.ey - r.sy) * (r.ey - r.sy);
+}
+PPE_HD bool ribbon_covered(const RibbonD& r, bool strict, double W) { // Ribbon.cpp:23-25, :52-58
+    const double minLength = 2 * W;
+    return ribbon_sqlen(r) < minLength * minLength / (strict ? 2.0 * 2.0 : 1.0);
+}
+PPE_HD void ribbon_projection(const RibbonD& r, double x, double y, double* px, double* py) { // Ribbon.cpp:72-78
+    const double squaredL = ribbon_sqlen(r);
+    const double dot = (x - r.sx) * (r.ex - r.sx) + (y - r.sy) * (r.ey - r.sy);
+    const double projectedX = (r.ex - r.sx) * dot / squaredL;
+    const double projectedY = (r.ey - r.sy) * dot / squaredL;
+    *px = projectedX + r.sx;
+    *py = projectedY + r.sy;
+}
+PPE_HD bool ribbon_contains_projection(const RibbonD& r, double px, double py) { // Ribbon.cpp:90-95
+    const double tol = 1e-5;
+    return !(((px - r.sx < -tol && px - r.ex < -tol) || (px - r.sx > tol && px - r.ex > tol)) ||
+             ((py - r.sy < -tol && py - r.ey < -tol) || (py - r.sy > tol && py - r.ey > tol)));
+}
+PPE_HD double ribbon_distance(const RibbonD& r, double x, double y) { // Ribbon.h:118-121
+    return (fabs((r.ey - r.sy) * x - (r.ex - r.sx) * y + r.ex * r.sy - r.ey * r.sx)) / sqrt(ribbon_sqlen(r));
+}
+PPE_HD bool ribbon_contains(const RibbonD& r, double x, double y, double px, double py, bool strict, double W) { // Ribbon.cpp:39-43
+    if (!ribbon_contains_projection(r, px, py)) return false;
+    const double d = ribbon_distance(r, x, y);
+    return d < (strict ? W / 2.0 : W);
+}
+PPE_HD double point_distance(double x1, double y1, double x2, double y2) { // RibbonManager.h:289-291
+    return sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2));
+}
+
+} // namespace ppe

@@ -1,0 +1,57 @@
+// tests/host_helpers.cpp -- host build (g++, glibc libm) of the engine's scalar building blocks
+// in path_planner_b200/csrc/ppe_math.cuh, so the CPU test-suite can pin the formulas (operation
+// order, exact time stepping, skip counter, hoisted path sampler) bit for bit against the oracle.
+#include <stdint.h>
+
+#include "ppe_math.cuh"
+
+using namespace ppe;
+
+extern "C" {
+
+void hh_dubins_batch(int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type, double* param,
+                     double* length, int32_t* err) {
+    for (int64_t i = 0; i < n; i++) {
+        DubinsPathD p;
+        p.param[0] = p.param[1] = p.param[2] = 0;
+        p.type = 0;
+        const int e = dubins_shortest_path(&p, q0 + 3 * i, q1 + 3 * i, rho[i]);
+        type[i] = p.type;
+        param[3 * i] = p.param[0]; param[3 * i + 1] = p.param[1]; param[3 * i + 2] = p.param[2];
+        length[i] = e == kEdubOk ? dubins_path_length(p) : 0.0;
+        err[i] = e;
+    }
+}
+
+// t_i for i = 0..n-1 through the binade walker
+void hh_time_walk(double t0, double dt, int n, double* out) {
+    TimeWalker tw;
+    tw.init(t0, dt);
+    for (int i = 0; i < n; i++) out[i] = tw.at(i);
+}
+
+// same, but strided like the lanes of a warp (lane l asks for l, l+32, ...)
+void hh_time_walk_lane(double t0, double dt, int lane, int n, double* out) {
+    TimeWalker tw;
+    tw.init(t0, dt);
+    for (int i = lane, k = 0; k < n; i += 32, k++) out[k] = tw.at(i);
+}
+
+int hh_skip_count(double x, double c, int kmax) { return skip_count(x, c, kmax); }
+
+// DubinsWrapper::sample through the hoisted sampler: path = qi[3] param[3] rho type
+void hh_sample(const double* qi, const double* param, double rho, int type, double w_start, double w_speed, int n,
+               const double* times, double* x, double* y, double* heading, int32_t* ok) {
+    DubinsPathD p;
+    p.qi[0] = qi[0]; p.qi[1] = qi[1]; p.qi[2] = qi[2];
+    p.param[0] = param[0]; p.param[1] = param[1]; p.param[2] = param[2];
+    p.rho = rho; p.type = type;
+    PathSampler s;
+    sampler_init(&s, p);
+    for (int i = 0; i < n; i++) {
+        x[i] = y[i] = heading[i] = 0;
+        ok[i] = wrapper_sample_pose(s, w_start, w_speed, times[i], &x[i], &y[i], &heading[i]) ? 1 : 0;
+    }
+}
+
+} // extern "C"

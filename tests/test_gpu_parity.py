@@ -1,0 +1,125 @@
+"""GPU parity: the CUDA engine (through the C ABI, host buffers) against the CPU oracle on the
+same seeded inputs.  Bit-exact for word choice, flags, sample / check-point counts and ribbon
+counts; 1e-9 relative for costs, end states and ribbon coordinates (BASELINE.json north_star)."""
+import math
+
+import numpy as np
+import pytest
+
+from path_planner_b200 import EdgeEngine, abi, synth
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    return EdgeEngine(0)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return common.load_oracle()
+
+
+def _check_batch(engine, oracle, world, edges, ribbon_lists=200):
+    sid_o = world.upload(oracle)
+    sid_e = world.upload(engine)
+    assert sid_o == sid_e
+    edges["ribbon_set"] = sid_e
+    want = oracle.true_cost_batch(edges)
+    got = engine.true_cost_batch(edges)
+    bad = common.diff_results(got, want)
+    assert not bad, common.describe(bad, got, want)
+    changed = np.flatnonzero(want["ribbons_changed"])
+    for i in changed[:ribbon_lists]:
+        a = engine.ribbons_after(i)
+        b = oracle.ribbons_after(i)
+        assert a.shape == b.shape, (i, a.shape, b.shape)
+        assert np.allclose(a, b, rtol=common.RTOL, atol=common.ATOL), (i, a, b)
+    # unchanged edges hand back the parent's set
+    unchanged = np.flatnonzero(want["ribbons_changed"] == 0)
+    for i in unchanged[:5]:
+        assert np.array_equal(engine.ribbons_after(i), oracle.ribbons_after(i))
+    # K3: best feasible f
+    f, idx = engine.best()
+    ok = (want["infeasible"] == 0) & (want["status"] == 0)
+    if ok.any():
+        fo = (got["g"] + got["h"])[ok]
+        assert idx >= 0 and ok[idx]
+        assert f == fo.min()
+        assert idx == np.flatnonzero(ok)[np.argmin(fo)]
+    else:
+        assert idx == -1 and math.isinf(f)
+    return got, want
+
+
+@pytest.mark.parametrize("name,near,n", [("c1", 0.5, 3000), ("c2", 0.0, 4000), ("c2", 0.6, 4000),
+                                          ("c3", 0.3, 1000), ("c3b", 0.3, 1500), ("c4", 0.5, 2000), ("c5", 0.2, 600)])
+def test_true_cost_matches_oracle(engine, oracle, name, near, n):
+    world = synth.WORLDS[name]()
+    edges = synth.make_edges(world, n, seed=11, near_ribbons=near)
+    got, want = _check_batch(engine, oracle, world, edges)
+    assert (want["status"] == 0).all()
+
+
+def test_has_path_edges_match_oracle(engine, oracle):
+    """Winner edges of expand(): pre-solved wrapper + speed change (SamplingBasedPlanner.cpp:134-149)."""
+    world = synth.world_c2()
+    edges = synth.make_edges(world, 3000, seed=3, near_ribbons=0.4)
+    cfg = world.cfg
+    q0 = np.column_stack([edges["src"][:, 0], edges["src"][:, 1], _yaw(edges["src"][:, 2])])
+    q1 = np.column_stack([edges["dst"][:, 0], edges["dst"][:, 1], _yaw(edges["dst"][:, 2])])
+    rho = np.where(edges["coverage_allowed"] == 1, cfg.coverage_turning_radius, cfg.turning_radius)
+    world.upload(engine)
+    typ, par, length, err = engine.dubins_batch(q0, q1, rho)
+    assert (err == 0).all()
+    edges["has_path"] = 1
+    edges["path_qi"] = q0
+    edges["path_param"] = par
+    edges["path_rho"] = rho
+    edges["path_type"] = typ
+    edges["w_speed"] = edges["dst"][:, 3]
+    edges["w_start_time"] = edges["src"][:, 4]
+    edges["w_end_time"] = edges["src"][:, 4] + length / edges["dst"][:, 3]
+    _check_batch(engine, oracle, world, edges)
+
+
+def _yaw(h):
+    y = math.pi / 2 - h
+    return np.where(y < 0, y + 2 * math.pi, y)
+
+
+def test_dubins_batch_matches_oracle(engine, oracle):
+    n = 1 << 20
+    rng = np.random.default_rng(0)
+    q0 = np.column_stack([rng.uniform(-100, 100, n), rng.uniform(-100, 100, n), rng.uniform(0, 2 * math.pi, n)])
+    q1 = np.column_stack([q0[:, 0] + rng.uniform(-75, 75, n), q0[:, 1] + rng.uniform(-75, 75, n), rng.uniform(0, 2 * math.pi, n)])
+    q1[: n // 4, 0] = q0[: n // 4, 0] + rng.uniform(-10, 10, n // 4)
+    q1[: n // 4, 1] = q0[: n // 4, 1] + rng.uniform(-10, 10, n // 4)
+    rho = np.where(np.arange(n) % 2 == 0, 8.0, 16.0)
+    engine.set_config(abi.PpeConfig())
+    oracle.set_config(abi.PpeConfig())
+    gt, gp, gl, ge = engine.dubins_batch(q0, q1, rho)
+    wt, wp, wl, we = oracle.dubins_batch(q0, q1, rho)
+    assert np.array_equal(ge, we)
+    mism = np.flatnonzero(gt != wt)
+    assert mism.size == 0, "word mismatches: %s" % mism[:10]
+    assert np.allclose(gp, wp, rtol=1e-9, atol=1e-9)
+    assert np.allclose(gl, wl, rtol=1e-9, atol=1e-9)
+    assert np.bincount(gt, minlength=6).min() > 1000  # every word exercised
+
+
+def test_degenerate_dubins(engine, oracle):
+    """Co-located, collinear, d ~ 0 and tie cases: straight lines tie LSL/RSR/LSR/RSL -> LSL wins."""
+    q0 = [[0, 0, math.pi / 2], [0, 0, 0], [0, 0, 0], [5, 5, 1.0], [0, 0, math.pi / 2], [0, 0, 0.0], [0, 0, 0.0]]
+    q1 = [[0, 5, math.pi / 2], [25, 0, 0], [0, 0, 0], [5, 5, 2.0], [0, 16, 3 * math.pi / 2], [0, 1e-9, 0.0], [-10, 0, 0.0]]
+    rho = [8, 8, 8, 8, 8, 8, 8]
+    engine.set_config(abi.PpeConfig())
+    oracle.set_config(abi.PpeConfig())
+    gt, gp, gl, ge = engine.dubins_batch(q0, q1, rho)
+    wt, wp, wl, we = oracle.dubins_batch(q0, q1, rho)
+    assert np.array_equal(gt, wt) and np.array_equal(ge, we)
+    assert np.allclose(gp, wp, rtol=1e-9, atol=1e-12)
+    assert gt[0] == abi.LSL and gt[1] == abi.LSL
+    assert gl[0] == 5 and gl[1] == 25

@@ -641,3 +641,79 @@ int oracle_max_threads(void) {
     int n = (int)sysconf(_SC_NPROCESSORS_ONLN);
     return n < 1 ? 1 : n;
 }
+
+/* ------------------------------------------------------------------------------------------- */
+/* Direct access to the restated primitives, for the transcribed reference unit tests            */
+/* (tests/test_golden_reference.py) and the host-side pinning of the engine's scalar helpers.    */
+/* ------------------------------------------------------------------------------------------- */
+
+/* RibbonManager::approximateDistanceUntilDone with MaxDistance (RibbonManager.cpp:28-36,234-248) */
+double oracle_max_distance(oracle_ctx* c, int set, double x, double y) {
+    const ribset_t* s = &c->sets[set];
+    if (s->n == 0) return 0;
+    return ribs_max_distance(s->r, s->n, x, y, c->cfg.ribbon_width);
+}
+
+/* RibbonManager::minDistanceFrom (RibbonManager.cpp:142-152) */
+double oracle_min_distance_from(oracle_ctx* c, int set, double x, double y) {
+    const ribset_t* s = &c->sets[set];
+    return ribs_min_distance_from(s->r, s->n, x, y, c->cfg.ribbon_width);
+}
+
+/* RibbonManager::cover applied to a stored set (in place).  Returns the new ribbon count. */
+int oracle_cover(oracle_ctx* c, int set, double x, double y, int strict) {
+    ribset_t* s = &c->sets[set];
+    rib_t* tmp = (rib_t*)malloc(RIB_CAP * sizeof(rib_t));
+    int n = s->n;
+    memcpy(tmp, s->r, (size_t)n * sizeof(rib_t));
+    if (ribs_cover(tmp, &n, RIB_CAP, x, y, strict, c->cfg.ribbon_width)) { free(tmp); return -1; }
+    free(s->r);
+    s->r = (rib_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(rib_t));
+    memcpy(s->r, tmp, (size_t)n * sizeof(rib_t));
+    s->n = n;
+    free(tmp);
+    return n;
+}
+
+int oracle_get_ribbon_set(oracle_ctx* c, int set, double* xyxy, int cap) {
+    const ribset_t* s = &c->sets[set];
+    int k;
+    for (k = 0; k < s->n && k < cap; k++) memcpy(xyxy + 4 * k, &s->r[k], sizeof(rib_t));
+    return s->n;
+}
+
+/* Ribbon::split on a free-standing ribbon (Ribbon.cpp:9-17): rib = sx sy ex ey (updated in place),
+ * piece receives the split-off part. */
+void oracle_ribbon_split(oracle_ctx* c, double* rib, double x, double y, int strict, double* piece) {
+    rib_t r, p;
+    memcpy(&r, rib, sizeof r);
+    p = rib_split(&r, x, y, strict, c->cfg.ribbon_width);
+    memcpy(rib, &r, sizeof r);
+    memcpy(piece, &p, sizeof p);
+}
+
+double oracle_collision_exists(oracle_ctx* c, double x, double y, double t, int strict) {
+    return collision_exists(c, x, y, t, strict);
+}
+
+int oracle_is_blocked(oracle_ctx* c, double x, double y) { return map_blocked(c, x, y); }
+
+/* DubinsWrapper::sample for a filled wrapper (DubinsWrapper.cpp:29-49,84-93); ok[i] = 0 where the
+ * reference throws. */
+void oracle_wrapper_sample(const double* qi, const double* param, double rho, int type, double w_start,
+                           double w_speed, int n, const double* times, double* x, double* y, double* heading,
+                           int32_t* ok) {
+    wrapper_t w;
+    int i;
+    wrapper_init(&w);
+    w.path.qi[0] = qi[0]; w.path.qi[1] = qi[1]; w.path.qi[2] = qi[2];
+    w.path.param[0] = param[0]; w.path.param[1] = param[1]; w.path.param[2] = param[2];
+    w.path.rho = rho; w.path.type = (DubinsPathType)type;
+    w.speed = w_speed; w.start = w.ustart = w_start;
+    w.end = w.start + dubins_path_length(&w.path) / w.speed;
+    for (i = 0; i < n; i++) {
+        double pose[4] = {0, 0, 0, 0};
+        ok[i] = wrapper_sample(&w, pose, times[i]) ? 0 : 1;
+        x[i] = pose[0]; y[i] = pose[1]; heading[i] = pose[2];
+    }
+}

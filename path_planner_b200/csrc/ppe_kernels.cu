@@ -312,7 +312,7 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
             return;
         }
         ex = 0; ey = 0; eh = 0;
-        if (!wrapper_sample_pose(smp, w_start, w_speed, w_end, &ex, &ey, &eh)) {
+        if (!wrapper_sample_pose<true>(smp, w_start, w_speed, w_end, &ex, &ey, &eh)) {
             eh = heading_to_yaw(eh);
             sample_fault = true;
         }
@@ -388,7 +388,7 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
         if (valid) {
             in_time = (w_start <= t_i) && (w_end >= t_i); // DubinsWrapper::containsTime
             if (in_time) {
-                sample_ok = wrapper_sample_pose(smp, w_start, w_speed, t_i, &x, &y, &hd);
+                sample_ok = wrapper_sample_pose<false>(smp, w_start, w_speed, t_i, &x, &y, &hd);
                 if (sample_ok) blocked = map_blocked(w, x, y);
             }
         }
@@ -481,7 +481,7 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
         if (lane == 0) write_result(result, o);
         return;
     }
-    if (!wrapper_sample_pose(smp, w_start, w_speed, endTime, &ex, &ey, &eh)) {
+    if (!wrapper_sample_pose<true>(smp, w_start, w_speed, endTime, &ex, &ey, &eh)) {
         eh = heading_to_yaw(eh);
         sample_fault = true;
     }

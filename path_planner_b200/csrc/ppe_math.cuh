@@ -14,66 +14,10 @@
 //   toCoverDistance skip counter          Edge.cpp:153-154
 #pragma once
 
-#include <math.h>
-#include <stdint.h>
-#include <string.h>
-
-#if defined(__CUDACC__)
-#define PPE_HD __host__ __device__ __forceinline__
-#define PPE_HD_NOINLINE __host__ __device__ __noinline__
-#else
-#define PPE_HD inline
-#define PPE_HD_NOINLINE inline
-#endif
+#include "ppe_math_base.cuh"
+#include "ppe_crmath.cuh"
 
 namespace ppe {
-
-constexpr double kPi = 3.14159265358979323846;       // M_PI
-constexpr double kPi2 = 1.57079632679489661923;      // M_PI_2
-constexpr double kTwoPi = 2 * 3.14159265358979323846; // 2 * M_PI (exact doubling)
-
-// ---- bit helpers -----------------------------------------------------------------------------
-PPE_HD int64_t f64_bits(double x) {
-#if defined(__CUDA_ARCH__)
-    return __double_as_longlong(x);
-#else
-    int64_t b;
-    memcpy(&b, &x, sizeof b);
-    return b;
-#endif
-}
-PPE_HD double bits_f64(int64_t b) {
-#if defined(__CUDA_ARCH__)
-    return __longlong_as_double(b);
-#else
-    double x;
-    memcpy(&x, &b, sizeof x);
-    return x;
-#endif
-}
-// unbiased exponent of a positive normal double
-PPE_HD int f64_exponent(double x) { return (int)((f64_bits(x) >> 52) & 0x7ff) - 1023; }
-// 2^e for -1022 <= e <= 1023
-PPE_HD double f64_pow2(int e) { return bits_f64((int64_t)(e + 1023) << 52); }
-
-PPE_HD void sincos_f64(double x, double* s, double* c) {
-#if defined(__CUDA_ARCH__)
-    sincos(x, s, c);
-#else
-    *s = sin(x);
-    *c = cos(x);
-#endif
-}
-
-// dubins.c: fmodr(theta, 2*M_PI)
-PPE_HD double mod2pi(double theta) { return theta - kTwoPi * floor(theta / kTwoPi); }
-
-// State::yaw(), State.h:51-55 (also the inverse map State::setYaw, State.h:62-65: the same formula)
-PPE_HD double heading_to_yaw(double heading) {
-    double h = kPi2 - heading;
-    if (h < 0) h += kTwoPi;
-    return h;
-}
 
 // ---- Dubins shortest path ----------------------------------------------------------------------
 struct DubinsPathD {
@@ -85,6 +29,8 @@ struct DubinsPathD {
 
 enum { kEdubOk = 0, kEdubCoconfigs = 1, kEdubParam = 2, kEdubBadRho = 3, kEdubNoPath = 4 };
 
+// Transcendentals go through ppe_crmath.cuh (correctly rounded w.h.p.) so that word choice and the
+// segment parameters agree with the glibc-based reference to the last bit.
 // All six words are evaluated unconditionally (no data-dependent branch per word: the feasibility
 // tests become selects), in enum order LSL, LSR, RSL, RSR, RLR, LRL with a strict `<` so ties go
 // to the earliest word.
@@ -95,13 +41,13 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     const double D = sqrt(dx * dx + dy * dy);
     const double d = D / rho;
     double theta = 0;
-    if (d > 0) theta = mod2pi(atan2(dy, dx));
+    if (d > 0) theta = mod2pi(cr_atan2(dy, dx));
     const double alpha = mod2pi(q0[2] - theta);
     const double beta = mod2pi(q1[2] - theta);
     double sa, ca, sb, cb;
-    sincos_f64(alpha, &sa, &ca);
-    sincos_f64(beta, &sb, &cb);
-    const double c_ab = cos(alpha - beta);
+    cr_sincos(alpha, &sa, &ca);
+    cr_sincos(beta, &sb, &cb);
+    const double c_ab = cr_cos(alpha - beta);
     const double d_sq = d * d;
 
     path->qi[0] = q0[0];
@@ -125,7 +71,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     { // LSL
         const double tmp0 = d + sa - sb;
         const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sa - sb));
-        const double tmp1 = atan2((cb - ca), tmp0);
+        const double tmp1 = cr_atan2((cb - ca), tmp0);
         const double t = mod2pi(tmp1 - alpha);
         const double p = sqrt(p_sq);
         const double q = mod2pi(beta - tmp1);
@@ -134,7 +80,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     { // LSR
         const double p_sq = -2 + (d_sq) + (2 * c_ab) + (2 * d * (sa + sb));
         const double p = sqrt(p_sq);
-        const double tmp0 = atan2((-ca - cb), (d + sa + sb)) - atan2(-2.0, p);
+        const double tmp0 = cr_atan2((-ca - cb), (d + sa + sb)) - cr_atan2(-2.0, p);
         const double t = mod2pi(tmp0 - alpha);
         const double q = mod2pi(tmp0 - mod2pi(beta));
         PPE_TAKE(1, p_sq >= 0, t, p, q)
@@ -142,7 +88,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     { // RSL
         const double p_sq = -2 + d_sq + (2 * c_ab) - (2 * d * (sa + sb));
         const double p = sqrt(p_sq);
-        const double tmp0 = atan2((ca + cb), (d - sa - sb)) - atan2(2.0, p);
+        const double tmp0 = cr_atan2((ca + cb), (d - sa - sb)) - cr_atan2(2.0, p);
         const double t = mod2pi(alpha - tmp0);
         const double q = mod2pi(beta - tmp0);
         PPE_TAKE(2, p_sq >= 0, t, p, q)
@@ -150,7 +96,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     { // RSR
         const double tmp0 = d - sa + sb;
         const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sb - sa));
-        const double tmp1 = atan2((ca - cb), tmp0);
+        const double tmp1 = cr_atan2((ca - cb), tmp0);
         const double t = mod2pi(alpha - tmp1);
         const double p = sqrt(p_sq);
         const double q = mod2pi(tmp1 - beta);
@@ -158,16 +104,16 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     }
     { // RLR
         const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sa - sb)) / 8.;
-        const double phi = atan2(ca - cb, d - sa + sb);
-        const double p = mod2pi((2 * kPi) - acos(tmp0));
+        const double phi = cr_atan2(ca - cb, d - sa + sb);
+        const double p = mod2pi((2 * kPi) - cr_acos(tmp0));
         const double t = mod2pi(alpha - phi + mod2pi(p / 2.));
         const double q = mod2pi(alpha - beta - t + mod2pi(p));
         PPE_TAKE(4, fabs(tmp0) <= 1, t, p, q)
     }
     { // LRL
         const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sb - sa)) / 8.;
-        const double phi = atan2(ca - cb, d + sa - sb);
-        const double p = mod2pi(2 * kPi - acos(tmp0));
+        const double phi = cr_atan2(ca - cb, d + sa - sb);
+        const double p = mod2pi(2 * kPi - cr_acos(tmp0));
         const double t = mod2pi(-alpha - phi + p / 2.);
         const double q = mod2pi(mod2pi(beta) - alpha - t + mod2pi(p));
         PPE_TAKE(5, fabs(tmp0) <= 1, t, p, q)
@@ -205,6 +151,7 @@ struct PathSampler {
 };
 
 // one dubins_segment step from base configuration k by normalised length t
+template <bool kExact>
 PPE_HD void sampler_segment(const PathSampler& s, int k, double t, double* qx, double* qy, double* qth) {
     const int type = s.seg[k];
     double x, y, th;
@@ -215,12 +162,12 @@ PPE_HD void sampler_segment(const PathSampler& s, int k, double t, double* qx, d
     } else {
         double sn, cs;
         if (type == kSegL) {
-            sincos_f64(s.bth[k] + t, &sn, &cs);
+            if (kExact) cr_sincos(s.bth[k] + t, &sn, &cs); else sincos_f64(s.bth[k] + t, &sn, &cs);
             x = +sn - s.bs[k];
             y = -cs + s.bc[k];
             th = t;
         } else {
-            sincos_f64(s.bth[k] - t, &sn, &cs);
+            if (kExact) cr_sincos(s.bth[k] - t, &sn, &cs); else sincos_f64(s.bth[k] - t, &sn, &cs);
             x = -sn + s.bs[k];
             y = +cs - s.bc[k];
             th = -t;
@@ -243,24 +190,25 @@ PPE_HD void sampler_init(PathSampler* s, const DubinsPathD& p) {
     s->p2 = p.param[1];
     s->p12 = p.param[0] + p.param[1];
     s->bx[0] = 0.0; s->by[0] = 0.0; s->bth[0] = p.qi[2];
-    sincos_f64(s->bth[0], &s->bs[0], &s->bc[0]);
-    sampler_segment(*s, 0, p.param[0], &s->bx[1], &s->by[1], &s->bth[1]);
-    sincos_f64(s->bth[1], &s->bs[1], &s->bc[1]);
-    sampler_segment(*s, 1, p.param[1], &s->bx[2], &s->by[2], &s->bth[2]);
-    sincos_f64(s->bth[2], &s->bs[2], &s->bc[2]);
+    cr_sincos(s->bth[0], &s->bs[0], &s->bc[0]);
+    sampler_segment<true>(*s, 0, p.param[0], &s->bx[1], &s->by[1], &s->bth[1]);
+    cr_sincos(s->bth[1], &s->bs[1], &s->bc[1]);
+    sampler_segment<true>(*s, 1, p.param[1], &s->bx[2], &s->by[2], &s->bth[2]);
+    cr_sincos(s->bth[2], &s->bs[2], &s->bc[2]);
 }
 
 // dubins_path_sample(path, t, q): returns kEdubParam (q untouched) when t is outside [0, length]
+template <bool kExact>
 PPE_HD int sampler_sample(const PathSampler& s, double t, double* x, double* y, double* yaw) {
     const double tprime = t / s.rho;
     if (t < 0 || t > s.length) return kEdubParam;
     double qx, qy, qth;
     if (tprime < s.p1) {
-        sampler_segment(s, 0, tprime, &qx, &qy, &qth);
+        sampler_segment<kExact>(s, 0, tprime, &qx, &qy, &qth);
     } else if (tprime < s.p12) {
-        sampler_segment(s, 1, tprime - s.p1, &qx, &qy, &qth);
+        sampler_segment<kExact>(s, 1, tprime - s.p1, &qx, &qy, &qth);
     } else {
-        sampler_segment(s, 2, tprime - s.p1 - s.p2, &qx, &qy, &qth);
+        sampler_segment<kExact>(s, 2, tprime - s.p1 - s.p2, &qx, &qy, &qth);
     }
     *x = qx * s.rho + s.x0;
     *y = qy * s.rho + s.y0;
@@ -271,12 +219,15 @@ PPE_HD int sampler_sample(const PathSampler& s, double t, double* x, double* y, 
 // DubinsWrapper::sample body, DubinsWrapper.cpp:36-48: distance, EDUBPARAM retry at distance-1e-5,
 // yaw -> heading.  Returns false when both library calls fail (the reference then keeps the stale
 // pose; the engine reports that as a per-edge status instead).
+// kExact = true: per-edge samples (end state) with the correctly rounded sincos; false: the
+// per-sample hot loop with libdevice's fast sincos.
+template <bool kExact>
 PPE_HD bool wrapper_sample_pose(const PathSampler& s, double w_start, double w_speed, double time, double* x,
                                 double* y, double* heading) {
     const double distance = (time - w_start) * w_speed;
     double yaw;
-    int err = sampler_sample(s, distance, x, y, &yaw);
-    if (err == kEdubParam) err = sampler_sample(s, distance - 1e-5, x, y, &yaw);
+    int err = sampler_sample<kExact>(s, distance, x, y, &yaw);
+    if (err == kEdubParam) err = sampler_sample<kExact>(s, distance - 1e-5, x, y, &yaw);
     if (err != kEdubOk) return false;
     double h = kPi2 - yaw;
     if (h < 0) h += kTwoPi;

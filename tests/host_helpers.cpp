@@ -50,8 +50,30 @@ void hh_sample(const double* qi, const double* param, double rho, int type, doub
     sampler_init(&s, p);
     for (int i = 0; i < n; i++) {
         x[i] = y[i] = heading[i] = 0;
-        ok[i] = wrapper_sample_pose(s, w_start, w_speed, times[i], &x[i], &y[i], &heading[i]) ? 1 : 0;
+        ok[i] = wrapper_sample_pose<true>(s, w_start, w_speed, times[i], &x[i], &y[i], &heading[i]) ? 1 : 0;
     }
+}
+
+// correctly-rounded helpers of ppe_crmath.cuh
+void hh_cr_sincos(int64_t n, const double* x, double* s, double* c) {
+    for (int64_t i = 0; i < n; i++) cr_sincos(x[i], &s[i], &c[i]);
+}
+void hh_cr_atan2(int64_t n, const double* y, const double* x, double* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = cr_atan2(y[i], x[i]);
+}
+void hh_cr_acos(int64_t n, const double* x, double* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = cr_acos(x[i]);
+}
+
+// the platform libm (glibc on the reference's x86-64 build), element-wise, for agreement statistics
+void hh_libm_sincos(int64_t n, const double* x, double* s, double* c) {
+    for (int64_t i = 0; i < n; i++) { s[i] = sin(x[i]); c[i] = cos(x[i]); }
+}
+void hh_libm_atan2(int64_t n, const double* y, const double* x, double* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = atan2(y[i], x[i]);
+}
+void hh_libm_acos(int64_t n, const double* x, double* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = acos(x[i]);
 }
 
 } // extern "C"

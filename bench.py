@@ -1,0 +1,350 @@
+#!/usr/bin/env python3
+"""bench.py -- Dubins edge true-cost evaluations per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c3b|c5|c1] [--edges E]
+    python bench.py --impl reference ...      # the reference's own CPU implementation of the path
+
+One "step" = one pass of the hot path (Edge::computeTrueCost incl. the Dubins solve, Edge.cpp:68-206)
+over one batch of E synthetic edges per GPU.  Default workload: BASELINE.json configs[1] -- the 1 km^2
+grid map with static obstacles and 10 survey ribbons -- as a 2^20-edge sweep per GPU (weak scaling).
+
+  value     edges/s, whole job, inputs already resident in HBM, timed with CUDA events on the
+            launching stream (max over ranks).
+  e2e       the same metric through the public host-buffer call (EdgeEngine.true_cost_batch ->
+            ppe_true_cost_batch): pinned host inputs, H2D + kernels + D2H inside the timed region.
+  roofline  the dominant kernel (k2_true_cost) against the MEASURED fp64 FMA peak of this GPU
+            (tensor cores are not used; HBM is not the bound -- its fraction is reported too).
+  cpu_baseline  the compiled reference (oracle/_ref/libref_planner.so, kind "reference") or the C
+            restatement (kind "port") single-threaded on this host, on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c1": "C1: single ribbon, empty map, no dynamic obstacles",
+    "c2": "C2: 1 km^2 grid map (1000x1000 @ 1 m, 40 static rectangles), 10 survey ribbons, no dynamic obstacles",
+    "c3": "C3: C2 + 50 Gaussian dynamic obstacles",
+    "c3b": "C3b: C2 + 50 binary (10 m x 30 m) dynamic obstacles",
+    "c4": "C4: 4096^2 occupancy map, 100 ribbons",
+    "c5": "C5: 4096^2 occupancy map, 100 ribbons, 50 Gaussian dynamic obstacles",
+}
+F_OBS = {"none": 0, "binary": 18, "gaussian": 51}  # SURVEY.md section 8d flop weights
+
+
+def algorithmic_flops(n_edges, sum_samples, sum_checkpoints, n_ribbons, n_obs, obs_kind):
+    """F_edge = 1451 + 43 R + S (111 + N F_obs) + C R 180  (SURVEY.md section 8d), summed over a batch."""
+    return (n_edges * (1451.0 + 43.0 * n_ribbons) + sum_samples * (111.0 + n_obs * F_OBS[obs_kind])
+            + sum_checkpoints * n_ribbons * 180.0)
+
+
+def algorithmic_bytes(n_edges, sum_samples):
+    """208 B in + 120 B out per edge as the reference's structs hold them + S/8 bitmap bytes (8d)."""
+    return n_edges * (208.0 + 120.0) + sum_samples / 8.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [v for v in sm if v >= 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_cpu_lib():
+    """(world wrapper, kind): the compiled reference when present, else the C restatement."""
+    from tests import common
+    if common.have_ref():
+        return common.load_ref(), "reference"
+    return common.load_oracle("glibc"), "port"
+
+
+def cpu_rate(world, edges, budget_s, threads):
+    """edges/s of the CPU implementation on a bounded sample of `edges` sized for ~budget_s."""
+    from tests import common
+    w, kind = load_cpu_lib()
+    if kind == "reference":
+        world.upload_ref(w)
+    else:
+        world.upload(w)
+    probe = edges[: min(len(edges), 512)]
+    t0 = time.perf_counter()
+    common.true_cost_mt(w, probe, threads)
+    dt = time.perf_counter() - t0
+    rate = len(probe) / max(dt, 1e-9)
+    n = int(max(512, min(len(edges), rate * budget_s)))
+    sample = edges[:n]
+    t0 = time.perf_counter()
+    common.true_cost_mt(w, sample, threads)
+    dt = time.perf_counter() - t0
+    return n / dt, kind, n, dt
+
+
+def run_reference(args, world, edges_fn):
+    """--impl reference: the reference's CPU implementation, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests import common
+    w, kind = load_cpu_lib()
+    if kind == "reference":
+        world.upload_ref(w)
+    else:
+        world.upload(w)
+    cores = os.cpu_count() or 1
+    edges = edges_fn(0)
+    probe = edges[:1024]
+    t0 = time.perf_counter()
+    common.true_cost_mt(w, probe, 0)
+    rate = len(probe) / (time.perf_counter() - t0)
+    total_steps = args.steps + args.warmup
+    n = int(max(1024, min(len(edges), rate * (120.0 / total_steps))))
+    sample = edges[:n]
+    for _ in range(args.warmup):
+        common.true_cost_mt(w, sample, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        common.true_cost_mt(w, sample, 0)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "dubins_edge_true_cost_evals_per_sec", "value": value, "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "edges_per_gpu": args.edges,
+                   "note": "CPU arm: each step evaluates a bounded sample of the same edge batch"},
+        "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": kind,
+                         "sample": "%d edges of the %d-edge batch per step, %d host threads" % (n, len(edges), cores)},
+        "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--edges", type=int, default=1 << 20, help="edges per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--near-ribbons", type=float, default=0.0)
+    args = ap.parse_args()
+
+    from path_planner_b200 import abi, synth
+
+    world = synth.WORLDS[args.workload]()
+    n = args.edges
+
+    def edges_fn(rank):
+        return synth.make_edges(world, n, seed=5 + 1000 * rank, near_ribbons=args.near_ribbons)
+
+    if args.impl == "reference":
+        run_reference(args, world, edges_fn)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from path_planner_b200 import EdgeEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world_size > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = EdgeEngine(local_rank)
+    set_id = world.upload(eng)
+    edges = edges_fn(rank)
+    edges["ribbon_set"] = set_id
+
+    # device-resident inputs / outputs (torch = plumbing: memory, streams, events)
+    h_edges = torch.from_numpy(edges.view(np.uint8).reshape(n, abi.EDGE_DTYPE.itemsize)).pin_memory()
+    d_edges = h_edges.to(dev, non_blocking=True)
+    d_results = torch.empty((n, abi.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    best_local = torch.zeros(2, dtype=torch.float64, device=dev)  # {f64 f, i64 idx} as 16 raw bytes
+    best_all = torch.zeros(2 * world_size, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    torch.cuda.synchronize()
+
+    def step():
+        eng.true_cost_batch_device(n, d_edges.data_ptr(), d_results.data_ptr(), sh)
+        if distributed:
+            # the path's only exchange: one (best f, edge index) record per GPU back to the planner
+            eng.best_copy_device(best_local.data_ptr(), sh)
+            dist.all_gather_into_tensor(best_all, best_local)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    fp64_peak = eng.measure_fp64_peak(sh) if rank == 0 else 0.0
+    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    launches = eng.launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+
+    # per-batch work counters from the result records (int32 columns 47 / 48 = n_samples / n_checkpoints)
+    r32 = d_results.view(torch.int32).reshape(n, abi.RESULT_DTYPE.itemsize // 4)
+    sum_samples = int(r32[:, 47].to(torch.int64).sum().item())
+    sum_cp = int(r32[:, 48].to(torch.int64).sum().item())
+    infeasible = int(r32[:, 45].to(torch.int64).sum().item())
+    bad_status = int((r32[:, 46] != 0).sum().item())
+
+    # ---- end to end through the public host-buffer API -----------------------------------------
+    res_host = torch.empty((n, abi.RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    lib = eng._lib
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step():
+        rc = lib.ppe_true_cost_batch(eng._ctx, n, C.c_void_p(h_edges.data_ptr()), C.c_void_p(res_host.data_ptr()))
+        if rc != 0:
+            raise RuntimeError("ppe_true_cost_batch failed: %d" % rc)
+
+    e2e_step()
+    if distributed:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s_max = float(te.item())
+
+    if rank == 0:
+        ms_per_step = total_ms_max / args.steps
+        value = world_size * n * args.steps / (total_ms_max * 1e-3)
+        n_rib = len(world.ribbons)
+        n_obs = 0 if world.obstacle_kind == "none" else len(world.obstacles["x"])
+        flops = algorithmic_flops(n, sum_samples, sum_cp, n_rib, n_obs, world.obstacle_kind)
+        kernel_s = total_ms * 1e-3 / args.steps  # rank 0's own average launch duration
+        achieved_tf = flops / kernel_s / 1e12
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        bytes_alg = algorithmic_bytes(n, sum_samples)
+        line = {
+            "metric": "dubins_edge_true_cost_evals_per_sec", "value": value, "unit": "edges/s",
+            "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "edges_per_gpu": n, "edge_bytes": abi.EDGE_DTYPE.itemsize,
+                       "result_bytes": abi.RESULT_DTYPE.itemsize, "l2": "inputs+outputs (%.0f MB per GPU) larger than L2" %
+                       (n * (abi.EDGE_DTYPE.itemsize + abi.RESULT_DTYPE.itemsize) / 1e6),
+                       "mean_samples_per_edge": sum_samples / n, "mean_checkpoints_per_edge": sum_cp / n,
+                       "infeasible_edges": infeasible, "edges_with_status": bad_status,
+                       "parallelism": "edges sharded over %d GPU(s), one process per GPU" % world_size},
+            "e2e": {"value": world_size * n * e2e_steps / e2e_s_max, "unit": "edges/s",
+                    "h2d_bytes_per_step": n * abi.EDGE_DTYPE.itemsize, "d2h_bytes_per_step": n * abi.RESULT_DTYPE.itemsize + 8,
+                    "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": {
+                "bound": "fp64", "kernel": "k2_true_cost", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
+                "peak_source": "measured live: ppe_measure_fp64_peak (DFMA chain, 2 flop/FMA) -- MEASURED_PEAKS.json has no fp64 entry",
+                "flops_per_launch": flops, "traffic": None,
+                "hbm": {"achieved": bytes_alg / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_alg / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                        "bytes_moved_per_launch": n * (abi.EDGE_DTYPE.itemsize + abi.RESULT_DTYPE.itemsize)},
+            },
+        }
+        if world_size == 1 and not args.no_cpu_baseline:
+            rate, kind, ns, dt = cpu_rate(world, edges, args.cpu_seconds, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "edges/s", "cores": 1, "kind": kind,
+                                    "sample": "first %d edges of the same batch, single thread, %.1f s" % (ns, dt),
+                                    "host_cores": os.cpu_count()}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -187,6 +187,10 @@ int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges,
                                ppe_edge_result* d_results, void* stream);
 /* (f, edge_index) of the last *_device batch; synchronises `stream`. */
 int ppe_best_device(ppe_ctx* ctx, double* f, int64_t* edge_index, void* stream);
+/* Same record as 16 bytes {double f; int64 edge_index} copied device-to-device into d_dst on
+ * `stream` without synchronising: the send buffer of the per-batch NCCL gather (one record per
+ * GPU) when edge batches are sharded over ranks. */
+int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, void* stream);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* number of engine kernels launched on this ctx since creation */

@@ -452,6 +452,13 @@ int ppe_best_device(ppe_ctx* ctx, double* f, int64_t* edge_index, void* stream) 
     return PPE_OK;
 }
 
+int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, void* stream) {
+    if (!ctx || !d_dst16) return PPE_ERR_INVALID;
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    PPE_CUDA(ctx, cudaMemcpyAsync(d_dst16, ctx->d_best, sizeof(BestD), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PPE_OK;
+}
+
 int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge_result* results) {
     if (!ctx || n < 0 || (n > 0 && (!edges || !results))) return fail(ctx, PPE_ERR_INVALID, "ppe_true_cost_batch: bad arguments");
     PPE_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -26,6 +26,24 @@ struct dd {
     double hi, lo;
 };
 
+// coefficient / lookup tables: one copy for device code, one for host code
+#if defined(__CUDACC__)
+#define PPE_TABLE_DECL(name, dims, init) \
+    static __device__ const double d_##name dims = init; \
+    static const double h_##name dims = init;
+#else
+#define PPE_TABLE_DECL(name, dims, init) static const double h_##name dims = init;
+#endif
+#if defined(__CUDA_ARCH__)
+#define PPE_TABLE(name) d_##name
+#else
+#define PPE_TABLE(name) h_##name
+#endif
+PPE_TABLE_DECL(sin_coeffs, [crtab::kSinCosTerms][2], PPE_SIN_COEFFS)
+PPE_TABLE_DECL(cos_coeffs, [crtab::kSinCosTerms][2], PPE_COS_COEFFS)
+PPE_TABLE_DECL(atan_table, [65][2], PPE_ATAN_TABLE)
+PPE_TABLE_DECL(atan_coeffs, [crtab::kAtanTerms][2], PPE_ATAN_COEFFS)
+
 PPE_HD double fma_(double a, double b, double c) {
 #if defined(__CUDA_ARCH__)
     return __fma_rn(a, b, c);
@@ -112,7 +130,7 @@ PPE_HD dd reduce_pio2(double x, int* quadrant) {
 }
 
 PPE_HD dd sin_kernel(dd r) {
-    const double C[crtab::kSinCosTerms][2] = PPE_SIN_COEFFS;
+    const double (*C)[2] = PPE_TABLE(sin_coeffs);
     const dd z = dd_mul(r, r);
     dd p = dd{C[crtab::kSinCosTerms - 1][0], C[crtab::kSinCosTerms - 1][1]};
 #pragma unroll
@@ -121,7 +139,7 @@ PPE_HD dd sin_kernel(dd r) {
     return dd_add(r, dd_mul(dd_mul(r, z), p));
 }
 PPE_HD dd cos_kernel(dd r) {
-    const double C[crtab::kSinCosTerms][2] = PPE_COS_COEFFS;
+    const double (*C)[2] = PPE_TABLE(cos_coeffs);
     const dd z = dd_mul(r, r);
     dd p = dd{C[crtab::kSinCosTerms - 1][0], C[crtab::kSinCosTerms - 1][1]};
 #pragma unroll
@@ -156,8 +174,8 @@ PPE_HD double cr_cos(double x) { double s, c; cr_sincos(x, &s, &c); return c; }
 // ---- atan / atan2 / acos --------------------------------------------------------------------------------
 // atan(q) for a double-double 0 <= q <= 1
 PPE_HD dd atan_dd_unit(dd q) {
-    const double T[65][2] = PPE_ATAN_TABLE;
-    const double C[crtab::kAtanTerms][2] = PPE_ATAN_COEFFS;
+    const double (*T)[2] = PPE_TABLE(atan_table);
+    const double (*C)[2] = PPE_TABLE(atan_coeffs);
     int i = (int)rint(q.hi * 64.0);
     if (i < 0) i = 0;
     if (i > 64) i = 64;

@@ -46,6 +46,8 @@ def load_library():
     lib.ppe_true_cost_batch_device.restype = C.c_int
     lib.ppe_best_device.argtypes = [C.c_void_p, D, C.POINTER(C.c_int64), C.c_void_p]
     lib.ppe_best_device.restype = C.c_int
+    lib.ppe_best_copy_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ppe_best_copy_device.restype = C.c_int
     lib.ppe_launch_count.argtypes = [C.c_void_p]
     lib.ppe_launch_count.restype = C.c_int64
     lib.ppe_measure_fp64_peak.argtypes = [C.c_void_p, D, C.c_void_p]
@@ -98,6 +100,10 @@ class EdgeEngine(CApiWorld):
         idx = C.c_int64()
         self._check(self._lib.ppe_best_device(self._ctx, C.byref(f), C.byref(idx), C.c_void_p(stream)), "best_device")
         return f.value, idx.value
+
+    def best_copy_device(self, d_dst16, stream=0):
+        """{f64 f, i64 edge_index} of the last device batch -> 16 bytes at d_dst16 (no sync)."""
+        self._check(self._lib.ppe_best_copy_device(self._ctx, C.c_void_p(d_dst16), C.c_void_p(stream)), "best_copy_device")
 
     # ---- instrumentation ---------------------------------------------------------------------
     def launch_count(self):

@@ -16,6 +16,7 @@ from path_planner_b200._capi import CApiWorld
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_ref", "libppe_oracle.so")
+ORACLE_CR_SO = os.path.join(ORACLE_DIR, "_ref", "libppe_oracle_cr.so")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libref_planner.so")
 
 DISCRETE = ("path_type", "infeasible", "status", "n_samples", "n_checkpoints", "n_ribbons_after", "ribbons_changed")
@@ -27,7 +28,7 @@ ATOL = 1e-9  # absolute floor for quantities that are legitimately ~0 (e.g. x of
 
 def build_oracles():
     """Build what can be built here: the C restatement always, the reference when its sources exist."""
-    if not os.path.exists(ORACLE_SO):
+    if not os.path.exists(ORACLE_SO) or not os.path.exists(ORACLE_CR_SO):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"], stdout=subprocess.DEVNULL)
     if not os.path.exists(REF_SO) and os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "ref"], stdout=subprocess.DEVNULL)
@@ -45,9 +46,12 @@ def _load(path, prefix):
     return w
 
 
-def load_oracle():
+def load_oracle(variant="glibc"):
+    """variant "glibc": oracle-A, bit-identical to the compiled reference.
+    variant "cr": oracle-B, the same restatement with the Dubins transcendentals correctly rounded
+    (oracle/crmath_redirect.h) -- bit-identical to the engine's per-edge arithmetic."""
     build_oracles()
-    w = _load(ORACLE_SO, "oracle_")
+    w = _load(ORACLE_CR_SO if variant == "cr" else ORACLE_SO, "oracle_")
     w.lib.oracle_true_cost_batch_mt.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     return w
 

@@ -52,6 +52,8 @@ struct ppe_ctx {
     ppe_edge* d_edges = nullptr;
     ppe_edge_result* d_results = nullptr;
     size_t cap_edges = 0, cap_results = 0, cap_dubi = 0;
+    unsigned char* d_prepared = nullptr; // K2a -> K2b per-edge scratch
+    size_t cap_prepared = 0;
     double* d_dub = nullptr; // q0 q1 rho param length
     int32_t* d_dubi = nullptr; // type err
     size_t cap_dub = 0;
@@ -232,7 +234,7 @@ void ppe_destroy(ppe_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_map); cudaFree(ctx->d_obs);
     cudaFree(ctx->d_ribbons); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct);
-    cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
+    cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_prepared); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
     cudaFree(ctx->d_work); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -435,8 +437,10 @@ int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges,
     ctx->out_downloaded = false;
     if (n == 0) return PPE_OK;
     int launches = 0;
-    PPE_CUDA(ctx, launch_true_cost_batch(w, n, d_edges, d_results, ctx->d_work, ctx->d_block_best, ctx->max_blocks,
-                                         ctx->d_best, ctx->sm_count, (cudaStream_t)stream, &launches));
+    rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, (size_t)n * prepared_edge_bytes());
+    if (rc != PPE_OK) return rc;
+    PPE_CUDA(ctx, launch_true_cost_batch(w, n, d_edges, ctx->d_prepared, d_results, ctx->d_work, ctx->d_block_best,
+                                         ctx->max_blocks, ctx->d_best, ctx->sm_count, (cudaStream_t)stream, &launches));
     ctx->launches += launches;
     return PPE_OK;
 }

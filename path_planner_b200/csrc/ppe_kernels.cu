@@ -23,6 +23,9 @@ namespace ppe {
 
 namespace {
 
+#ifndef PPE_K2_MIN_BLOCKS
+#define PPE_K2_MIN_BLOCKS 2
+#endif
 constexpr int kWarpsPerBlock = 4;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -198,6 +201,108 @@ __device__ __forceinline__ double warp_max_distance(const double4* cur, int nr, 
     return fmax(sumLength + mn, mx);
 }
 
+
+// Per-edge state produced by K2a (one THREAD per edge) and consumed by K2b (one WARP per edge):
+// the solved path, the sampler's per-path constants, the wrapper times and the connected end
+// state.  Splitting the edge this way removes the 32-fold redundancy a warp would have on the
+// expensive, purely scalar part (the correctly rounded Dubins solve).
+struct PreparedEdge {
+    DubinsPathD path;                 // qi[3], param[3], rho, type
+    double length, p1, p2, p12;
+    double bx[3], by[3], bth[3], bs[3], bc[3];
+    double w_speed, w_start, w_end;
+    double approx;
+    double ex, ey, eh, es;            // end()->state() as connected
+    int seg[3];
+    int status;                       // PPE_EDGE_* raised while preparing
+    int sample_fault;
+    int pad;
+};
+
+// Edge.cpp:73-85, Edge::setEnd :208-215, DubinsWrapper.cpp:9-17,84-93 -- scalar, one thread.
+__device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__ edge, PreparedEdge* __restrict__ out) {
+    const double src_x = edge->src[0], src_y = edge->src[1], src_h = edge->src[2], src_speed = edge->src[3],
+                 src_t = edge->src[4];
+    const bool has_path = edge->has_path != 0;
+    const bool cov = edge->coverage_allowed != 0;
+
+    DubinsPathD path;
+    path.qi[0] = path.qi[1] = path.qi[2] = 0;
+    path.param[0] = path.param[1] = path.param[2] = 0;
+    path.rho = 0; path.type = 0;
+    PathSampler smp;
+    memset(&smp, 0, sizeof smp);
+    double w_speed = 0, w_start = -1, w_end = -1;
+    bool w_init = false;
+    double ex, ey, eh, es; // end()->state() pose
+    double approx = -1;
+    int status = PPE_EDGE_OK;
+    bool sample_fault = false; // both dubins_path_sample attempts failed (stale-pose case)
+
+    if (has_path) {
+        path.qi[0] = edge->path_qi[0]; path.qi[1] = edge->path_qi[1]; path.qi[2] = edge->path_qi[2];
+        path.param[0] = edge->path_param[0]; path.param[1] = edge->path_param[1]; path.param[2] = edge->path_param[2];
+        path.rho = edge->path_rho; path.type = edge->path_type;
+        w_speed = edge->w_speed;
+        w_start = edge->w_start_time;
+        w_init = w_start >= 0;
+        sampler_init(&smp, path);
+        w_end = w_start + smp.length / w_speed;
+        if (edge->w_end_time < w_end) w_end = edge->w_end_time;
+        ex = 0; ey = 0; eh = 0;
+        if (!w_init || !(w_start <= w_end)) {
+            status = PPE_EDGE_ERR_END_SAMPLE;
+        } else if (!wrapper_sample_pose<true>(smp, w_start, w_speed, w_end, &ex, &ey, &eh)) {
+            eh = heading_to_yaw(eh);
+            sample_fault = true;
+        }
+        es = w_speed;
+        approx = (w_end - src_t) * cfg.time_penalty_factor;
+    } else {
+        ex = edge->dst[0]; ey = edge->dst[1]; eh = edge->dst[2]; es = edge->dst[3];
+    }
+    const double speed = es;
+    const double rho = cov ? cfg.coverage_turning_radius : cfg.turning_radius;
+    if (status == PPE_EDGE_OK && (approx == -1 || path.rho != rho)) {
+        if (src_x == ex && src_y == ey && src_h == eh) {
+            approx = 0; // co-located (State::isCoLocated, State.cpp:87-91): wrapper untouched
+        } else {
+            const double q1[3] = {src_x, src_y, heading_to_yaw(src_h)};
+            const double q2[3] = {ex, ey, heading_to_yaw(eh)};
+            dubins_shortest_path(&path, q1, q2, rho); // return code ignored, as DubinsWrapper.cpp:13 does
+            sampler_init(&smp, path);
+            w_speed = src_speed;
+            w_start = src_t;
+            w_init = w_start >= 0;
+            w_end = w_start + smp.length / w_speed;
+            approx = smp.length / speed * cfg.time_penalty_factor;
+        }
+    }
+    if (status == PPE_EDGE_OK && w_speed != speed) {
+        if (!w_init) { // setSpeed -> setEndTime -> length() throws on an unset wrapper
+            status = PPE_EDGE_ERR_NO_PATH;
+        } else {
+            w_speed = speed;
+            w_end = w_start + smp.length / w_speed;
+        }
+    }
+    if (status == PPE_EDGE_OK && approx < 0) status = PPE_EDGE_ERR_NO_PATH; // Edge.cpp:85
+
+    out->path = path;
+    out->length = smp.length; out->p1 = smp.p1; out->p2 = smp.p2; out->p12 = smp.p12;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        out->bx[k] = smp.bx[k]; out->by[k] = smp.by[k]; out->bth[k] = smp.bth[k];
+        out->bs[k] = smp.bs[k]; out->bc[k] = smp.bc[k]; out->seg[k] = smp.seg[k];
+    }
+    out->w_speed = w_speed; out->w_start = w_start; out->w_end = w_end;
+    out->approx = approx;
+    out->ex = ex; out->ey = ey; out->eh = eh; out->es = es;
+    out->status = status;
+    out->sample_fault = sample_fault ? 1 : 0;
+    out->pad = 0;
+}
+
 struct EdgeOut {
     double true_cost, collision_penalty, approx_cost;
     double ex, ey, eh, es, et;
@@ -235,8 +340,9 @@ __device__ __forceinline__ void write_result(ppe_edge_result* r, const EdgeOut& 
 
 // One edge, one warp.  All lanes hold identical copies of the per-edge scalars; lane i of a chunk
 // owns sample index base + i.
-__device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge, ppe_edge_result* __restrict__ result,
-                             const ObstacleD* s_obs, double4* bufA, double4* bufB, int lane, double* out_f) {
+__device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge, const PreparedEdge* __restrict__ prep,
+                             ppe_edge_result* __restrict__ result, const ObstacleD* s_obs, double4* bufA, double4* bufB,
+                             int lane, double* out_f) {
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width;
     const double inc = cfg.collision_checking_increment;
@@ -255,10 +361,8 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
     o.n_ribbons_after = 0; o.ribbons_changed = 0;
     *out_f = INFINITY;
 
-    const double src_x = edge->src[0], src_y = edge->src[1], src_h = edge->src[2], src_speed = edge->src[3],
-                 src_t = edge->src[4];
+    const double src_x = edge->src[0], src_y = edge->src[1], src_h = edge->src[2], src_t = edge->src[4];
     const double src_g = edge->src_g;
-    const bool has_path = edge->has_path != 0;
     const bool cov = edge->coverage_allowed != 0;
     const int set = edge->ribbon_set;
 
@@ -284,74 +388,26 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
     bool modified = false;
     bool overflow = false;
 
-    // ---- wrapper / path (Edge.cpp:73-85, Edge::setEnd :208-215, DubinsWrapper.cpp:9-17,84-93) ----------
-    DubinsPathD path;
-    path.qi[0] = path.qi[1] = path.qi[2] = 0;
-    path.param[0] = path.param[1] = path.param[2] = 0;
-    path.rho = 0; path.type = 0;
-    PathSampler smp;
-    double w_speed = 0, w_start = -1, w_end = -1;
-    bool w_init = false;
-    double ex, ey, eh, es; // end()->state() pose
-    double approx = -1;
-    bool sample_fault = false; // both dubins_path_sample attempts failed somewhere (stale-pose case)
-
-    if (has_path) {
-        path.qi[0] = edge->path_qi[0]; path.qi[1] = edge->path_qi[1]; path.qi[2] = edge->path_qi[2];
-        path.param[0] = edge->path_param[0]; path.param[1] = edge->path_param[1]; path.param[2] = edge->path_param[2];
-        path.rho = edge->path_rho; path.type = edge->path_type;
-        w_speed = edge->w_speed;
-        w_start = edge->w_start_time;
-        w_init = w_start >= 0;
-        sampler_init(&smp, path);
-        w_end = w_start + smp.length / w_speed;
-        if (edge->w_end_time < w_end) w_end = edge->w_end_time;
-        if (!w_init || !(w_start <= w_end)) {
-            o.status = PPE_EDGE_ERR_END_SAMPLE;
-            if (lane == 0) write_result(result, o);
-            return;
-        }
-        ex = 0; ey = 0; eh = 0;
-        if (!wrapper_sample_pose<true>(smp, w_start, w_speed, w_end, &ex, &ey, &eh)) {
-            eh = heading_to_yaw(eh);
-            sample_fault = true;
-        }
-        es = w_speed;
-        approx = (w_end - src_t) * cfg.time_penalty_factor;
-    } else {
-        ex = edge->dst[0]; ey = edge->dst[1]; eh = edge->dst[2]; es = edge->dst[3];
-    }
-    const double speed = es;
-    const double rho = cov ? cfg.coverage_turning_radius : cfg.turning_radius;
-    if (approx == -1 || path.rho != rho) {
-        if (src_x == ex && src_y == ey && src_h == eh) {
-            approx = 0; // co-located (State::isCoLocated, State.cpp:87-91): wrapper untouched
-        } else {
-            const double q1[3] = {src_x, src_y, heading_to_yaw(src_h)};
-            const double q2[3] = {ex, ey, heading_to_yaw(eh)};
-            dubins_shortest_path(&path, q1, q2, rho); // return code ignored, as DubinsWrapper.cpp:13 does
-            sampler_init(&smp, path);
-            w_speed = src_speed;
-            w_start = src_t;
-            w_init = w_start >= 0;
-            w_end = w_start + smp.length / w_speed;
-            approx = smp.length / speed * cfg.time_penalty_factor;
-        }
-    }
-    if (w_speed != speed) {
-        if (!w_init) { // setSpeed -> setEndTime -> length() throws on an unset wrapper
-            o.status = PPE_EDGE_ERR_NO_PATH;
-            if (lane == 0) write_result(result, o);
-            return;
-        }
-        w_speed = speed;
-        w_end = w_start + smp.length / w_speed;
-    }
-    if (approx < 0) {
-        o.status = PPE_EDGE_ERR_NO_PATH;
+    // ---- wrapper / path: prepared by K2a ------------------------------------------------------------------
+    if (prep->status != PPE_EDGE_OK) {
+        o.status = prep->status;
         if (lane == 0) write_result(result, o);
         return;
     }
+    const DubinsPathD path = prep->path;
+    PathSampler smp;
+    smp.x0 = path.qi[0]; smp.y0 = path.qi[1]; smp.rho = path.rho;
+    smp.length = prep->length; smp.p1 = prep->p1; smp.p2 = prep->p2; smp.p12 = prep->p12;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        smp.bx[k] = prep->bx[k]; smp.by[k] = prep->by[k]; smp.bth[k] = prep->bth[k];
+        smp.bs[k] = prep->bs[k]; smp.bc[k] = prep->bc[k]; smp.seg[k] = prep->seg[k];
+    }
+    const double w_speed = prep->w_speed, w_start = prep->w_start;
+    double w_end = prep->w_end;
+    double ex = prep->ex, ey = prep->ey, eh = prep->eh, es = prep->es;
+    const double approx = prep->approx;
+    bool sample_fault = prep->sample_fault != 0;
 
     // ---- the sampling loop (Edge.cpp:86-175) ---------------------------------------------------------------
     double endTime = fmin(w.horizon_end, w_end);
@@ -481,7 +537,7 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
         if (lane == 0) write_result(result, o);
         return;
     }
-    if (!wrapper_sample_pose<true>(smp, w_start, w_speed, endTime, &ex, &ey, &eh)) {
+    if (!wrapper_sample_pose<false>(smp, w_start, w_speed, endTime, &ex, &ey, &eh)) {
         eh = heading_to_yaw(eh);
         sample_fault = true;
     }
@@ -541,9 +597,18 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
     if (!infeasible && o.status == PPE_EDGE_OK && o.h >= 0) *out_f = o.g + o.h;
 }
 
-__global__ void __launch_bounds__(kBlockThreads)
-k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edges, ppe_edge_result* __restrict__ results,
-             unsigned long long* work_counter, BestD* block_best) {
+// K2a: one thread per edge
+__global__ void __launch_bounds__(128)
+k2a_prepare(const ppe_config cfg, const long long n, const ppe_edge* __restrict__ edges, PreparedEdge* __restrict__ prepared) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    prepare_edge(cfg, edges + i, prepared + i);
+}
+
+// K2b: one warp per edge, persistent CTAs pulling edges from a global counter
+__global__ void __launch_bounds__(kBlockThreads, PPE_K2_MIN_BLOCKS)
+k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edges, const PreparedEdge* __restrict__ prepared,
+             ppe_edge_result* __restrict__ results, unsigned long long* work_counter, BestD* block_best) {
     extern __shared__ double4 smem4[];
     ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
     double4* s_rib = smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4));
@@ -568,7 +633,7 @@ k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edg
         ei = __shfl_sync(kFull, ei, 0);
         if (ei >= (unsigned long long)n) break;
         double f;
-        process_edge(w, edges + ei, results + ei, s_obs, bufA, bufB, lane, &f);
+        process_edge(w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, lane, &f);
         if (f < best_f || (f == best_f && (long long)ei < best_idx)) { best_f = f; best_idx = (long long)ei; }
         __syncwarp();
     }
@@ -665,9 +730,12 @@ cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, c
     return cudaGetLastError();
 }
 
-cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edge* edges, ppe_edge_result* results,
-                                   unsigned long long* work_counter, BestD* block_best, int max_blocks, BestD* best,
-                                   int sm_count, cudaStream_t stream, int* launches) {
+size_t prepared_edge_bytes() { return sizeof(PreparedEdge); }
+
+cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
+                                   ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best,
+                                   int max_blocks, BestD* best, int sm_count, cudaStream_t stream, int* launches) {
+    PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
     const size_t smem = true_cost_smem_bytes(world.ribbon_cap, world.n_obs);
     static size_t configured = 0;
     cudaError_t e;
@@ -690,12 +758,15 @@ cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edg
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(world.out_count, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    k2_true_cost<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(world, (long long)n, edges, results, work_counter,
-                                                                   block_best);
+    k2a_prepare<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(world.cfg, (long long)n, edges, prepared);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k2_true_cost<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(world, (long long)n, edges, prepared, results,
+                                                                   work_counter, block_best);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k3_best_final<<<1, 256, 0, stream>>>(block_best, (int)blocks, best);
-    if (launches) *launches += 2;
+    if (launches) *launches += 3;
     return cudaGetLastError();
 }
 

@@ -14,7 +14,8 @@ from . import abi
 from ._capi import CApiWorld, PpeError
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppe.so")
+# PPE_LIB_PATH: build-variant experiments only (profiles/); the shipped library is libppe.so
+LIB_PATH = os.environ.get("PPE_LIB_PATH") or os.path.join(_HERE, "libppe.so")
 
 _lib = None
 

@@ -1,0 +1,29 @@
+// oracle/harness_shim.cpp -- TEST INFRASTRUCTURE: runs the product's BatchedAStarPlanner
+// (path_planner_b200/harness/) on exactly the inputs ref_plan gives the reference's AStarPlanner,
+// so tests can compare the final plans (plan identity in virtual-clock mode) and bench.py can
+// report plan cost at a wall-clock budget.  Links the compiled reference objects + libppe.so.
+#include "ref_shim.h"
+
+#include "BatchedAStarPlanner.h"
+
+extern "C" {
+
+// stats13 = the 10 values of ref_plan + true-cost edges, Dubins solves, engine batches
+int harness_plan(ref_ctx* ctx, int device, int ribbon_set, const double* start5, double timeRemaining, double clock0,
+                 double tick, int initialSamples, int useBrownPaths, int knnChunk, double* plan_out, int plan_cap,
+                 double* stats13) {
+    static ppe_ctx* engine = nullptr; // one engine context per process (one planning thread)
+    if (!engine) {
+        int rc = ppe_create(device, &engine);
+        if (rc != PPE_OK) { ctx->lastError = "ppe_create failed: no CUDA device (the engine has no CPU path)"; return -2; }
+    }
+    BatchedAStarPlanner planner(engine, knnChunk > 0 ? knnChunk : 128);
+    int n = ref_run_plan(planner, ctx, ribbon_set, start5, timeRemaining, clock0, tick, initialSamples, useBrownPaths,
+                         plan_out, plan_cap, stats13);
+    stats13[10] = (double)planner.trueCostEdges();
+    stats13[11] = (double)planner.dubinsSolves();
+    stats13[12] = (double)planner.batches();
+    return n;
+}
+
+} // extern "C"

@@ -1,0 +1,85 @@
+// oracle/ref_shim.h -- TEST INFRASTRUCTURE: context of the compiled-reference shim (ref_shim.cpp),
+// shared with the harness shim that runs the product's BatchedAStarPlanner on the same inputs.
+#ifndef PPE_ORACLE_REF_SHIM_H
+#define PPE_ORACLE_REF_SHIM_H
+
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "planner/AStarPlanner.h"
+#include "planner/utilities/RibbonManager.h"
+#include "common/dynamic_obstacles/BinaryDynamicObstaclesManager.h"
+#include "common/dynamic_obstacles/GaussianDynamicObstaclesManager.h"
+#include "ppe.h"
+
+struct NullBuf : std::streambuf { int overflow(int c) override { return c; } };
+
+struct ref_ctx {
+    NullBuf nullBuf;
+    std::ostream nullStream;
+    PlannerConfig config;
+    ppe_config cfg;
+    std::vector<RibbonManager> sets;
+    std::vector<std::vector<double>> ribbonsAfter;
+    std::shared_ptr<BinaryDynamicObstaclesManager> binary;
+    std::shared_ptr<GaussianDynamicObstaclesManager> gaussian;
+    std::string lastError;
+    // virtual clock for ref_plan
+    double clockNow = 0, clockTick = 0;
+    long clockCalls = 0;
+    ref_ctx() : nullStream(&nullBuf), config(&nullStream) {}
+};
+
+
+// Runs `planner.plan` with the ctx's world and (optionally) a virtual clock; fills the plan record
+// (12 doubles per Dubins path: qi[3], param[3], rho, type, speed, start, end, 0) and
+// stats10 = Samples, Generated, Expanded, Iterations, PlanFValue, PlanCollisionPenalty,
+// PlanTimePenalty, PlanHValue, PlanDepth, now() calls.  Returns the number of paths or -1.
+template <typename PlannerT>
+int ref_run_plan(PlannerT& planner, ref_ctx* ctx, int ribbon_set, const double* start5, double timeRemaining,
+                 double clock0, double tick, int initialSamples, int useBrownPaths, double* plan_out, int plan_cap,
+                 double* stats10) {
+    PlannerConfig config = ctx->config;
+    config.setInitialSamples(initialSamples);
+    config.setUseBrownPaths(useBrownPaths != 0);
+    ctx->clockNow = clock0; ctx->clockTick = tick; ctx->clockCalls = 0;
+    if (tick > 0) {
+        // parity mode: deterministic clock (PlannerConfig::setNowFunction, PlannerConfig.h:110);
+        // the RNG seed (AStarPlanner.cpp:33) and every deadline test then depend on call counts only
+        config.setNowFunction([ctx]() -> double {
+            double t = ctx->clockNow + (double)ctx->clockCalls * ctx->clockTick;
+            ctx->clockCalls++;
+            return t;
+        });
+    }
+    State start(start5[0], start5[1], start5[2], start5[3], start5[4]);
+    Planner::Stats stats;
+    try {
+        stats = planner.plan(ctx->sets[ribbon_set], start, config, DubinsPlan(), timeRemaining);
+    } catch (std::exception& ex) {
+        ctx->lastError = ex.what();
+        return -1;
+    }
+    int n = 0;
+    for (const auto& w : stats.Plan.get()) {
+        if (n < plan_cap) {
+            double* o = plan_out + 12 * n;
+            const DubinsPath& p = w.unwrap();
+            o[0] = p.qi[0]; o[1] = p.qi[1]; o[2] = p.qi[2];
+            o[3] = p.param[0]; o[4] = p.param[1]; o[5] = p.param[2];
+            o[6] = p.rho; o[7] = (double)p.type; o[8] = w.getSpeed();
+            o[9] = w.getStartTime(); o[10] = w.getEndTime(); o[11] = 0;
+        }
+        n++;
+    }
+    stats10[0] = (double)stats.Samples; stats10[1] = (double)stats.Generated;
+    stats10[2] = (double)stats.Expanded; stats10[3] = (double)stats.Iterations;
+    stats10[4] = n ? stats.PlanFValue : -1; stats10[5] = stats.PlanCollisionPenalty;
+    stats10[6] = n ? stats.PlanTimePenalty : -1; stats10[7] = n ? stats.PlanHValue : -1;
+    stats10[8] = n ? (double)stats.PlanDepth : -1; stats10[9] = (double)ctx->clockCalls;
+    return n;
+}
+
+#endif

@@ -205,18 +205,19 @@ __device__ __forceinline__ double warp_max_distance(const double4* cur, int nr, 
 // Per-edge state produced by K2a (one THREAD per edge) and consumed by K2b (one WARP per edge):
 // the solved path, the sampler's per-path constants, the wrapper times and the connected end
 // state.  Splitting the edge this way removes the 32-fold redundancy a warp would have on the
-// expensive, purely scalar part (the correctly rounded Dubins solve).
+// expensive, purely scalar part (the correctly rounded Dubins solve).  The record is a flat array
+// of kPrepDoubles doubles so that a warp stages it into shared memory with two coalesced loads;
+// every lane then reads the (warp-uniform) values it needs as shared-memory broadcasts instead of
+// holding ~60 registers of per-edge state.
+enum PrepSlot {
+    kX0 = 0, kY0, kRho, kInvRho, kLength, kP1, kP2, kP12,
+    kBx = 8, kBy = 11, kBth = 14, kBs = 17, kBc = 20, kSgn = 23,   // 3 entries each, one per segment
+    kWStart = 26, kWSpeed, kWEnd, kApprox, kEx, kEy, kEh, kEs,
+    kYaw0 = 34, kParam0, kParam1, kParam2, kType, kStatus, kSampleFault,
+    kPrepDoubles = 48
+};
 struct PreparedEdge {
-    DubinsPathD path;                 // qi[3], param[3], rho, type
-    double length, p1, p2, p12;
-    double bx[3], by[3], bth[3], bs[3], bc[3];
-    double w_speed, w_start, w_end;
-    double approx;
-    double ex, ey, eh, es;            // end()->state() as connected
-    int seg[3];
-    int status;                       // PPE_EDGE_* raised while preparing
-    int sample_fault;
-    int pad;
+    double v[kPrepDoubles];
 };
 
 // Edge.cpp:73-85, Edge::setEnd :208-215, DubinsWrapper.cpp:9-17,84-93 -- scalar, one thread.
@@ -288,313 +289,320 @@ __device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__
     }
     if (status == PPE_EDGE_OK && approx < 0) status = PPE_EDGE_ERR_NO_PATH; // Edge.cpp:85
 
-    out->path = path;
-    out->length = smp.length; out->p1 = smp.p1; out->p2 = smp.p2; out->p12 = smp.p12;
+    double* v = out->v;
+    v[kX0] = path.qi[0]; v[kY0] = path.qi[1]; v[kRho] = path.rho; v[kInvRho] = 1.0 / path.rho;
+    v[kLength] = smp.length; v[kP1] = smp.p1; v[kP2] = smp.p2; v[kP12] = smp.p12;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        out->bx[k] = smp.bx[k]; out->by[k] = smp.by[k]; out->bth[k] = smp.bth[k];
-        out->bs[k] = smp.bs[k]; out->bc[k] = smp.bc[k]; out->seg[k] = smp.seg[k];
+        v[kBx + k] = smp.bx[k]; v[kBy + k] = smp.by[k]; v[kBth + k] = smp.bth[k];
+        v[kBs + k] = smp.bs[k]; v[kBc + k] = smp.bc[k];
+        v[kSgn + k] = smp.seg[k] == kSegL ? 1.0 : (smp.seg[k] == kSegR ? -1.0 : 0.0);
     }
-    out->w_speed = w_speed; out->w_start = w_start; out->w_end = w_end;
-    out->approx = approx;
-    out->ex = ex; out->ey = ey; out->eh = eh; out->es = es;
-    out->status = status;
-    out->sample_fault = sample_fault ? 1 : 0;
-    out->pad = 0;
+    v[kWStart] = w_start; v[kWSpeed] = w_speed; v[kWEnd] = w_end;
+    v[kApprox] = approx;
+    v[kEx] = ex; v[kEy] = ey; v[kEh] = eh; v[kEs] = es;
+    v[kYaw0] = path.qi[2]; v[kParam0] = path.param[0]; v[kParam1] = path.param[1]; v[kParam2] = path.param[2];
+    v[kType] = (double)path.type;
+    v[kStatus] = (double)status;
+    v[kSampleFault] = sample_fault ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = kSampleFault + 1; k < kPrepDoubles; k++) v[k] = 0.0;
 }
 
-struct EdgeOut {
-    double true_cost, collision_penalty, approx_cost;
-    double ex, ey, eh, es, et;
-    double g, h, cct;
-    DubinsPathD path;
-    double w_speed, w_start, w_end;
-    long long ribbons_offset;
-    int infeasible, status, n_samples, n_checkpoints, n_ribbons_after, ribbons_changed;
-};
-
-__device__ __forceinline__ void write_result(ppe_edge_result* r, const EdgeOut& o) {
-    r->true_cost = o.true_cost;
-    r->collision_penalty = o.collision_penalty;
-    r->approx_cost = o.approx_cost;
-    r->end[0] = o.ex; r->end[1] = o.ey; r->end[2] = o.eh; r->end[3] = o.es; r->end[4] = o.et;
-    r->g = o.g;
-    r->h = o.h;
-    r->coverage_completed_time = o.cct;
-    r->path_qi[0] = o.path.qi[0]; r->path_qi[1] = o.path.qi[1]; r->path_qi[2] = o.path.qi[2];
-    r->path_param[0] = o.path.param[0]; r->path_param[1] = o.path.param[1]; r->path_param[2] = o.path.param[2];
-    r->path_rho = o.path.rho;
-    r->w_speed = o.w_speed;
-    r->w_start_time = o.w_start;
-    r->w_end_time = o.w_end;
-    r->ribbons_offset = o.ribbons_offset;
-    r->path_type = o.path.type;
-    r->infeasible = o.infeasible;
-    r->status = o.status;
-    r->n_samples = o.n_samples;
-    r->n_checkpoints = o.n_checkpoints;
-    r->n_ribbons_after = o.n_ribbons_after;
-    r->ribbons_changed = o.ribbons_changed;
-    r->reserved = 0;
+// sin and cos for |x| up to a few thousand (path angles stay within a few turns): three-constant
+// Cody-Waite reduction by pi/2 + Taylor polynomials on [-pi/4, pi/4].  ~1 ulp; used for the
+// per-sample poses only (1e-9 tolerance class) -- and small enough to keep the sample loop inside
+// the instruction cache, unlike libdevice's sincos with its Payne-Hanek slow path.
+__device__ __forceinline__ void sincos_bounded(double x, double* sn, double* cs) {
+    const double kd = rint(x * 0x1.45f306dc9c883p-1);
+    const int q = (int)kd;
+    double r = __fma_rn(-kd, 0x1.921fb54442d18p+0, x);
+    r = __fma_rn(-kd, 0x1.1a62633145c07p-54, r);
+    r = __fma_rn(-kd, -0x1.f1976b7ed8fbcp-110, r);
+    const double z = r * r;
+    double ps = -0x1.2f49b46814157p-57;
+    ps = __fma_rn(ps, z, 0x1.952c77030ad4ap-49);
+    ps = __fma_rn(ps, z, -0x1.ae7f3e733b81fp-41);
+    ps = __fma_rn(ps, z, 0x1.6124613a86d09p-33);
+    ps = __fma_rn(ps, z, -0x1.ae64567f544e4p-26);
+    ps = __fma_rn(ps, z, 0x1.71de3a556c734p-19);
+    ps = __fma_rn(ps, z, -0x1.a01a01a01a01ap-13);
+    ps = __fma_rn(ps, z, 0x1.1111111111111p-7);
+    ps = __fma_rn(ps, z, -0x1.5555555555555p-3);
+    const double s0 = __fma_rn(r * z, ps, r);
+    double pc = 0x1.e542ba4020225p-62;
+    pc = __fma_rn(pc, z, -0x1.6827863b97d97p-53);
+    pc = __fma_rn(pc, z, 0x1.ae7f3e733b81fp-45);
+    pc = __fma_rn(pc, z, -0x1.93974a8c07c9dp-37);
+    pc = __fma_rn(pc, z, 0x1.1eed8eff8d898p-29);
+    pc = __fma_rn(pc, z, -0x1.27e4fb7789f5cp-22);
+    pc = __fma_rn(pc, z, 0x1.a01a01a01a01ap-16);
+    pc = __fma_rn(pc, z, -0x1.6c16c16c16c17p-10);
+    pc = __fma_rn(pc, z, 0x1.5555555555555p-5);
+    pc = __fma_rn(pc, z, -0x1.0000000000000p-1);
+    const double c0 = __fma_rn(z, pc, 1.0);
+    const double a = (q & 1) ? c0 : s0;
+    const double b2 = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -a : a;
+    *cs = ((q + 1) & 2) ? -b2 : b2;
 }
 
-// One edge, one warp.  All lanes hold identical copies of the per-edge scalars; lane i of a chunk
-// owns sample index base + i.
+// One edge, one warp.  Per-edge scalars that every lane would hold identically live in the warp's
+// shared-memory copy of the prepared record (`pe`); lane i of a chunk owns sample index base + i.
+// The pose evaluation, the ribbon cover and the end-state sample each exist exactly once in the
+// instruction stream: the truncated end state (Edge.cpp:177-178) and the final cover (:182-191)
+// run as one extra "tail" pass through the same loop body.
 __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge, const PreparedEdge* __restrict__ prep,
                              ppe_edge_result* __restrict__ result, const ObstacleD* s_obs, double4* bufA, double4* bufB,
-                             int lane, double* out_f) {
+                             double* pe, int lane, double* out_f) {
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width;
     const double inc = cfg.collision_checking_increment;
     const int cap = w.ribbon_cap;
-
-    EdgeOut o;
-    o.true_cost = 0; o.collision_penalty = 0; o.approx_cost = 0;
-    o.ex = o.ey = o.eh = o.es = o.et = 0;
-    o.g = 0; o.h = 0; o.cct = 0;
-    o.path.qi[0] = o.path.qi[1] = o.path.qi[2] = 0;
-    o.path.param[0] = o.path.param[1] = o.path.param[2] = 0;
-    o.path.rho = 0; o.path.type = 0;
-    o.w_speed = o.w_start = o.w_end = 0;
-    o.ribbons_offset = -1;
-    o.infeasible = 0; o.status = PPE_EDGE_OK; o.n_samples = 0; o.n_checkpoints = 0;
-    o.n_ribbons_after = 0; o.ribbons_changed = 0;
     *out_f = INFINITY;
 
-    const double src_x = edge->src[0], src_y = edge->src[1], src_h = edge->src[2], src_t = edge->src[4];
-    const double src_g = edge->src_g;
-    const bool cov = edge->coverage_allowed != 0;
+    // stage the prepared record (48 doubles) and the parent's ribbons into shared memory
+    __syncwarp();
+    pe[lane] = prep->v[lane];
+    if (lane < kPrepDoubles - 32) pe[32 + lane] = prep->v[32 + lane];
     const int set = edge->ribbon_set;
-
-    // v->m_RibbonManager = start->m_RibbonManager (Vertex.cpp:24,32): parent's ribbons -> shared memory
+    int status = PPE_EDGE_OK;
     int nr = 0;
     double cct = -1;
     if (set >= 0 && set < w.n_sets) {
         nr = w.set_count[set];
         cct = w.set_cct[set];
         const double4* src_ribbons = w.ribbons + w.set_offset[set];
-        if (nr > cap) { o.status = PPE_EDGE_ERR_RIBBON_CAPACITY; nr = 0; }
-        for (int r = lane; r < nr; r += 32) bufA[r] = src_ribbons[r];
+        if (nr > cap) { status = PPE_EDGE_ERR_RIBBON_CAPACITY; nr = 0; }
+        for (int r = lane; r < nr; r += 32) bufA[r] = src_ribbons[r]; // v->m_RibbonManager = start->m_RibbonManager
     } else {
-        o.status = PPE_EDGE_ERR_RIBBON_CAPACITY;
+        status = PPE_EDGE_ERR_RIBBON_CAPACITY;
     }
     __syncwarp();
-    if (o.status != PPE_EDGE_OK) {
-        if (lane == 0) write_result(result, o);
-        return;
-    }
+    if (status == PPE_EDGE_OK && pe[kStatus] != 0.0) status = (int)pe[kStatus];
+
+    const double src_t = edge->src[4];
+    const bool cov = edge->coverage_allowed != 0;
     double4* cur = bufA;
     double4* alt = bufB;
-    bool modified = false;
-    bool overflow = false;
+    bool modified = false, overflow = false;
+    bool sample_fault = pe[kSampleFault] != 0.0;
 
-    // ---- wrapper / path: prepared by K2a ------------------------------------------------------------------
-    if (prep->status != PPE_EDGE_OK) {
-        o.status = prep->status;
-        if (lane == 0) write_result(result, o);
-        return;
-    }
-    const DubinsPathD path = prep->path;
-    PathSampler smp;
-    smp.x0 = path.qi[0]; smp.y0 = path.qi[1]; smp.rho = path.rho;
-    smp.length = prep->length; smp.p1 = prep->p1; smp.p2 = prep->p2; smp.p12 = prep->p12;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        smp.bx[k] = prep->bx[k]; smp.by[k] = prep->by[k]; smp.bth[k] = prep->bth[k];
-        smp.bs[k] = prep->bs[k]; smp.bc[k] = prep->bc[k]; smp.seg[k] = prep->seg[k];
-    }
-    const double w_speed = prep->w_speed, w_start = prep->w_start;
-    double w_end = prep->w_end;
-    double ex = prep->ex, ey = prep->ey, eh = prep->eh, es = prep->es;
-    const double approx = prep->approx;
-    bool sample_fault = prep->sample_fault != 0;
-
-    // ---- the sampling loop (Edge.cpp:86-175) ---------------------------------------------------------------
-    double endTime = fmin(w.horizon_end, w_end);
+    // ---- loop state (Edge.cpp:86-120) -----------------------------------------------------------------------
+    double endTime = fmin(w.horizon_end, pe[kWEnd]);
     int ribbonsDoneTime = -1;
     const bool startedDone = (nr == 0);
     double penalty = 0;
-    bool infeasible = false;
-    if (src_t >= endTime) infeasible = true;
+    bool infeasible = src_t >= endTime;
     const double dt = w.dt;
     const double t0 = src_t + fmod(src_t - cfg.start_state_time, dt);
-
-    int next_cp = 0;             // sample index of the next ribbon check-point (toCoverDistance starts at 0)
-    double carry_x = src_x, carry_y = src_y, carry_h = src_h; // pose of sample base-1 (`intermediate` before the chunk)
-    double P_x = src_x, P_y = src_y, P_h = src_h, lastHeading = src_h, t_exit = t0;
+    int next_cp = 0; // sample index of the next ribbon check-point (toCoverDistance starts at 0)
+    double carry_x = edge->src[0], carry_y = edge->src[1], carry_h = edge->src[2]; // `intermediate` before the chunk
+    double P_x = carry_x, P_y = carry_y, P_h = carry_h, lastHeading = carry_h, t_exit = t0;
+    double ex = 0, ey = 0, eh = 0;
     int n_samples = 0, n_cp = 0;
-
-    const double span = (endTime - t0) / dt;
-    const bool loop_ok = (dt > 0) && (span < (double)kMaxSamples || !(t0 < endTime));
-    if (!loop_ok) {
-        o.status = PPE_EDGE_ERR_END_SAMPLE;
-        if (lane == 0) write_result(result, o);
-        return;
+    {
+        const double span = (endTime - t0) / dt;
+        if (!((dt > 0) && (span < (double)kMaxSamples || !(t0 < endTime)))) status = PPE_EDGE_ERR_END_SAMPLE;
     }
 
-    TimeWalker tw;
-    tw.init(t0, dt);
-
-    for (int base = 0;; base += 32) {
-        const int i = base + lane;
-        const double t_i = tw.at(i);
-        bool valid = t_i < endTime;
-        double x = 0, y = 0, hd = 0;
-        bool in_time = true, sample_ok = true, blocked = false;
-        if (valid) {
-            in_time = (w_start <= t_i) && (w_end >= t_i); // DubinsWrapper::containsTime
-            if (in_time) {
-                sample_ok = wrapper_sample_pose<false>(smp, w_start, w_speed, t_i, &x, &y, &hd);
-                if (sample_ok) blocked = map_blocked(w, x, y);
-            }
-        }
-        const unsigned m_valid = __ballot_sync(kFull, valid);
-        const unsigned m_stop = __ballot_sync(kFull, valid && (!in_time || blocked));
-        if (__any_sync(kFull, valid && in_time && !sample_ok)) sample_fault = true;
-        int nvalid = __popc(m_valid); // valid lanes form a prefix (times increase)
-        const int fstop = m_stop ? (__ffs(m_stop) - 1) : 32;
-        int limit = nvalid < fstop ? nvalid : fstop; // lanes [0, limit) execute the full loop body
-
-        // -- ribbon check-points inside this chunk, in order (Edge.cpp:153-172)
-        while (next_cp < base + limit) {
-            const int l = next_cp - base;
-            const double cx = __shfl_sync(kFull, x, l);
-            const double cy = __shfl_sync(kFull, y, l);
-            const double ch = __shfl_sync(kFull, hd, l);
-            const double ct = __shfl_sync(kFull, t_i, l);
-            const double ph_prev = __shfl_sync(kFull, hd, l > 0 ? l - 1 : 0);
-            const double ph = l > 0 ? ph_prev : carry_h;
-            n_cp++;
-            const double toCover = warp_min_distance_from(cur, nr, cx, cy, W, lane);
-            if (cov || ph == ch) {
-                bool changed = false;
-                const int nn = warp_cover(cur, alt, nr, cap, cx, cy, W, lane, &changed, &overflow);
-                if (changed) {
-                    double4* tmp = cur; cur = alt; alt = tmp;
-                    nr = nn;
-                    modified = true;
+    if (status == PPE_EDGE_OK) {
+        TimeWalker tw;
+        tw.init(t0, dt);
+        bool tail = false;
+        for (int base = 0;;) {
+            // ---- pose at this lane's time (tail pass: every lane at the truncated end time) ------------------
+            const double t_i = tail ? endTime : tw.at(base + lane);
+            bool valid = tail || (t_i < endTime);
+            const double w_start = pe[kWStart];
+            const bool in_time = (w_start <= t_i) && (pe[kWEnd] >= t_i); // DubinsWrapper::containsTime
+            double dist = (t_i - w_start) * pe[kWSpeed];
+            bool sample_ok = true;
+            {
+                const double length = pe[kLength];
+                if (dist < 0 || dist > length) { // EDUBPARAM -> one retry at distance - 1e-5 (DubinsWrapper.cpp:39-42)
+                    dist = dist - 1e-5;
+                    sample_ok = !(dist < 0 || dist > length);
                 }
             }
-            if (nr == 0) {
-                if (cct == -1) cct = ct;
-                ribbonsDoneTime = (int)ct;
-                endTime = fmin(endTime, cct + cfg.time_minimum);
-                valid = t_i < endTime;
-                nvalid = __popc(__ballot_sync(kFull, valid));
-                limit = nvalid < fstop ? nvalid : fstop;
-                if (limit < l + 1) limit = l + 1; // the check-point's own iteration has already run
-            }
-            next_cp = next_cp + 1 + skip_count(toCover, inc, kSkipCap);
-        }
+            const double tprime = dist * pe[kInvRho];
+            const double p1 = pe[kP1];
+            const int k = tprime < p1 ? 0 : (tprime < pe[kP12] ? 1 : 2);
+            const double tl = k == 0 ? tprime : (k == 1 ? tprime - p1 : tprime - p1 - pe[kP2]);
+            const double sg = pe[kSgn + k], bth = pe[kBth + k], bs = pe[kBs + k], bc = pe[kBc + k];
+            const double ang = sg * tl + bth; // L: t + th, R: -t + th, S: 0 + th  (dubins_segment)
+            double sn, cs;
+            sincos_bounded(ang, &sn, &cs);
+            const double qx = (sg == 0.0 ? bc * tl : sg * (sn - bs)) + pe[kBx + k];
+            const double qy = (sg == 0.0 ? bs * tl : -sg * (cs - bc)) + pe[kBy + k];
+            const double rho = pe[kRho];
+            const double x = qx * rho + pe[kX0];
+            const double y = qy * rho + pe[kY0];
+            const double yaw = ang - kTwoPi * floor(ang * 0x1.45f306dc9c883p-3);
+            double hd = kPi2 - yaw; // State::setYaw
+            if (hd < 0) hd += kTwoPi;
 
-        // -- dynamic-obstacle penalty of the executed iterations (Edge.cpp:150-151), in sample order
-        if (w.obs_kind != kObsNone && w.n_obs > 0) {
-            double p = 0;
-            if (lane < limit) p = collision_exists(w.obs_kind, w.n_obs, s_obs, x, y, t_i) * cfg.collision_penalty_factor;
-            if (__any_sync(kFull, p != 0)) {
-                for (int k = 0; k < limit; k++) penalty += __shfl_sync(kFull, p, k);
-            }
-        }
-
-        n_samples += limit;
-        if (limit < 32) {
-            // the loop ends inside this chunk
-            // the iteration at lane `limit` was entered and broke out only if that lane is still inside
-            // the (possibly truncated) end time
-            const bool stop_lane_valid = __shfl_sync(kFull, (int)valid, limit) != 0;
-            const bool stopped = (fstop == limit) && ((m_stop >> fstop) & 1u) && stop_lane_valid;
-            const int lp = limit > 0 ? limit - 1 : 0;
-            const double px = __shfl_sync(kFull, x, lp), py = __shfl_sync(kFull, y, lp), ph = __shfl_sync(kFull, hd, lp);
-            const double prev_x = limit > 0 ? px : carry_x, prev_y = limit > 0 ? py : carry_y,
-                         prev_h = limit > 0 ? ph : carry_h;
-            const double sx_ = __shfl_sync(kFull, x, limit), sy_ = __shfl_sync(kFull, y, limit),
-                         sh_ = __shfl_sync(kFull, hd, limit);
-            const bool stop_blocked = __shfl_sync(kFull, (int)blocked, limit) != 0;
-            t_exit = __shfl_sync(kFull, t_i, limit);
-            lastHeading = prev_h;
-            if (stopped) {
-                infeasible = true;
-                n_samples += 1; // the breaking iteration was entered
-                if (stop_blocked) { P_x = sx_; P_y = sy_; P_h = sh_; } // `intermediate` holds the blocked sample
-                else { P_x = prev_x; P_y = prev_y; P_h = prev_h; }     // sample() threw before touching it
+            int limit = 0, fstop = 32;
+            unsigned m_stop = 0;
+            bool blocked = false;
+            if (!tail) {
+                if (valid && in_time && sample_ok) blocked = map_blocked(w, x, y);
+                const unsigned m_valid = __ballot_sync(kFull, valid);
+                m_stop = __ballot_sync(kFull, valid && (!in_time || blocked));
+                if (__any_sync(kFull, valid && in_time && !sample_ok)) sample_fault = true;
+                const int nvalid = __popc(m_valid); // valid lanes form a prefix (times increase)
+                fstop = m_stop ? (__ffs(m_stop) - 1) : 32;
+                limit = nvalid < fstop ? nvalid : fstop; // lanes [0, limit) execute the full loop body
             } else {
-                P_x = prev_x; P_y = prev_y; P_h = prev_h;
+                if (!in_time) status = PPE_EDGE_ERR_END_SAMPLE; // sample(end state) throws, DubinsWrapper.cpp:30-35
+                if (!sample_ok) sample_fault = true;
+                ex = x; ey = y; eh = hd;
             }
-            break;
+
+            // ---- ribbon check-points of this chunk, in order (Edge.cpp:153-172); tail: the final cover (:182-191)
+            for (;;) {
+                if (!tail && !(next_cp < base + limit)) break;
+                const int l = tail ? 0 : next_cp - base;
+                double cx = __shfl_sync(kFull, x, l);
+                double cy = __shfl_sync(kFull, y, l);
+                double ch = __shfl_sync(kFull, hd, l);
+                double ct = __shfl_sync(kFull, t_i, l);
+                const double ph_prev = __shfl_sync(kFull, hd, l > 0 ? l - 1 : 0);
+                double ph = l > 0 ? ph_prev : carry_h;
+                double toCover = 0;
+                if (tail) {
+                    cx = P_x; cy = P_y; ch = P_h; ct = t_exit; ph = lastHeading;
+                } else {
+                    n_cp++;
+                    toCover = warp_min_distance_from(cur, nr, cx, cy, W, lane);
+                }
+                if (cov || ph == ch) {
+                    bool changed = false;
+                    const int nn = warp_cover(cur, alt, nr, cap, cx, cy, W, lane, &changed, &overflow);
+                    if (changed) {
+                        double4* tmp = cur; cur = alt; alt = tmp;
+                        nr = nn;
+                        modified = true;
+                    }
+                }
+                if (nr == 0) {
+                    if (cct == -1) cct = ct;
+                    ribbonsDoneTime = (int)ct;
+                    if (!tail) {
+                        endTime = fmin(endTime, cct + cfg.time_minimum);
+                        valid = t_i < endTime;
+                        const int nvalid = __popc(__ballot_sync(kFull, valid));
+                        limit = nvalid < fstop ? nvalid : fstop;
+                        if (limit < l + 1) limit = l + 1; // the check-point's own iteration has already run
+                    }
+                }
+                if (tail) break;
+                next_cp = next_cp + 1 + skip_count(toCover, inc, kSkipCap);
+            }
+            if (tail) break;
+
+            // ---- dynamic-obstacle penalty of the executed iterations (Edge.cpp:150-151), in sample order
+            if (w.obs_kind != kObsNone && w.n_obs > 0) {
+                double p = 0;
+                if (lane < limit) p = collision_exists(w.obs_kind, w.n_obs, s_obs, x, y, t_i) * cfg.collision_penalty_factor;
+                if (__any_sync(kFull, p != 0)) {
+                    for (int q = 0; q < limit; q++) penalty += __shfl_sync(kFull, p, q);
+                }
+            }
+
+            n_samples += limit;
+            if (limit < 32) {
+                // the loop ends inside this chunk.  The iteration at lane `limit` was entered and broke
+                // out only if that lane is still inside the (possibly truncated) end time.
+                const bool stop_lane_valid = __shfl_sync(kFull, (int)valid, limit) != 0;
+                const bool stopped = (fstop == limit) && ((m_stop >> fstop) & 1u) && stop_lane_valid;
+                const int lp = limit > 0 ? limit - 1 : 0;
+                const double px = __shfl_sync(kFull, x, lp), py = __shfl_sync(kFull, y, lp), ph = __shfl_sync(kFull, hd, lp);
+                const double prev_x = limit > 0 ? px : carry_x, prev_y = limit > 0 ? py : carry_y,
+                             prev_h = limit > 0 ? ph : carry_h;
+                const double sx_ = __shfl_sync(kFull, x, limit), sy_ = __shfl_sync(kFull, y, limit),
+                             sh_ = __shfl_sync(kFull, hd, limit);
+                const bool stop_blocked = __shfl_sync(kFull, (int)blocked, limit) != 0;
+                t_exit = __shfl_sync(kFull, t_i, limit);
+                lastHeading = prev_h;
+                P_x = prev_x; P_y = prev_y; P_h = prev_h;
+                if (stopped) {
+                    infeasible = true;
+                    n_samples += 1; // the breaking iteration was entered
+                    if (stop_blocked) { P_x = sx_; P_y = sy_; P_h = sh_; } // `intermediate` holds the blocked sample
+                }
+                tail = true;
+                continue;
+            }
+            carry_x = __shfl_sync(kFull, x, 31);
+            carry_y = __shfl_sync(kFull, y, 31);
+            carry_h = __shfl_sync(kFull, hd, 31);
+            base += 32;
+            if (base > kMaxSamples) { status = PPE_EDGE_ERR_END_SAMPLE; break; }
         }
-        carry_x = __shfl_sync(kFull, x, 31);
-        carry_y = __shfl_sync(kFull, y, 31);
-        carry_h = __shfl_sync(kFull, hd, 31);
-        if (base > kMaxSamples) { o.status = PPE_EDGE_ERR_END_SAMPLE; break; }
     }
 
-    // ---- tail (Edge.cpp:176-203) ------------------------------------------------------------------------------
-    o.infeasible = infeasible ? 1 : 0;
-    o.n_samples = n_samples;
-    if (!((w_start <= endTime) && (w_end >= endTime)) || o.status != PPE_EDGE_OK) {
-        // m_DubinsWrapper.sample(end()->state()) throws out of computeTrueCost (DubinsWrapper.cpp:30-35)
-        o.status = PPE_EDGE_ERR_END_SAMPLE;
-        if (lane == 0) write_result(result, o);
-        return;
-    }
-    if (!wrapper_sample_pose<false>(smp, w_start, w_speed, endTime, &ex, &ey, &eh)) {
-        eh = heading_to_yaw(eh);
-        sample_fault = true;
-    }
-    es = w_speed;
-    w_end = endTime; // updateEndTime
-    double t_done = t_exit;
-    if (cov || lastHeading == P_h) {
-        bool changed = false;
-        const int nn = warp_cover(cur, alt, nr, cap, P_x, P_y, W, lane, &changed, &overflow);
-        if (changed) {
-            double4* tmp = cur; cur = alt; alt = tmp;
-            nr = nn;
-            modified = true;
+    // ---- cost, g, h and the result record (Edge.cpp:193-203) ------------------------------------------------------
+    double true_cost = 0, g = 0, h = 0;
+    if (status == PPE_EDGE_OK) {
+        const double netTime = endTime - src_t;
+        double T = fmax(netTime - (nr == 0 ? (endTime - (double)ribbonsDoneTime) : 0.0), 0.0);
+        if (startedDone) T = 0;
+        true_cost = T * cfg.time_penalty_factor + penalty;
+        g = edge->src_g + true_cost;                                  // Vertex::setCurrentCost
+        if (cfg.heuristic == PPE_H_MAX_DISTANCE) {                    // Vertex::computeApproxToGo
+            const double d = nr == 0 ? 0.0 : warp_max_distance(cur, nr, ex, ey, W, lane, (double*)alt);
+            h = d / cfg.max_speed * cfg.time_penalty_factor;
+        } else {
+            h = -1;
         }
+        if (overflow) status = PPE_EDGE_ERR_RIBBON_CAPACITY;
+        else if (sample_fault) status = PPE_EDGE_ERR_END_SAMPLE;
     }
-    if (nr == 0) {
-        if (cct == -1) cct = t_done;
-        ribbonsDoneTime = (int)t_done;
-    }
-    const double netTime = endTime - src_t;
-    double T = fmax(netTime - (nr == 0 ? (endTime - (double)ribbonsDoneTime) : 0.0), 0.0);
-    if (startedDone) T = 0;
-    o.collision_penalty = penalty;
-    o.true_cost = T * cfg.time_penalty_factor + penalty;
-    o.approx_cost = approx;
-    o.ex = ex; o.ey = ey; o.eh = eh; o.es = es; o.et = endTime;
-    o.g = src_g + o.true_cost;                                  // Vertex::setCurrentCost
-    if (cfg.heuristic == PPE_H_MAX_DISTANCE) {                  // Vertex::computeApproxToGo
-        const double d = nr == 0 ? 0.0 : warp_max_distance(cur, nr, ex, ey, W, lane, (double*)alt);
-        o.h = d / cfg.max_speed * cfg.time_penalty_factor;
-    } else {
-        o.h = -1;
-    }
-    o.cct = cct;
-    o.path = path;
-    o.w_speed = w_speed; o.w_start = w_start; o.w_end = w_end;
-    o.n_checkpoints = n_cp;
-    o.n_ribbons_after = nr;
-    o.ribbons_changed = modified ? 1 : 0;
-    if (overflow) o.status = PPE_EDGE_ERR_RIBBON_CAPACITY;
-    else if (sample_fault) o.status = PPE_EDGE_ERR_END_SAMPLE;
 
     // ribbons-after: only edges that changed their parent's set materialise a list
-    if (modified && !overflow) {
+    long long ribbons_offset = -1;
+    if (status == PPE_EDGE_OK && modified) {
         unsigned long long off = 0;
         if (lane == 0) off = atomicAdd(w.out_count, (unsigned long long)nr);
         off = __shfl_sync(kFull, off, 0);
         if (off + (unsigned long long)nr <= w.out_cap) {
             for (int r = lane; r < nr; r += 32) w.out_ribbons[off + r] = cur[r];
-            o.ribbons_offset = (long long)off;
+            ribbons_offset = (long long)off;
         } else {
-            o.status = PPE_EDGE_ERR_RIBBON_CAPACITY;
+            status = PPE_EDGE_ERR_RIBBON_CAPACITY;
         }
     }
     __syncwarp();
-    if (lane == 0) write_result(result, o);
-    if (!infeasible && o.status == PPE_EDGE_OK && o.h >= 0) *out_f = o.g + o.h;
+    if (lane == 0) {
+        ppe_edge_result* r = result;
+        const bool ok = status == PPE_EDGE_OK;
+        r->true_cost = ok ? true_cost : 0.0;
+        r->collision_penalty = ok ? penalty : 0.0;
+        r->approx_cost = ok ? pe[kApprox] : 0.0;
+        r->end[0] = ok ? ex : 0.0; r->end[1] = ok ? ey : 0.0; r->end[2] = ok ? eh : 0.0;
+        r->end[3] = ok ? pe[kWSpeed] : 0.0; r->end[4] = ok ? endTime : 0.0;
+        r->g = ok ? g : 0.0;
+        r->h = ok ? h : 0.0;
+        r->coverage_completed_time = ok ? cct : 0.0;
+        r->path_qi[0] = ok ? pe[kX0] : 0.0; r->path_qi[1] = ok ? pe[kY0] : 0.0; r->path_qi[2] = ok ? pe[kYaw0] : 0.0;
+        r->path_param[0] = ok ? pe[kParam0] : 0.0; r->path_param[1] = ok ? pe[kParam1] : 0.0;
+        r->path_param[2] = ok ? pe[kParam2] : 0.0;
+        r->path_rho = ok ? pe[kRho] : 0.0;
+        r->w_speed = ok ? pe[kWSpeed] : 0.0;
+        r->w_start_time = ok ? pe[kWStart] : 0.0;
+        r->w_end_time = ok ? endTime : 0.0; // updateEndTime (Edge.cpp:179)
+        r->ribbons_offset = ribbons_offset;
+        r->path_type = ok ? (int)pe[kType] : 0;
+        r->infeasible = infeasible ? 1 : 0;
+        r->status = status;
+        r->n_samples = ok ? n_samples : 0;
+        r->n_checkpoints = ok ? n_cp : 0;
+        r->n_ribbons_after = ok ? nr : 0;
+        r->ribbons_changed = (ok && modified) ? 1 : 0;
+        r->reserved = 0;
+    }
+    if (!infeasible && status == PPE_EDGE_OK && h >= 0) *out_f = g + h;
 }
 
 // K2a: one thread per edge
@@ -616,6 +624,8 @@ k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edg
     const int warp = threadIdx.x >> 5;
     double4* bufA = s_rib + (size_t)warp * 2 * w.ribbon_cap;
     double4* bufB = bufA + w.ribbon_cap;
+    __shared__ double s_pe[kWarpsPerBlock][kPrepDoubles];
+    double* pe = s_pe[warp];
 
     {
         const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
@@ -633,7 +643,7 @@ k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edg
         ei = __shfl_sync(kFull, ei, 0);
         if (ei >= (unsigned long long)n) break;
         double f;
-        process_edge(w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, lane, &f);
+        process_edge(w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, lane, &f);
         if (f < best_f || (f == best_f && (long long)ei < best_idx)) { best_f = f; best_idx = (long long)ei; }
         __syncwarp();
     }

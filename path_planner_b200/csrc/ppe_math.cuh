@@ -282,9 +282,12 @@ struct TimeWalker {
     PPE_HD void init(double t0, double dt_) {
         dt = dt_;
         edt = (dt_ > 0) ? f64_exponent(dt_) : -2000;
+        // empty run in front of t0: the first at() builds the first run (one build() call site)
         i0 = 0;
+        cnt = 0;
         base = t0;
-        build();
+        D = 0.0;
+        t_next = t0;
     }
 
     // t_i for non-decreasing i

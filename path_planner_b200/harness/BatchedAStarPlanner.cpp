@@ -1,0 +1,346 @@
+// BatchedAStarPlanner.cpp -- see the header.  Host-side restructuring of
+// SamplingBasedPlanner::expand (SamplingBasedPlanner.cpp:52-151): the three per-edge call sites
+//   :76   computeTrueCost for the nearest-ribbon-endpoint edges
+//   :119  computeApproxCost (Dubins solve) for the k-nearest candidates
+//   :145  computeTrueCost for every winner x speed
+// become one K1 launch per chunk of candidates and ONE K2 launch per expansion, while the heap
+// operations, the candidate tests and the pushVertexQueue order are replayed exactly as the
+// reference performs them, so the open list evolves identically.
+#include "BatchedAStarPlanner.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <list>
+#include <stdexcept>
+#include <string>
+
+#include "common/dynamic_obstacles/BinaryDynamicObstaclesManager.h"
+#include "common/dynamic_obstacles/GaussianDynamicObstaclesManager.h"
+#include "common/map/Map.h"
+#include "planner/search/Edge.h"
+#include "planner/search/Vertex.h"
+#include "planner/utilities/Ribbon.h"
+#include "planner/utilities/RibbonManager.h"
+
+// ---- write access to the members Edge::computeTrueCost fills in (Edge.h:132-149, Vertex.h:180-188,
+// RibbonManager.h:184-200) without modifying the reference: explicit template instantiation may
+// name private members ([temp.explicit]/12).
+namespace {
+template <typename Tag, typename Tag::type M>
+struct Access {
+    friend typename Tag::type get(Tag) { return M; }
+};
+#define PPE_ACCESS(Tag, Class, Type, Member)                 \
+    struct Tag { typedef Type Class::*type; friend type get(Tag); }; \
+    template struct Access<Tag, &Class::Member>;
+PPE_ACCESS(EdgeWrapper, Edge, DubinsWrapper, m_DubinsWrapper)
+PPE_ACCESS(EdgeInfeasible, Edge, bool, m_Infeasible)
+PPE_ACCESS(EdgeApprox, Edge, double, m_ApproxCost)
+PPE_ACCESS(EdgeTrue, Edge, double, m_TrueCost)
+PPE_ACCESS(EdgePenalty, Edge, double, m_CollisionPenalty)
+PPE_ACCESS(VertexG, Vertex, double, m_CurrentCost)
+PPE_ACCESS(VertexH, Vertex, double, m_ApproxToGo)
+PPE_ACCESS(RibbonList, RibbonManager, std::list<Ribbon>, m_Ribbons)
+PPE_ACCESS(RibbonHeuristic, RibbonManager, RibbonManager::Heuristic, m_Heuristic)
+PPE_ACCESS(RibbonCct, RibbonManager, double, m_CoverageCompletedTime)
+#undef PPE_ACCESS
+
+int heuristicId(RibbonManager::Heuristic h) {
+    switch (h) {
+        case RibbonManager::MaxDistance: return PPE_H_MAX_DISTANCE;
+        case RibbonManager::TspPointRobotNoSplitAllRibbons: return PPE_H_TSP_POINT_ROBOT_NO_SPLIT_ALL;
+        case RibbonManager::TspPointRobotNoSplitKRibbons: return PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K;
+        case RibbonManager::TspDubinsNoSplitAllRibbons: return PPE_H_TSP_DUBINS_NO_SPLIT_ALL;
+        default: return PPE_H_TSP_DUBINS_NO_SPLIT_K;
+    }
+}
+} // namespace
+
+BatchedAStarPlanner::BatchedAStarPlanner(ppe_ctx* ctx, int knnChunk) : m_Ctx(ctx), m_KnnChunk(knnChunk) {}
+
+void BatchedAStarPlanner::check(int rc, const char* what) {
+    if (rc < 0) throw std::runtime_error(std::string(what) + ": " + ppe_last_error(m_Ctx));
+}
+
+// Read-only world state, once per plan (PlannerConfig is passed by value per plan, Planner.h:50).
+void BatchedAStarPlanner::uploadWorld(const RibbonManager& ribbonManager, const State& start, const PlannerConfig& config) {
+    ppe_config c;
+    c.max_speed = config.maxSpeed();
+    c.slow_speed = config.slowSpeed();
+    c.turning_radius = config.turningRadius();
+    c.coverage_turning_radius = config.coverageTurningRadius();
+    c.time_horizon = config.timeHorizon();
+    c.time_minimum = config.timeMinimum();
+    c.collision_checking_increment = config.collisionCheckingIncrement();
+    c.start_state_time = start.time();                      // AStarPlanner.cpp:16
+    c.ribbon_width = Ribbon::RibbonWidth;
+    c.collision_penalty_factor = Edge::collisionPenaltyFactor();
+    c.time_penalty_factor = Edge::timePenaltyFactor();
+    c.branching_factor = config.branchingFactor();
+    // changeHeuristicIfTooManyRibbons (AStarPlanner.cpp:18, RibbonManager.cpp:381-385)
+    RibbonManager::Heuristic h = ribbonManager.*get(RibbonHeuristic());
+    if (ribbonManager.get().size() > 5) h = RibbonManager::MaxDistance;
+    m_Heuristic = heuristicId(h);
+    c.heuristic = m_Heuristic;
+    check(ppe_set_config(m_Ctx, &c), "ppe_set_config");
+
+    // static map: rasterise Map::isBlocked at cell centres (GridWorldMap cells are res x res squares)
+    const Map::SharedPtr& map = config.map();
+    const double res = map->resolution();
+    const double* ext = map->extremes();
+    if (!(res > 0) || !(ext[1] < 1e300)) {
+        check(ppe_set_map_none(m_Ctx), "ppe_set_map_none");
+    } else {
+        const int cols = (int)std::llround((ext[1] - ext[0]) / res), rows = (int)std::llround((ext[3] - ext[2]) / res);
+        const int stride = (cols + 7) / 8;
+        std::vector<uint8_t> bits((size_t)rows * stride, 0);
+        for (int r = 0; r < rows; r++)
+            for (int cc = 0; cc < cols; cc++)
+                if (map->isBlocked((cc + 0.5) * res, (r + 0.5) * res)) bits[(size_t)r * stride + (cc >> 3)] |= (uint8_t)(1u << (cc & 7));
+        check(ppe_set_map_bitmap(m_Ctx, bits.data(), rows, cols, stride, res), "ppe_set_map_bitmap");
+    }
+
+    // dynamic obstacles in container iteration order (the summation order of collisionExists)
+    const DynamicObstaclesManager* mgr = &config.obstaclesManager();
+    if (auto* b = dynamic_cast<const BinaryDynamicObstaclesManager*>(mgr)) {
+        std::vector<double> x, y, yaw, sp, tm, wd, ln;
+        for (const auto& o : b->get()) {
+            x.push_back(o.second.X); y.push_back(o.second.Y); yaw.push_back(o.second.Yaw); sp.push_back(o.second.Speed);
+            tm.push_back(o.second.Time); wd.push_back(o.second.Width); ln.push_back(o.second.Length);
+        }
+        check(ppe_set_obstacles_binary(m_Ctx, (int)x.size(), x.data(), y.data(), yaw.data(), sp.data(), tm.data(), wd.data(), ln.data()),
+              "ppe_set_obstacles_binary");
+    } else if (auto* g = dynamic_cast<const GaussianDynamicObstaclesManager*>(mgr)) {
+        std::vector<double> x, y, yaw, sp, tm, cov;
+        for (const auto& o : g->get()) {
+            x.push_back(o.second.X); y.push_back(o.second.Y); yaw.push_back(o.second.Yaw); sp.push_back(o.second.Speed);
+            tm.push_back(o.second.Time);
+            cov.push_back(o.second.covariance(0, 0)); cov.push_back(o.second.covariance(0, 1));
+            cov.push_back(o.second.covariance(1, 0)); cov.push_back(o.second.covariance(1, 1));
+        }
+        check(ppe_set_obstacles_gaussian(m_Ctx, (int)x.size(), x.data(), y.data(), yaw.data(), sp.data(), tm.data(), cov.data()),
+              "ppe_set_obstacles_gaussian");
+    } else {
+        check(ppe_set_obstacles_none(m_Ctx), "ppe_set_obstacles_none");
+    }
+    check(ppe_clear_ribbon_sets(m_Ctx), "ppe_clear_ribbon_sets");
+}
+
+Planner::Stats BatchedAStarPlanner::plan(const RibbonManager& ribbonManager, const State& start, PlannerConfig config,
+                                         const DubinsPlan& previousPlan, double timeRemaining) {
+    uploadWorld(ribbonManager, start, config);
+    m_TrueCostEdges = m_DubinsSolves = m_Batches = 0;
+    return AStarPlanner::plan(ribbonManager, start, std::move(config), previousPlan, timeRemaining);
+}
+
+void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, const DynamicObstaclesManager& obstacles) {
+    (void)obstacles;
+    visualizeVertex(sourceVertex, "vertex", true);
+    const State& src = sourceVertex->state();
+    const double inc = m_Config.collisionCheckingIncrement();
+
+    // configurations, SamplingBasedPlanner.cpp:58-63
+    const double speeds[2] = {m_Config.maxSpeed(), m_Config.maxSpeed() == m_Config.slowSpeed() ? -1 : m_Config.slowSpeed()};
+    const int nTurningRadii = 2;
+    const double turningRadii[nTurningRadii] = {m_Config.turningRadius(),
+                                                m_Config.coverageTurningRadius() == m_Config.turningRadius() ? -1 : m_Config.coverageTurningRadius()};
+
+    // intern the parent's ribbon set once; every edge of this expansion refers to it
+    const RibbonManager& parentRibbons = sourceVertex->ribbonManager();
+    m_RibbonBuf.clear();
+    for (const auto& r : parentRibbons.get()) {
+        m_RibbonBuf.push_back(r.start().first); m_RibbonBuf.push_back(r.start().second);
+        m_RibbonBuf.push_back(r.end().first); m_RibbonBuf.push_back(r.end().second);
+    }
+    int32_t setId = -1;
+    check(ppe_put_ribbon_set(m_Ctx, (int)(m_RibbonBuf.size() / 4), m_RibbonBuf.data(), parentRibbons.coverageCompletedTime(), &setId),
+          "ppe_put_ribbon_set");
+
+    m_Edges.clear();
+    auto baseEdge = [&]() {
+        ppe_edge e;
+        std::memset(&e, 0, sizeof e);
+        e.src[0] = src.x(); e.src[1] = src.y(); e.src[2] = src.heading(); e.src[3] = src.speed(); e.src[4] = src.time();
+        e.src_g = sourceVertex->currentCost();
+        e.ribbon_set = setId;
+        return e;
+    };
+
+    // (a) nearest ribbon endpoint, :65-81 -- path-less edges, the engine solves them (Edge.cpp:78-80)
+    if (!sourceVertex->done()) {
+        auto s = sourceVertex->getNearestPointAsState();
+        if (src.distanceTo(s) > inc) {
+            for (double speed : speeds) {
+                if (speed <= 0) continue;
+                for (double turningRadius : turningRadii) {
+                    if (turningRadius <= 0) continue;
+                    ppe_edge e = baseEdge();
+                    e.dst[0] = s.x(); e.dst[1] = s.y(); e.dst[2] = s.heading(); e.dst[3] = speed;
+                    e.has_path = 0;
+                    e.coverage_allowed = turningRadius == m_Config.coverageTurningRadius();
+                    m_Edges.push_back(e);
+                }
+            }
+        }
+    }
+    const size_t nEndpointEdges = m_Edges.size();
+
+    // (b) k nearest samples by Dubins distance, :83-133.  Same heap operations on m_Samples as the
+    // reference; the Dubins solves of the next `m_KnnChunk` samples in Euclidean order go to K1
+    // in one launch, found by popping a scratch copy of the heap.
+    auto comp = [&](const State& s1, const State& s2) { return s1.distanceTo(src) > s2.distanceTo(src); };
+    auto dubinsComp = [](const Candidate& a, const Candidate& b) { return a.approxCost < b.approxCost; };
+    std::make_heap(m_Samples.begin(), m_Samples.end(), comp);
+    m_Scratch = m_Samples;
+    std::vector<Candidate> bestSamplesHeaps[nTurningRadii];
+    bool doneChecks[nTurningRadii] = {false, false};
+    const size_t nSamples = m_Samples.size();
+    const size_t kBranch = (size_t)k();
+    size_t pops = 0; // how many samples the reference's loop has consumed
+    size_t scratchPopped = 0;
+    std::vector<State> chunk;
+    while (pops < nSamples && (!doneChecks[0] || !doneChecks[1])) {
+        // next chunk of samples in Euclidean order
+        chunk.clear();
+        const size_t want = std::min<size_t>((size_t)m_KnnChunk, nSamples - scratchPopped);
+        for (size_t c = 0; c < want; c++) {
+            chunk.push_back(m_Scratch.front());
+            std::pop_heap(m_Scratch.begin(), m_Scratch.end() - scratchPopped, comp);
+            scratchPopped++;
+        }
+        // K1: src -> sample at every radius in use
+        const size_t m = chunk.size();
+        m_Q0.resize(6 * m); m_Q1.resize(6 * m); m_Rho.resize(2 * m);
+        m_Param.resize(6 * m); m_Length.resize(2 * m); m_Type.resize(2 * m); m_Err.resize(2 * m);
+        size_t nq = 0;
+        std::vector<long> slot(2 * m, -1);
+        for (size_t c = 0; c < m; c++)
+            for (int j = 0; j < nTurningRadii; j++) {
+                if (turningRadii[j] <= 0 || doneChecks[j]) continue;
+                m_Q0[3 * nq] = src.x(); m_Q0[3 * nq + 1] = src.y(); m_Q0[3 * nq + 2] = src.yaw();
+                m_Q1[3 * nq] = chunk[c].x(); m_Q1[3 * nq + 1] = chunk[c].y(); m_Q1[3 * nq + 2] = chunk[c].yaw();
+                m_Rho[nq] = turningRadii[j];
+                slot[2 * c + j] = (long)nq++;
+            }
+        if (nq) {
+            check(ppe_dubins_batch(m_Ctx, (int64_t)nq, m_Q0.data(), m_Q1.data(), m_Rho.data(), m_Type.data(), m_Param.data(),
+                                   m_Length.data(), m_Err.data()), "ppe_dubins_batch");
+            m_DubinsSolves += (long)nq;
+            m_Batches++;
+        }
+        // replay of the reference's loop body over this chunk
+        for (size_t c = 0; c < m && (!doneChecks[0] || !doneChecks[1]); c++) {
+            State sample = chunk[c];
+            pops++;
+            for (int j = 0; j < nTurningRadii; j++) {
+                if (doneChecks[j]) continue;
+                const double turningRadius = turningRadii[j];
+                if (turningRadius <= 0) { doneChecks[j] = true; continue; }
+                auto& bestSamples = bestSamplesHeaps[j];
+                if (bestSamples.size() < kBranch || bestSamples.front().length > sample.distanceTo(src)) {
+                    if (src.distanceTo(sample) > inc) {
+                        sample.speed() = m_Config.maxSpeed();
+                        const long q = slot[2 * c + j];
+                        Candidate cand;
+                        cand.sample = sample;
+                        cand.coverageAllowed = turningRadius == m_Config.coverageTurningRadius();
+                        cand.path[0] = m_Q0[3 * q]; cand.path[1] = m_Q0[3 * q + 1]; cand.path[2] = m_Q0[3 * q + 2];
+                        cand.path[3] = m_Param[3 * q]; cand.path[4] = m_Param[3 * q + 1]; cand.path[5] = m_Param[3 * q + 2];
+                        cand.path[6] = turningRadius;
+                        cand.type = m_Type[q];
+                        cand.length = m_Length[q];
+                        // Edge::computeApproxCost(): length / end speed (= max speed) * timePenaltyFactor, Edge.cpp:11-20,64-66
+                        cand.approxCost = cand.length / sample.speed() * Edge::timePenaltyFactor();
+                        bestSamples.push_back(cand);
+                        std::push_heap(bestSamples.begin(), bestSamples.end(), dubinsComp);
+                        if (bestSamples.size() > kBranch) {
+                            std::pop_heap(bestSamples.begin(), bestSamples.end(), dubinsComp);
+                            bestSamples.pop_back();
+                        }
+                    }
+                } else {
+                    doneChecks[j] = true;
+                }
+            }
+        }
+    }
+    // leave m_Samples exactly as the reference's pops would
+    for (size_t i = 0; i < pops; i++) std::pop_heap(m_Samples.begin(), m_Samples.end() - i, comp);
+
+    // (c) winners x speeds, :134-149 -- wrapper reused, speed set per edge
+    struct Winner { const Candidate* cand; double speed; };
+    std::vector<Winner> winners;
+    for (auto& bestSamples : bestSamplesHeaps) {
+        if (bestSamples.size() > kBranch) throw std::runtime_error("Somehow got too many samples in the heap");
+        for (auto& cand : bestSamples) {
+            for (double speed : speeds) {
+                if (speed <= 0) continue;
+                ppe_edge e = baseEdge();
+                e.has_path = 1;
+                e.path_qi[0] = cand.path[0]; e.path_qi[1] = cand.path[1]; e.path_qi[2] = cand.path[2];
+                e.path_param[0] = cand.path[3]; e.path_param[1] = cand.path[4]; e.path_param[2] = cand.path[5];
+                e.path_rho = cand.path[6];
+                e.path_type = cand.type;
+                e.w_speed = speed;                          // wrapper.setSpeed(speed)
+                e.w_start_time = src.time();                // DubinsWrapper::set, DubinsWrapper.cpp:15
+                e.w_end_time = src.time() + cand.length / speed; // setEndTime, DubinsWrapper.cpp:96-98
+                e.dst[0] = cand.sample.x(); e.dst[1] = cand.sample.y(); e.dst[2] = cand.sample.heading(); e.dst[3] = speed;
+                e.coverage_allowed = cand.coverageAllowed;
+                m_Edges.push_back(e);
+                winners.push_back(Winner{&cand, speed});
+            }
+        }
+    }
+
+    // ---- one K2 launch for the whole expansion ---------------------------------------------------------
+    m_Results.resize(m_Edges.size());
+    if (!m_Edges.empty()) {
+        check(ppe_true_cost_batch(m_Ctx, (int64_t)m_Edges.size(), m_Edges.data(), m_Results.data()), "ppe_true_cost_batch");
+        m_TrueCostEdges += (long)m_Edges.size();
+        m_Batches++;
+    }
+
+    // ---- hand the results back through the reference's own objects, in the reference's push order ------
+    for (size_t i = 0; i < m_Edges.size(); i++) {
+        const ppe_edge& e = m_Edges[i];
+        const ppe_edge_result& r = m_Results[i];
+        if (r.status != PPE_EDGE_OK)
+            throw std::runtime_error("edge evaluation failed where the reference throws (status " + std::to_string(r.status) + ")");
+        State end(r.end[0], r.end[1], r.end[2], r.end[3], r.end[4]);
+        const double rho = e.coverage_allowed ? m_Config.coverageTurningRadius() : m_Config.turningRadius();
+        auto v = Vertex::connect(sourceVertex, end, rho, e.coverage_allowed != 0);
+        Edge& edge = *v->parentEdge();
+        // Edge members written by computeTrueCost (Edge.cpp:177-199)
+        DubinsPath p;
+        p.qi[0] = r.path_qi[0]; p.qi[1] = r.path_qi[1]; p.qi[2] = r.path_qi[2];
+        p.param[0] = r.path_param[0]; p.param[1] = r.path_param[1]; p.param[2] = r.path_param[2];
+        p.rho = r.path_rho; p.type = (DubinsPathType)r.path_type;
+        DubinsWrapper w;
+        w.fill(p, r.w_speed, r.w_start_time);
+        if (r.w_end_time < w.getEndTime()) w.updateEndTime(r.w_end_time);
+        edge.*get(EdgeWrapper()) = w;
+        edge.*get(EdgeInfeasible()) = r.infeasible != 0;
+        edge.*get(EdgeApprox()) = r.approx_cost;
+        edge.*get(EdgeTrue()) = r.true_cost;
+        edge.*get(EdgePenalty()) = r.collision_penalty;
+        // Vertex members (Vertex.cpp:102-104, :49-64)
+        (*v).*get(VertexG()) = r.g;
+        RibbonManager& rm = v->ribbonManager();
+        if (r.ribbons_changed) {
+            m_RibbonBuf.resize((size_t)std::max(1, r.n_ribbons_after) * 4);
+            const int n = ppe_get_ribbons_after(m_Ctx, (int64_t)i, m_RibbonBuf.data(), r.n_ribbons_after);
+            check(n, "ppe_get_ribbons_after");
+            std::list<Ribbon>& list = rm.*get(RibbonList());
+            list.clear();
+            for (int k2 = 0; k2 < n; k2++)
+                list.emplace_back(m_RibbonBuf[4 * k2], m_RibbonBuf[4 * k2 + 1], m_RibbonBuf[4 * k2 + 2], m_RibbonBuf[4 * k2 + 3]);
+        }
+        rm.*get(RibbonCct()) = r.coverage_completed_time;
+        if (m_Heuristic == PPE_H_MAX_DISTANCE) (*v).*get(VertexH()) = r.h;
+        else v->computeApproxToGo(m_Config); // TSP heuristics stay on the host (RibbonManager.cpp:53-140)
+        pushVertexQueue(v);
+    }
+    (void)nEndpointEdges;
+    m_Stats.Expanded++;
+}

@@ -1,0 +1,65 @@
+// BatchedAStarPlanner -- the reference's anytime A* planner with its expansion loop restructured
+// to emit whole edge batches into the B200 edge engine (include/ppe.h).
+//
+// Drop-in: it IS an AStarPlanner (path_planner/src/planner/AStarPlanner.h); only the virtual
+//   SamplingBasedPlanner::expand (SamplingBasedPlanner.h:43, SamplingBasedPlanner.cpp:52-151)
+// is overridden, plus a thin plan() wrapper that uploads the read-only world state once per plan.
+// Planner::Stats, tracePlan, pushVertexQueue, goalCondition, the open list and the anytime loop
+// of AStarPlanner::plan are the reference's own code, untouched.
+//
+// Compiles against the reference headers where they lie (-I<ref>/path_planner/src
+// -I<ref>/path_planner_common/include) and any dubins.h; links libppe.so.
+#ifndef PPE_BATCHED_ASTAR_PLANNER_H
+#define PPE_BATCHED_ASTAR_PLANNER_H
+
+#include <vector>
+
+#include "planner/AStarPlanner.h"
+#include "ppe.h"
+
+class BatchedAStarPlanner : public AStarPlanner {
+public:
+    // `ctx` is borrowed (one ppe_ctx per planning thread); `knnChunk` = how many nearest samples
+    // (Euclidean order) get their Dubins paths solved per K1 launch while replaying the
+    // reference's k-nearest selection.
+    explicit BatchedAStarPlanner(ppe_ctx* ctx, int knnChunk = 128);
+    ~BatchedAStarPlanner() override = default;
+
+    Stats plan(const RibbonManager& ribbonManager, const State& start, PlannerConfig config,
+               const DubinsPlan& previousPlan, double timeRemaining) override;
+
+    void expand(const std::shared_ptr<Vertex>& sourceVertex, const DynamicObstaclesManager& obstacles) override;
+
+    // instrumentation
+    long trueCostEdges() const { return m_TrueCostEdges; }
+    long dubinsSolves() const { return m_DubinsSolves; }
+    long batches() const { return m_Batches; }
+
+private:
+    struct Candidate {
+        State sample;          // destination state (speed = max speed)
+        double path[7];        // qi[3], param[3], rho
+        int type;
+        double length;         // dubins_path_length
+        double approxCost;     // Edge::approxCost() of the candidate edge
+        bool coverageAllowed;
+    };
+
+    void uploadWorld(const RibbonManager& ribbonManager, const State& start, const PlannerConfig& config);
+    void check(int rc, const char* what);
+
+    ppe_ctx* m_Ctx;
+    int m_KnnChunk;
+    int m_Heuristic = PPE_H_MAX_DISTANCE;
+    long m_TrueCostEdges = 0, m_DubinsSolves = 0, m_Batches = 0;
+
+    // scratch reused across expansions
+    std::vector<State> m_Scratch;
+    std::vector<double> m_Q0, m_Q1, m_Rho, m_Param, m_Length;
+    std::vector<int32_t> m_Type, m_Err;
+    std::vector<ppe_edge> m_Edges;
+    std::vector<ppe_edge_result> m_Results;
+    std::vector<double> m_RibbonBuf;
+};
+
+#endif

@@ -156,8 +156,10 @@ int ppe_set_obstacles_gaussian(ppe_ctx* ctx, int n, const double* x, const doubl
                                const double* speed, const double* time, const double* cov);
 
 /* RibbonManager state of a parent vertex (RibbonManager::get() in list order, 4 doubles per
- * ribbon: startX, startY, endX, endY) + coverageCompletedTime.  Sets are interned: every edge
- * leaving that vertex refers to the returned id. */
+ * ribbon: startX, startY, endX, endY) + coverageCompletedTime.  The list is taken verbatim, as a
+ * child vertex copies its parent's (Vertex.cpp:24,32): the covered-filter of RibbonManager::add
+ * (RibbonManager.cpp:154-158) is the caller's.  Sets are interned: every edge leaving that vertex
+ * refers to the returned id. */
 int ppe_put_ribbon_set(ppe_ctx* ctx, int n, const double* xyxy, double coverage_completed_time,
                        int32_t* set_id);
 int ppe_clear_ribbon_sets(ppe_ctx* ctx);

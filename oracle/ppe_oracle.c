@@ -530,8 +530,8 @@ int oracle_put_ribbon_set(oracle_ctx* c, int n, const double* xyxy, double cct, 
     for (i = 0; i < n; i++) {
         rib_t rb;
         rb.sx = xyxy[4 * i]; rb.sy = xyxy[4 * i + 1]; rb.ex = xyxy[4 * i + 2]; rb.ey = xyxy[4 * i + 3];
-        /* RibbonManager::add(x1,y1,x2,y2) -> add(r, end, strict=false) drops covered ribbons, RibbonManager.cpp:7-12,154-158 */
-        if (rib_covered(&rb, 0, c->cfg.ribbon_width)) continue;
+        /* verbatim: a child vertex copies its parent's list (Vertex.cpp:24,32); the covered-filter of
+         * RibbonManager::add (RibbonManager.cpp:154-158) has been applied by whoever built the list */
         s->r[s->n++] = rb;
     }
     s->cct = cct;

@@ -41,9 +41,11 @@ struct Rob {
 };
 struct VertexCurrentCost { typedef double Vertex::*type; friend type get(VertexCurrentCost); };
 struct EdgeApproxCost { typedef double Edge::*type; friend type get(EdgeApproxCost); };
+struct ManagerRibbons { typedef std::list<Ribbon> RibbonManager::*type; friend type get(ManagerRibbons); };
 }
 template struct Rob<VertexCurrentCost, &Vertex::m_CurrentCost>;
 template struct Rob<EdgeApproxCost, &Edge::m_ApproxCost>;
+template struct Rob<ManagerRibbons, &RibbonManager::m_Ribbons>;
 
 #include "ref_shim.h"
 
@@ -194,10 +196,10 @@ int ref_get_obstacles(ref_ctx* ctx, double* out, int cap) {
 
 int ref_put_ribbon_set(ref_ctx* ctx, int n, const double* xyxy, double coverageCompletedTime, int32_t* id) {
     RibbonManager m(heuristicOf(ctx->cfg.heuristic), ctx->cfg.turning_radius, 2);
-    for (int i = 0; i < n; i++) {
-        // RibbonManager::add drops ribbons that are already "covered" (RibbonManager.cpp:154-158)
-        m.add(xyxy[4 * i], xyxy[4 * i + 1], xyxy[4 * i + 2], xyxy[4 * i + 3]);
-    }
+    // verbatim list, as a child vertex copies its parent's (Vertex.cpp:24,32); RibbonManager::add would
+    // drop ribbons shorter than 2 * RibbonWidth (RibbonManager.cpp:154-158) that a strict cover keeps
+    std::list<Ribbon>& list = m.*get(ManagerRibbons());
+    for (int i = 0; i < n; i++) list.emplace_back(xyxy[4 * i], xyxy[4 * i + 1], xyxy[4 * i + 2], xyxy[4 * i + 3]);
     if (coverageCompletedTime != -1) m.setCoverageCompletedTime(coverageCompletedTime);
     ctx->sets.push_back(m);
     *id = (int32_t)ctx->sets.size() - 1;

@@ -348,19 +348,12 @@ int ppe_set_obstacles_gaussian(ppe_ctx* ctx, int n, const double* x, const doubl
 int ppe_put_ribbon_set(ppe_ctx* ctx, int n, const double* xyxy, double coverage_completed_time, int32_t* set_id) {
     if (!ctx || n < 0 || (n > 0 && !xyxy) || !set_id) return fail(ctx, PPE_ERR_INVALID, "ppe_put_ribbon_set: bad arguments");
     if (!ctx->have_cfg) return fail(ctx, PPE_ERR_STATE, "ppe_set_config must precede ppe_put_ribbon_set (ribbon width)");
-    const double W = ctx->cfg.ribbon_width;
     const int off = (int)(ctx->h_ribbons.size() / 4);
-    int kept = 0;
-    for (int i = 0; i < n; i++) {
-        const double sx = xyxy[4 * i], sy = xyxy[4 * i + 1], ex = xyxy[4 * i + 2], ey = xyxy[4 * i + 3];
-        // RibbonManager::add drops ribbons that are already covered (RibbonManager.cpp:7-12,154-158)
-        const double sq = (ex - sx) * (ex - sx) + (ey - sy) * (ey - sy);
-        const double minLength = 2 * W;
-        if (sq < minLength * minLength / 1) continue;
-        ctx->h_ribbons.push_back(sx); ctx->h_ribbons.push_back(sy);
-        ctx->h_ribbons.push_back(ex); ctx->h_ribbons.push_back(ey);
-        kept++;
-    }
+    // verbatim, in list order: a child vertex copies its parent's list (Vertex.cpp:24,32).  The
+    // covered-filter of RibbonManager::add (RibbonManager.cpp:154-158) is NOT applied here -- a strict
+    // cover keeps remainders shorter than 2 * RibbonWidth that add() would drop.
+    ctx->h_ribbons.insert(ctx->h_ribbons.end(), xyxy, xyxy + (size_t)4 * n);
+    const int kept = n;
     if (ribbon_cap_for(kept) > 512) {
         ctx->h_ribbons.resize((size_t)off * 4);
         return fail(ctx, PPE_ERR_CAPACITY, "ribbon set larger than the per-edge device working set (480 ribbons)");

@@ -123,3 +123,44 @@ def describe(bad, got, want, limit=3):
         for i in idx[:limit]:
             lines.append("   [%d] got %s want %s" % (i, got[name][i], want[name][i]))
     return "\n".join(lines)
+
+
+# ---- whole-plan runs: the reference's AStarPlanner and the product's BatchedAStarPlanner --------------
+HARNESS_SO = os.path.join(ORACLE_DIR, "_ref", "libppe_harness.so")
+PLAN_STATS = ("samples", "generated", "expanded", "iterations", "f", "collision_penalty", "time_penalty", "h", "depth",
+              "now_calls", "true_cost_edges", "dubins_solves", "batches")
+
+
+def have_harness():
+    return os.path.exists(HARNESS_SO)
+
+
+def load_harness(path=None):
+    """libppe_harness.so = the compiled reference objects + ref_shim + the product's C++ host adapter
+    (path_planner_b200/harness/BatchedAStarPlanner.cpp) linked against libppe.so.  One ref_ctx holds the
+    world both planners read, so `ref_plan` and `harness_plan` see identical inputs."""
+    w = _load(path or HARNESS_SO, "ref_")
+    D = C.POINTER(C.c_double)
+    w.lib.ref_get_obstacles.argtypes = [C.c_void_p, D, C.c_int]
+    w.lib.ref_plan.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D, C.c_int, D]
+    w.lib.harness_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                   C.c_int, D, C.c_int, D]
+    return w
+
+
+def run_plan(w, which, ribbon_set, start, time_remaining, clock0, tick, initial_samples=100, brown=0, knn_chunk=128,
+             device=0, cap=256):
+    """which = "ref" (AStarPlanner) or "harness" (BatchedAStarPlanner on `device`).  tick > 0 selects the
+    virtual clock (now() = clock0 + calls * tick).  Returns (plan [n,12], stats dict)."""
+    start = np.ascontiguousarray(start, dtype=np.float64)
+    plan = np.zeros((cap, 12))
+    stats = np.zeros(13)
+    if which == "ref":
+        n = w.lib.ref_plan(w.ctx, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples, brown,
+                           abi.dptr(plan), cap, abi.dptr(stats))
+    else:
+        n = w.lib.harness_plan(w.ctx, device, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples,
+                               brown, knn_chunk, abi.dptr(plan), cap, abi.dptr(stats))
+    if n < 0:
+        raise RuntimeError("%s plan failed (%d): %s" % (which, n, (w.lib.ref_last_error(w.ctx) or b"").decode()))
+    return plan[:min(n, cap)].copy(), dict(zip(PLAN_STATS, stats.tolist()))

@@ -1,0 +1,50 @@
+"""Whole-plan parity cases shared by tests/test_harness_host_logic.py (CPU, evaluator = oracle test
+double, plans must be BIT-identical) and tests/test_gpu_plan.py (B200, evaluator = the CUDA engine,
+words/counters identical, continuous fields within 1e-9).  Every case is one Planner::plan call of
+the reference's AStarPlanner and of the product's BatchedAStarPlanner on the same world, start
+state and virtual clock (PlannerConfig::setNowFunction, PlannerConfig.h:110)."""
+import numpy as np
+
+from path_planner_b200 import synth
+from tests import common
+
+COUNTERS = ("samples", "generated", "expanded", "iterations", "depth", "now_calls")
+VALUES = ("f", "collision_penalty", "time_penalty", "h")
+
+# name, world factory key, start (None = world.start), budget s, tick s, initial samples
+CASES = [
+    ("c1-single-ribbon", "c1", None, 0.95, 5e-4, 100),            # BASELINE configs[0] (test_planner.cpp:1276-1286)
+    ("c2-default-start", "c2", None, 0.95, 2e-3, 100),            # BASELINE configs[1]
+    ("c2-near-ribbons", "c2", (395.0, 390.0, 0.3, 2.5, 1.0), 0.95, 2e-3, 100),
+    ("c2-deep-anytime", "c2", (470.0, 610.0, 3.0, 2.5, 1.0), 0.95, 6e-3, 100),   # 15 iterations, 714k samples
+    ("c2-late-start", "c2", (505.0, 500.0, 1.0, 2.5, 7.0), 0.95, 2e-3, 100),
+    ("c3-gaussian", "c3", (420.0, 395.0, 0.0, 2.5, 1.0), 0.95, 4e-3, 100),       # BASELINE configs[2]
+    ("c3-binary", "c3b", (420.0, 395.0, 0.0, 2.5, 1.0), 0.95, 4e-3, 100),
+    ("c4-10k-samples", "c4", None, 0.95, 0.12, 10000),            # BASELINE configs[3]
+]
+CASE_IDS = [c[0] for c in CASES]
+
+
+def compare(lib, case, exact, knn_chunk=128, clock0=1000.0):
+    """Runs both planners; asserts plan identity.  Returns (harness stats, reference plan)."""
+    _, wname, start, budget, tick, initial = case
+    world = synth.WORLDS[wname]()
+    start = world.start if start is None else np.array(start, dtype=np.float64)
+    sid = world.upload_ref(lib)
+    want_plan, want = common.run_plan(lib, "ref", sid, start, budget, clock0, tick, initial)
+    got_plan, got = common.run_plan(lib, "harness", sid, start, budget, clock0, tick, initial, knn_chunk=knn_chunk)
+    for k in COUNTERS:
+        assert got[k] == want[k], (k, got, want)
+    assert got_plan.shape == want_plan.shape
+    if exact:
+        for k in VALUES:
+            assert got[k] == want[k], (k, got, want)
+        assert np.array_equal(got_plan, want_plan), (got_plan, want_plan)
+    else:
+        for k in VALUES:
+            assert np.isclose(got[k], want[k], rtol=common.RTOL, atol=common.ATOL), (k, got, want)
+        assert np.array_equal(got_plan[:, 7], want_plan[:, 7]), "Dubins words differ"
+        assert np.array_equal(got_plan[:, 6], want_plan[:, 6]), "radii differ"
+        assert np.allclose(got_plan, want_plan, rtol=common.RTOL, atol=common.ATOL), (got_plan, want_plan)
+    assert got["true_cost_edges"] > 0 and got["batches"] > 0
+    return got, want_plan

@@ -1,0 +1,36 @@
+"""Host logic of the C++ adapter (path_planner_b200/harness/BatchedAStarPlanner.cpp) without a GPU.
+
+oracle/_ref/libppe_harness_cpu.so links the adapter against a TEST DOUBLE of the C ABI
+(oracle/ppe_on_oracle.c: ppe_* forwarded to the CPU oracle, which is bit-identical to the compiled
+reference).  With a bit-identical evaluator behind it, everything the adapter does on the host --
+batch assembly for the three call sites of SamplingBasedPlanner::expand (:76, :119, :145), the
+replay of the Euclid / Dubins heaps, ribbon-set interning, handing results back through the
+reference's Edge / Vertex members in push order -- must reproduce the reference's plan BIT FOR BIT,
+together with its Samples / Generated / Expanded / Iterations counters."""
+import numpy as np
+import pytest
+
+from tests import common, plan_cases
+
+CPU_SO = common.HARNESS_SO.replace("libppe_harness.so", "libppe_harness_cpu.so")
+pytestmark = pytest.mark.skipif(not __import__("os").path.exists(CPU_SO),
+                                reason="oracle/_ref/libppe_harness_cpu.so not built (needs /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return common.load_harness(CPU_SO)
+
+
+@pytest.mark.parametrize("case", plan_cases.CASES, ids=plan_cases.CASE_IDS)
+def test_batched_planner_reproduces_the_reference_plan_bit_for_bit(lib, case):
+    got, plan = plan_cases.compare(lib, case, exact=True)
+    assert got["expanded"] >= 2
+
+
+def test_knn_chunk_only_changes_the_launch_count(lib):
+    case = plan_cases.CASES[0][:4] + (2e-3, 100)
+    a, plan_a = plan_cases.compare(lib, case, exact=True, knn_chunk=16)
+    b, plan_b = plan_cases.compare(lib, case, exact=True, knn_chunk=512)
+    assert np.array_equal(plan_a, plan_b)
+    assert a["dubins_solves"] < b["dubins_solves"] and a["batches"] > b["batches"]

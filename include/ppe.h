@@ -125,7 +125,7 @@ typedef struct {
     int32_t n_checkpoints;      /* executions of the ribbon branch (Edge.cpp:155-171) */
     int32_t n_ribbons_after;    /* size of end()->ribbonManager().get() after the call */
     int32_t ribbons_changed;    /* 0: identical to the parent's set                   */
-    int32_t reserved;
+    int32_t reserved;           /* engine instrumentation: 32-sample chunks skipped by the culling probe */
 } ppe_edge_result;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

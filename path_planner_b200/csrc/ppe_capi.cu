@@ -29,8 +29,12 @@ struct ppe_ctx {
 
     // static map
     uint32_t* d_map = nullptr;
+    uint32_t* d_safe = nullptr;     // dilated free-space bitmap for chunk culling (built lazily per config)
+    uint32_t* d_safe_tmp = nullptr;
+    int safe_radius = -1;           // radius d_safe was built for; -1 = stale
     int map_kind = kMapNone, rows = 0, cols = 0, stride_words = 0;
     double resolution = 1;
+    int obs_cull_ok = 1;
 
     // dynamic obstacles
     ObstacleD* d_obs = nullptr;
@@ -170,6 +174,29 @@ int make_world(ppe_ctx* ctx, WorldD* w) {
         rc = ensure_pool(ctx, want);
         if (rc != PPE_OK) return rc;
     }
+    // chunk culling: a probe sample whose cell has every neighbour within `radius` cells free proves that the
+    // other samples of its chunk (at most half a chunk of arc length away) are free and in bounds too
+    const uint32_t* safe = nullptr;
+    if (ctx->map_kind == kMapBitmap) {
+        const double reach = 0.5 * true_cost_chunk_samples() * ctx->cfg.collision_checking_increment * 1.001 + 1e-6;
+        const double cells = floor(reach / ctx->resolution);
+        if (cells <= 62) {
+            const int radius = (int)cells + 2; // +1: position inside the cell, +1: rounding of x / res at a cell edge
+            if (radius != ctx->safe_radius) {
+                const size_t words = (size_t)ctx->rows * ctx->stride_words;
+                if (!ctx->d_safe) {
+                    PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_safe, words * sizeof(uint32_t)));
+                    PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_safe_tmp, words * sizeof(uint32_t)));
+                }
+                PPE_CUDA(ctx, launch_safe_map(ctx->d_map, ctx->d_safe_tmp, ctx->d_safe, ctx->rows, ctx->cols, ctx->stride_words,
+                                              radius, ctx->stream));
+                PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                ctx->launches += 2;
+                ctx->safe_radius = radius;
+            }
+            safe = ctx->d_safe;
+        }
+    }
     memset(w, 0, sizeof *w);
     w->cfg = ctx->cfg;
     w->dt = ctx->cfg.collision_checking_increment / ctx->cfg.max_speed;
@@ -178,6 +205,14 @@ int make_world(ppe_ctx* ctx, WorldD* w) {
     w->map_kind = ctx->map_kind;
     w->rows = ctx->rows; w->cols = ctx->cols; w->stride_words = ctx->stride_words;
     w->resolution = ctx->resolution;
+    w->safe_bits = safe;
+    {
+        int e = 0;
+        const double m = frexp(ctx->resolution, &e);
+        w->res_pow2 = (m == 0.5 && e > -1000 && e < 1000) ? 1 : 0;
+        w->inv_resolution = 1.0 / ctx->resolution;
+    }
+    w->obs_cull_ok = ctx->obs_cull_ok;
     w->obstacles = ctx->d_obs;
     w->obs_kind = ctx->n_obs > 0 ? ctx->obs_kind : kObsNone;
     w->n_obs = ctx->obs_kind == kObsNone ? 0 : ctx->n_obs;
@@ -232,7 +267,7 @@ void ppe_destroy(ppe_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_map); cudaFree(ctx->d_obs);
+    cudaFree(ctx->d_map); cudaFree(ctx->d_safe); cudaFree(ctx->d_safe_tmp); cudaFree(ctx->d_obs);
     cudaFree(ctx->d_ribbons); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct);
     cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_prepared); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
@@ -276,6 +311,10 @@ int ppe_set_map_bitmap(ppe_ctx* ctx, const uint8_t* bits, int rows, int cols, in
     }
     if (ctx->d_map) PPE_CUDA(ctx, cudaFree(ctx->d_map));
     ctx->d_map = nullptr;
+    if (ctx->d_safe) PPE_CUDA(ctx, cudaFree(ctx->d_safe));
+    if (ctx->d_safe_tmp) PPE_CUDA(ctx, cudaFree(ctx->d_safe_tmp));
+    ctx->d_safe = ctx->d_safe_tmp = nullptr;
+    ctx->safe_radius = -1;
     PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_map, packed.size() * sizeof(uint32_t)));
     PPE_CUDA(ctx, cudaMemcpy(ctx->d_map, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->map_kind = kMapBitmap;
@@ -300,6 +339,10 @@ static int upload_obstacles(ppe_ctx* ctx, const std::vector<ObstacleD>& h, int k
     }
     ctx->obs_kind = kind;
     ctx->n_obs = (int)h.size();
+    // the chunk bound needs a 64-bit candidate mask and, for Gaussians, a norm induced by the quadratic form
+    ctx->obs_cull_ok = h.size() <= 64;
+    for (const ObstacleD& o : h)
+        if (!(o.cull >= 0) || !isfinite(o.cull)) ctx->obs_cull_ok = 0;
     return PPE_OK;
 }
 
@@ -315,6 +358,7 @@ int ppe_set_obstacles_binary(ppe_ctx* ctx, int n, const double* x, const double*
         o.cosYaw = cos(yaw[i]); o.sinYaw = sin(yaw[i]);
         o.a = (length[i] + 2) / 2; // strict: Length += 2, then `fabs(rotatedX) < Length / 2`
         o.b = (width[i] + 2) / 2;
+        o.cull = 0;
     }
     return upload_obstacles(ctx, h, kObsBinary);
 }
@@ -341,6 +385,16 @@ int ppe_set_obstacles_gaussian(ppe_ctx* ctx, int n, const double* x, const doubl
         o.d = c00 * invdet;   // i11
         const double twoPi = 2 * M_PI;
         o.norm = 1.0 / twoPi / sqrt(det);
+        // q(v) = a v0^2 + (b + c) v0 v1 + d v1^2; with S = its symmetric matrix positive definite, sqrt(q) is a norm
+        // and |sqrt(q(v + e)) - sqrt(q(v))| <= sqrt(lambda_max(S)) |e|.  Otherwise no bound (cull = -1).
+        const double s01 = 0.5 * (o.b + o.c);
+        const double tr = o.a + o.d, dt_ = o.a * o.d - s01 * s01;
+        if (o.a > 0 && dt_ > 0 && isfinite(o.norm) && o.norm > 0) {
+            const double lmax = 0.5 * tr + sqrt(fmax(0.25 * tr * tr - dt_, 0.0));
+            o.cull = sqrt(lmax) * (1 + 1e-9);
+        } else {
+            o.cull = -1;
+        }
     }
     return upload_obstacles(ctx, h, kObsGaussian);
 }

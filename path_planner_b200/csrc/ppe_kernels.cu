@@ -24,11 +24,12 @@ namespace ppe {
 namespace {
 
 #ifndef PPE_K2_MIN_BLOCKS
-#define PPE_K2_MIN_BLOCKS 2
+#define PPE_K2_MIN_BLOCKS 4
 #endif
 constexpr int kWarpsPerBlock = 4;
 constexpr int kBlockThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kChunk = 32; // samples per chunk of the K2b walker = one per lane
 constexpr int kSkipCap = 1 << 28;
 constexpr int kMaxSamples = 1 << 22;
 
@@ -66,56 +67,97 @@ __device__ __forceinline__ double4 pack_ribbon(double sx, double sy, double ex, 
 
 // Map::isBlocked (Map.cpp:4-6) / GridWorldMap::isBlocked (GridWorldMap.cpp:84-93).  The bitmap
 // (<= 2 MiB at 4096^2) stays L2/L1 resident; consecutive lanes are consecutive 0.05 m samples, so
-// a warp's 32 lookups fall into one or two 32-byte sectors.
+// a warp's 32 lookups fall into one or two 32-byte sectors.  x / res is a multiplication by the
+// exact reciprocal when the resolution is a power of two (bit-identical quotient), else a division.
+__device__ __forceinline__ bool map_cell(const WorldD& w, double x, double y, unsigned long long* r, unsigned long long* c) {
+    double qx, qy;
+    if (w.res_pow2) { qx = x * w.inv_resolution; qy = y * w.inv_resolution; }
+    else { qx = x / w.resolution; qy = y / w.resolution; }
+    if (x < 0 || qx >= (double)w.cols) return false;
+    if (y < 0 || qy >= (double)w.rows) return false;
+    *r = (unsigned long long)qy;
+    *c = (unsigned long long)qx;
+    return true;
+}
+
 __device__ __forceinline__ bool map_blocked(const WorldD& w, double x, double y) {
     if (w.map_kind == kMapNone) return false;
-    if (x < 0 || x / w.resolution >= (double)w.cols) return true;
-    if (y < 0 || y / w.resolution >= (double)w.rows) return true;
-    const unsigned long long r = (unsigned long long)(y / w.resolution);
-    const unsigned long long c = (unsigned long long)(x / w.resolution);
+    unsigned long long r, c;
+    if (!map_cell(w, x, y, &r, &c)) return true; // out of bounds = blocked
     const uint32_t word = __ldg(&w.map_bits[r * (unsigned long long)w.stride_words + (c >> 5)]);
+    return (word >> (c & 31)) & 1u;
+}
+
+// Chunk culling: true when every cell within the dilation radius of (x, y)'s cell is in bounds and free.
+__device__ __forceinline__ bool map_safe(const WorldD& w, double x, double y) {
+    if (w.map_kind == kMapNone) return true;
+    if (w.safe_bits == nullptr) return false;
+    unsigned long long r, c;
+    if (!map_cell(w, x, y, &r, &c)) return false;
+    const uint32_t word = __ldg(&w.safe_bits[r * (unsigned long long)w.stride_words + (c >> 5)]);
     return (word >> (c & 31)) & 1u;
 }
 
 // BinaryDynamicObstaclesManager::collisionExists (Binary...cpp:4-22) and
 // GaussianDynamicObstaclesManager::collisionExists (Gaussian...cpp:3-13), strict = true.
-// Obstacles are staged in shared memory once per CTA; every lane walks them in container order so
-// the per-sample sum has the reference's summation order.
-__device__ __forceinline__ double collision_exists(int kind, int n_obs, const ObstacleD* __restrict__ obs, double x,
-                                                   double y, double time) {
+// Obstacles are staged in shared memory once per CTA; every lane walks the chunk's candidate
+// obstacles (bit i of `mask`; all obstacles when the set has more than 64) in container order, so
+// the per-sample sum has the reference's summation order.  Obstacles outside the mask contribute
+// exactly 0 (binary) or less than 1e-26 each (gaussian) to every sample of the chunk.
+__device__ __forceinline__ double obstacle_binary(const ObstacleD& o, double x, double y, double time) {
+    const double dtm = time - o.Time;
+    const double dx = o.Speed * dtm * o.cosYaw;
+    const double dy = o.Speed * dtm * o.sinYaw;
+    const double X = o.X + dx, Y = o.Y + dy;
+    const double tx = x - X, ty = y - Y;
+    const double rx = tx * o.cosYaw - ty * o.sinYaw;
+    const double ry = tx * o.sinYaw + ty * o.cosYaw;
+    return (fabs(rx) < o.a && fabs(ry) < o.b) ? 1.0 : 0.0;
+}
+
+__device__ __forceinline__ double obstacle_quadform(const ObstacleD& o, double x, double y, double time) {
+    const double dtm = time - o.Time;
+    const double dx = o.Speed * dtm * o.cosYaw;
+    const double dy = o.Speed * dtm * o.sinYaw;
+    const double X = o.X + dx, Y = o.Y + dy;
+    const double d0 = x - X, d1 = y - Y;
+    const double r0 = d0 * o.a + d1 * o.b;  // (v^T Sigma^-1)_0 = v0*i00 + v1*i10
+    const double r1 = d0 * o.c + d1 * o.d;  // (v^T Sigma^-1)_1 = v0*i01 + v1*i11
+    return r0 * d0 + r1 * d1;
+}
+
+__device__ __noinline__ double collision_exists(int kind, int n_obs, const ObstacleD* __restrict__ obs,
+                                                   unsigned long long mask, bool use_mask, double x, double y, double time) {
     double sum = 0;
-    if (kind == kObsBinary) {
-        for (int i = 0; i < n_obs; i++) {
-            const ObstacleD& o = obs[i];
-            const double dtm = time - o.Time;
-            const double dx = o.Speed * dtm * o.cosYaw;
-            const double dy = o.Speed * dtm * o.sinYaw;
-            const double X = o.X + dx, Y = o.Y + dy;
-            const double tx = x - X, ty = y - Y;
-            const double rx = tx * o.cosYaw - ty * o.sinYaw;
-            const double ry = tx * o.sinYaw + ty * o.cosYaw;
-            if (fabs(rx) < o.a && fabs(ry) < o.b) sum += 1.0;
+    if (use_mask) {
+        if (kind == kObsBinary) {
+            while (mask) {
+                const int i = __ffsll((long long)mask) - 1;
+                mask &= mask - 1;
+                sum += obstacle_binary(obs[i], x, y, time);
+            }
+            return sum;
         }
-        return sum;
-    }
-    for (int i = 0; i < n_obs; i++) {
-        const ObstacleD& o = obs[i];
-        const double dtm = time - o.Time;
-        const double dx = o.Speed * dtm * o.cosYaw;
-        const double dy = o.Speed * dtm * o.sinYaw;
-        const double X = o.X + dx, Y = o.Y + dy;
-        const double d0 = x - X, d1 = y - Y;
-        const double r0 = d0 * o.a + d1 * o.b;  // (v^T Sigma^-1)_0 = v0*i00 + v1*i10
-        const double r1 = d0 * o.c + d1 * o.d;  // (v^T Sigma^-1)_1 = v0*i01 + v1*i11
-        const double quadform = r0 * d0 + r1 * d1;
-        sum += o.norm * exp(-0.5 * quadform);
+        while (mask) {
+            const int i = __ffsll((long long)mask) - 1;
+            mask &= mask - 1;
+            sum += obs[i].norm * exp(-0.5 * obstacle_quadform(obs[i], x, y, time));
+        }
+    } else {
+        if (kind == kObsBinary) {
+#pragma unroll 1
+            for (int i = 0; i < n_obs; i++) sum += obstacle_binary(obs[i], x, y, time);
+            return sum;
+        }
+#pragma unroll 1
+        for (int i = 0; i < n_obs; i++) sum += obs[i].norm * exp(-0.5 * obstacle_quadform(obs[i], x, y, time));
     }
     if (sum < 1e-5) return 0;
     return sum;
 }
 
 // RibbonManager::minDistanceFrom (RibbonManager.cpp:142-152): lanes over ribbons.
-__device__ __forceinline__ double warp_min_distance_from(const double4* cur, int nr, double x, double y, double W,
+__device__ __noinline__ double warp_min_distance_from(const double4* cur, int nr, double x, double y, double W,
                                                          int lane) {
     if (nr == 0) return 0;
     double mn = DBL_MAX;
@@ -137,7 +179,7 @@ __device__ __forceinline__ double warp_min_distance_from(const double4* cur, int
 // Ribbon.cpp:9-17 and add, RibbonManager.cpp:154-158): every ribbon is split independently; list
 // order is kept by a warp prefix sum over the 0/1/2 pieces each ribbon leaves behind.  Writes the
 // new list into `alt`; the caller swaps the buffers when something changed.
-__device__ __forceinline__ int warp_cover(const double4* cur, double4* alt, int nr, int cap, double x, double y,
+__device__ __noinline__ int warp_cover(const double4* cur, double4* alt, int nr, int cap, double x, double y,
                                           double W, int lane, bool* changed, bool* overflow) {
     int out_base = 0;
     bool any_change = false;
@@ -181,7 +223,7 @@ __device__ __forceinline__ int warp_cover(const double4* cur, double4* alt, int 
 }
 
 // RibbonManager::maxDistance (RibbonManager.cpp:234-248); `scratch` holds >= nr doubles.
-__device__ __forceinline__ double warp_max_distance(const double4* cur, int nr, double x, double y, double W,
+__device__ __noinline__ double warp_max_distance(const double4* cur, int nr, double x, double y, double W,
                                                     int lane, double* scratch) {
     double mn = DBL_MAX, mx = 0;
     for (int r = lane; r < nr; r += 32) {
@@ -210,11 +252,16 @@ __device__ __forceinline__ double warp_max_distance(const double4* cur, int nr, 
 // every lane then reads the (warp-uniform) values it needs as shared-memory broadcasts instead of
 // holding ~60 registers of per-edge state.
 enum PrepSlot {
-    kX0 = 0, kY0, kRho, kInvRho, kLength, kP1, kP2, kP12,
-    kBx = 8, kBy = 11, kBth = 14, kBs = 17, kBc = 20, kSgn = 23,   // 3 entries each, one per segment
-    kWStart = 26, kWSpeed, kWEnd, kApprox, kEx, kEy, kEh, kEs,
-    kYaw0 = 34, kParam0, kParam1, kParam2, kType, kStatus, kSampleFault,
-    kPrepDoubles = 48
+    // per segment k = 0..2 (three entries each): start of the segment in normalised path length, turn sign
+    // (+1 L, -1 R, 0 S), base angle, and the affine form of dubins_segment scaled to the world frame:
+    //   x = Ax * sin(ang) + Bx * tl + Cx,   y = Ay * cos(ang) + By * tl + Cy,   ang = sg * tl + bth
+    kOff = 0, kSgn = 3, kBth = 6, kAx = 9, kBx = 12, kCx = 15, kAy = 18, kBy = 21, kCy = 24,
+    kInvRho = 27, kLength, kWStart, kWSpeed, kWEnd, kApprox, kRho, kX0, kY0, kYaw0,
+    kParam0 = 37, kParam1, kParam2, kType, kStatus, kSampleFault,
+    // reference-order segment constants (pose_eval_ref): base x, y and sin / cos of the base angle per segment
+    kRefBx = 43, kRefBy = 46, kRefBs = 49, kRefBc = 52,
+    kT0 = 55,      // first sample time: src time nudged by fmod(t - startStateTime, dt), Edge.cpp:118-120
+    kPrepDoubles = 56
 };
 struct PreparedEdge {
     double v[kPrepDoubles];
@@ -290,71 +337,307 @@ __device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__
     if (status == PPE_EDGE_OK && approx < 0) status = PPE_EDGE_ERR_NO_PATH; // Edge.cpp:85
 
     double* v = out->v;
-    v[kX0] = path.qi[0]; v[kY0] = path.qi[1]; v[kRho] = path.rho; v[kInvRho] = 1.0 / path.rho;
-    v[kLength] = smp.length; v[kP1] = smp.p1; v[kP2] = smp.p2; v[kP12] = smp.p12;
+    const double rho_ = path.rho, x0 = path.qi[0], y0 = path.qi[1];
+    v[kOff] = 0.0; v[kOff + 1] = smp.p1; v[kOff + 2] = smp.p12;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        v[kBx + k] = smp.bx[k]; v[kBy + k] = smp.by[k]; v[kBth + k] = smp.bth[k];
-        v[kBs + k] = smp.bs[k]; v[kBc + k] = smp.bc[k];
-        v[kSgn + k] = smp.seg[k] == kSegL ? 1.0 : (smp.seg[k] == kSegR ? -1.0 : 0.0);
+        const double sg = smp.seg[k] == kSegL ? 1.0 : (smp.seg[k] == kSegR ? -1.0 : 0.0);
+        v[kSgn + k] = sg;
+        v[kBth + k] = smp.bth[k];
+        v[kRefBx + k] = smp.bx[k]; v[kRefBy + k] = smp.by[k]; v[kRefBs + k] = smp.bs[k]; v[kRefBc + k] = smp.bc[k];
+        if (sg != 0.0) { // arc: q = (sg (sin - bs) + bx, -sg (cos - bc) + by)
+            v[kAx + k] = rho_ * sg;  v[kBx + k] = 0.0; v[kCx + k] = rho_ * (smp.bx[k] - sg * smp.bs[k]) + x0;
+            v[kAy + k] = -rho_ * sg; v[kBy + k] = 0.0; v[kCy + k] = rho_ * (smp.by[k] + sg * smp.bc[k]) + y0;
+        } else {         // straight: q = (bc tl + bx, bs tl + by)
+            v[kAx + k] = 0.0; v[kBx + k] = rho_ * smp.bc[k]; v[kCx + k] = rho_ * smp.bx[k] + x0;
+            v[kAy + k] = 0.0; v[kBy + k] = rho_ * smp.bs[k]; v[kCy + k] = rho_ * smp.by[k] + y0;
+        }
     }
+    v[kInvRho] = 1.0 / path.rho; v[kLength] = smp.length;
     v[kWStart] = w_start; v[kWSpeed] = w_speed; v[kWEnd] = w_end;
     v[kApprox] = approx;
-    v[kEx] = ex; v[kEy] = ey; v[kEh] = eh; v[kEs] = es;
-    v[kYaw0] = path.qi[2]; v[kParam0] = path.param[0]; v[kParam1] = path.param[1]; v[kParam2] = path.param[2];
+    v[kRho] = path.rho; v[kX0] = x0; v[kY0] = y0; v[kYaw0] = path.qi[2];
+    v[kParam0] = path.param[0]; v[kParam1] = path.param[1]; v[kParam2] = path.param[2];
     v[kType] = (double)path.type;
     v[kStatus] = (double)status;
     v[kSampleFault] = sample_fault ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = kSampleFault + 1; k < kPrepDoubles; k++) v[k] = 0.0;
+    v[kT0] = src_t + fmod(src_t - cfg.start_state_time, cfg.collision_checking_increment / cfg.max_speed);
 }
 
 // sin and cos for |x| up to a few thousand (path angles stay within a few turns): three-constant
-// Cody-Waite reduction by pi/2 + Taylor polynomials on [-pi/4, pi/4].  ~1 ulp; used for the
-// per-sample poses only (1e-9 tolerance class) -- and small enough to keep the sample loop inside
-// the instruction cache, unlike libdevice's sincos with its Payne-Hanek slow path.
+// Cody-Waite reduction by pi/2 + the fdlibm minimax kernels on [-pi/4, pi/4] (|error| < 1 ulp).  Used for the
+// per-sample poses only (1e-9 tolerance class).  The coefficients live in constant memory so that every DFMA
+// takes its coefficient as a constant-bank operand instead of two register moves per coefficient per sample.
+__constant__ double c_sin[6] = {-0x1.5555555555549p-3, 0x1.111111110f8a6p-7, -0x1.a01a019c161d5p-13,
+                                0x1.71de357b1fe7dp-19, -0x1.ae5e68a2b9cebp-26, 0x1.5d93a5acfd57cp-33};
+__constant__ double c_cos[6] = {0x1.555555555554cp-5, -0x1.6c16c16c15177p-10, 0x1.a01a019cb159p-16,
+                                -0x1.27e4f809c52adp-22, 0x1.1ee9ebdb4b1c4p-29, -0x1.8fae9be8838d4p-37};
+__constant__ double c_red[4] = {0x1.45f306dc9c883p-1, 0x1.921fb54442d18p+0, 0x1.1a62633145c07p-54, -0x1.f1976b7ed8fbcp-110};
+
 __device__ __forceinline__ void sincos_bounded(double x, double* sn, double* cs) {
-    const double kd = rint(x * 0x1.45f306dc9c883p-1);
+    const double kd = rint(x * c_red[0]);
     const int q = (int)kd;
-    double r = __fma_rn(-kd, 0x1.921fb54442d18p+0, x);
-    r = __fma_rn(-kd, 0x1.1a62633145c07p-54, r);
-    r = __fma_rn(-kd, -0x1.f1976b7ed8fbcp-110, r);
+    double r = __fma_rn(-kd, c_red[1], x);
+    r = __fma_rn(-kd, c_red[2], r);
+    r = __fma_rn(-kd, c_red[3], r);
     const double z = r * r;
-    double ps = -0x1.2f49b46814157p-57;
-    ps = __fma_rn(ps, z, 0x1.952c77030ad4ap-49);
-    ps = __fma_rn(ps, z, -0x1.ae7f3e733b81fp-41);
-    ps = __fma_rn(ps, z, 0x1.6124613a86d09p-33);
-    ps = __fma_rn(ps, z, -0x1.ae64567f544e4p-26);
-    ps = __fma_rn(ps, z, 0x1.71de3a556c734p-19);
-    ps = __fma_rn(ps, z, -0x1.a01a01a01a01ap-13);
-    ps = __fma_rn(ps, z, 0x1.1111111111111p-7);
-    ps = __fma_rn(ps, z, -0x1.5555555555555p-3);
+    double ps = c_sin[5];
+    ps = __fma_rn(ps, z, c_sin[4]);
+    ps = __fma_rn(ps, z, c_sin[3]);
+    ps = __fma_rn(ps, z, c_sin[2]);
+    ps = __fma_rn(ps, z, c_sin[1]);
+    ps = __fma_rn(ps, z, c_sin[0]);
     const double s0 = __fma_rn(r * z, ps, r);
-    double pc = 0x1.e542ba4020225p-62;
-    pc = __fma_rn(pc, z, -0x1.6827863b97d97p-53);
-    pc = __fma_rn(pc, z, 0x1.ae7f3e733b81fp-45);
-    pc = __fma_rn(pc, z, -0x1.93974a8c07c9dp-37);
-    pc = __fma_rn(pc, z, 0x1.1eed8eff8d898p-29);
-    pc = __fma_rn(pc, z, -0x1.27e4fb7789f5cp-22);
-    pc = __fma_rn(pc, z, 0x1.a01a01a01a01ap-16);
-    pc = __fma_rn(pc, z, -0x1.6c16c16c16c17p-10);
-    pc = __fma_rn(pc, z, 0x1.5555555555555p-5);
-    pc = __fma_rn(pc, z, -0x1.0000000000000p-1);
-    const double c0 = __fma_rn(z, pc, 1.0);
+    double pc = c_cos[5];
+    pc = __fma_rn(pc, z, c_cos[4]);
+    pc = __fma_rn(pc, z, c_cos[3]);
+    pc = __fma_rn(pc, z, c_cos[2]);
+    pc = __fma_rn(pc, z, c_cos[1]);
+    pc = __fma_rn(pc, z, c_cos[0]);
+    const double c0 = __fma_rn(z * z, pc, __fma_rn(z, -0.5, 1.0));
     const double a = (q & 1) ? c0 : s0;
     const double b2 = (q & 1) ? s0 : c0;
     *sn = (q & 2) ? -a : a;
     *cs = ((q + 1) & 2) ? -b2 : b2;
 }
 
+// ---- exact replay of `t += dt` (Edge.cpp:173) as a per-edge table ------------------------------------------------
+// Within one binade the repeated addition is an exact arithmetic progression (see TimeWalker in
+// ppe_math.cuh); an edge crosses a handful of binades, so its sample times are a short table of runs
+// (start index, start time, exact increment) held in shared memory per warp.  Any lane then gets any t_i
+// in O(#runs) without carrying walker state in registers, which is what lets the probe pass look ahead.
+constexpr int kTimeRuns = 24;
+struct TimeTable {
+    double base[kTimeRuns];
+    double D[kTimeRuns];
+    int i0[kTimeRuns];
+    int n;
+    int i_after;     // first index after the last run ...
+    int overflow;    // ... reached with runs to spare (0) or because the table is full (1: step from there)
+    int pad_;
+    double t_after;  // ... and its time
+};
+
+// one run starting at time t: increment D (0 for a single step), sample count, time after the run
+__device__ __forceinline__ void time_run(double t, double dt, int edt, double* D_out, int* cnt_out, double* t_next_out) {
+    TimeWalker tw;
+    tw.dt = dt; tw.edt = edt; tw.base = t; tw.i0 = 0;
+    tw.build();
+    *D_out = tw.D; *cnt_out = tw.cnt; *t_next_out = tw.t_next;
+}
+
+// Runs are built until one STARTS at or beyond `end_time`, so the table covers every executed sample and the
+// first one past the end (whose time the reference keeps in `t` after the loop, Edge.cpp:185-191).
+__device__ __noinline__ void time_table_build(TimeTable* tt, double t0, double dt, double end_time, int lane) {
+    const int edt = (dt > 0) ? f64_exponent(dt) : -2000;
+    double t = t0;
+    int i = 0, n = 0, overflow = 0;
+    for (;;) {
+        double D, t_next;
+        int cnt;
+        time_run(t, dt, edt, &D, &cnt, &t_next);
+        if (lane == 0) { tt->base[n] = t; tt->D[n] = D; tt->i0[n] = i; }
+        n++;
+        const bool past = !(t < end_time);
+        i += cnt;
+        t = t_next;
+        if (past || i > kMaxSamples) break;
+        if (n == kTimeRuns) { overflow = 1; break; }
+    }
+    if (lane == 0) { tt->n = n; tt->i_after = i; tt->t_after = t; tt->overflow = overflow; }
+    __syncwarp();
+}
+
+__device__ __noinline__ double time_at_overflow(const TimeTable* tt, int i, double dt) {
+    double t = tt->t_after; // table full (pathological time scales): true additions from its end
+#pragma unroll 1
+    for (int k = tt->i_after; k < i; k++) t = t + dt;
+    return t;
+}
+
+__device__ __forceinline__ double time_at_from(const TimeTable* tt, int i, int r, double dt) {
+    const int n = tt->n;
+#pragma unroll 1
+    for (int k = r + 1; k < n && i >= tt->i0[k]; k++) r = k;
+    const double t = tt->base[r] + (double)(i - tt->i0[r]) * tt->D[r];
+    if (tt->overflow && i >= tt->i_after) return time_at_overflow(tt, i, dt);
+    return t;
+}
+
+// out of line: check-points of culled chunks, loop exit, probe pass
+__device__ __noinline__ double time_at(const TimeTable* tt, int i, double dt) { return time_at_from(tt, i, 0, dt); }
+
+// DubinsWrapper::sample (DubinsWrapper.cpp:29-49) with the per-path constants of the prepared record:
+// pose at time t.  `ang` is the un-wrapped path angle; the heading is derived from it only where it is
+// needed (check-points, loop exit).  Returns false when both dubins_path_sample attempts fail.
+__device__ __forceinline__ bool pose_eval(const double* pe, double t, double* x_out, double* y_out, double* ang_out,
+                                          bool* in_time) {
+    const double w_start = pe[kWStart];
+    *in_time = (w_start <= t) && (pe[kWEnd] >= t); // DubinsWrapper::containsTime
+    double dist = (t - w_start) * pe[kWSpeed];
+    bool sample_ok = true;
+    {
+        const double length = pe[kLength];
+        if (dist < 0 || dist > length) { // EDUBPARAM -> one retry at distance - 1e-5 (DubinsWrapper.cpp:39-42)
+            dist = dist - 1e-5;
+            sample_ok = !(dist < 0 || dist > length);
+        }
+    }
+    const double tprime = dist * pe[kInvRho];
+    const int k = (tprime < pe[kOff + 1] ? 0 : 1) + (tprime < pe[kOff + 2] ? 0 : 1);
+    const double* seg = pe + k;
+    const double tl = tprime - seg[kOff];
+    const double ang = seg[kSgn] * tl + seg[kBth]; // L: t + th, R: -t + th, S: 0 + th  (dubins_segment)
+    double sn, cs;
+    sincos_bounded(ang, &sn, &cs);
+    *x_out = (seg[kAx] * sn + seg[kBx] * tl) + seg[kCx];
+    *y_out = (seg[kAy] * cs + seg[kBy] * tl) + seg[kCy];
+    *ang_out = ang;
+    return sample_ok;
+}
+
+// The same pose in the reference's operation order (dubins_segment / dubins_path_sample: q = segment(t) + base,
+// x = q.x * rho + x0), out of line.  Everything that reaches an output or a ribbon decision -- check-point
+// poses, the pose the loop exits with, the truncated end state -- is evaluated with THIS function: on straight
+// segments its arithmetic is the reference's bit for bit, which is what keeps exact f-ties (straight survey
+// lines produce many) breaking the same way.  pose_eval above (affine form, 1e-16-class differences) only
+// decides map cells and obstacle sums.
+__device__ __noinline__ bool pose_eval_ref(const double* pe, double t, double* x_out, double* y_out, double* ang_out,
+                                           bool* in_time) {
+    const double w_start = pe[kWStart];
+    *in_time = (w_start <= t) && (pe[kWEnd] >= t);
+    double dist = (t - w_start) * pe[kWSpeed];
+    bool sample_ok = true;
+    {
+        const double length = pe[kLength];
+        if (dist < 0 || dist > length) {
+            dist = dist - 1e-5;
+            sample_ok = !(dist < 0 || dist > length);
+        }
+    }
+    const double tprime = dist * pe[kInvRho];
+    const double p1 = pe[kOff + 1];
+    const int k = tprime < p1 ? 0 : (tprime < pe[kOff + 2] ? 1 : 2);
+    const double tl = k == 0 ? tprime : (k == 1 ? tprime - p1 : tprime - p1 - pe[kParam1]);
+    const double sg = pe[kSgn + k], bth = pe[kBth + k], bs = pe[kRefBs + k], bc = pe[kRefBc + k];
+    const double ang = sg * tl + bth;
+    double sn, cs;
+    sincos_bounded(ang, &sn, &cs);
+    const double qx = (sg == 0.0 ? bc * tl : sg * (sn - bs)) + pe[kRefBx + k];
+    const double qy = (sg == 0.0 ? bs * tl : -sg * (cs - bc)) + pe[kRefBy + k];
+    const double rho = pe[kRho];
+    *x_out = qx * rho + pe[kX0];
+    *y_out = qy * rho + pe[kY0];
+    *ang_out = ang;
+    return sample_ok;
+}
+
+// mod2pi + State::setYaw (State.h:51-65): heading of a path angle
+__device__ __forceinline__ double heading_of(double ang) {
+    const double yaw = ang - kTwoPi * floor(ang * 0x1.45f306dc9c883p-3);
+    double hd = kPi2 - yaw;
+    if (hd < 0) hd += kTwoPi;
+    return hd;
+}
+
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+    return (unsigned long long)__shfl_sync(kFull, (long long)v, src);
+}
+
+// ---- chunk culling: the probe pass ---------------------------------------------------------------------------------
+// Lane m looks at chunk m of the next 32 chunks (samples [c0, c0 + 32), c0 = base + 32 m): it evaluates the exact pose
+// of the chunk's middle sample and proves, where it can, that NOTHING discrete happens in the chunk:
+//   * every sample time is below the end time and inside the wrapper, every distance inside the path
+//     (times and distances are monotone, so the two ends of the chunk decide);
+//   * every sample lies within `rad` (half a chunk of arc length) of the probe, and the probe's cell is `safe`
+//     (all cells within that reach are in bounds and free) => no sample is blocked;
+//   * the obstacles' contributions are bounded over the chunk: binary -- the probe is farther than the reach from
+//     every inflated rectangle => every sample counts 0; gaussian -- sum of per-obstacle upper bounds < 1e-5 =>
+//     collisionExists returns exactly 0 for every sample.
+// A proved chunk costs nothing but its check-points.  For the others the lane reports which obstacles can matter
+// at all in the chunk (candidate mask), so the exact per-sample evaluation touches a few obstacles, not all.
+__device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, const TimeTable* tt, const ObstacleD* s_obs,
+                                          int base, int lane, double end_time, double rad, bool* safe_out,
+                                          unsigned long long* mask_out) {
+    const WorldD& w = *wp;
+    const int c0 = base + lane * kChunk;
+    const double dt = w.dt;
+    const double t_first = time_at(tt, c0, dt);
+    const double t_mid = time_at(tt, c0 + kChunk / 2, dt);
+    const double t_last = time_at(tt, c0 + kChunk - 1, dt);
+    const double w_start = pe[kWStart], w_speed = pe[kWSpeed];
+    bool ok = (t_last < end_time) && (w_start <= t_first) && (pe[kWEnd] >= t_last) && (t_first <= t_mid) && (t_mid <= t_last);
+    const double d_first = (t_first - w_start) * w_speed, d_last = (t_last - w_start) * w_speed;
+    ok = ok && !(d_first < 0) && !(d_last > pe[kLength]);
+    // arc length between the probe and either end of the chunk, from the actual sample times
+    const double reach = fmax(t_mid - t_first, t_last - t_mid) * w_speed;
+    ok = ok && (reach * (1 + 1e-9) + 1e-9 <= rad);
+    double x = 0, y = 0, ang = 0;
+    bool in_time = false;
+    const bool sample_ok = pose_eval(pe, t_mid, &x, &y, &ang, &in_time);
+    ok = ok && sample_ok && in_time;
+    unsigned long long mask = ~0ull;
+    if (ok) {
+        ok = map_safe(w, x, y);
+        const int n_obs = w.n_obs;
+        if (w.obs_kind != kObsNone && n_obs > 0) {
+            if (!w.obs_cull_ok) {
+                ok = false;
+            } else {
+                const double half_t = fmax(t_mid - t_first, t_last - t_mid) * (1 + 1e-9);
+                mask = 0;
+                if (w.obs_kind == kObsBinary) {
+#pragma unroll 1
+                    for (int i = 0; i < n_obs; i++) {
+                        const ObstacleD& o = s_obs[i];
+                        const double dtm = t_mid - o.Time;
+                        const double X = o.X + o.Speed * dtm * o.cosYaw, Y = o.Y + o.Speed * dtm * o.sinYaw;
+                        const double tx = x - X, ty = y - Y;
+                        const double rx = tx * o.cosYaw - ty * o.sinYaw;
+                        const double ry = tx * o.sinYaw + ty * o.cosYaw;
+                        // relative displacement over the chunk: the sample moves <= rad, the obstacle <= |v| * half_t
+                        const double reach_i = (rad + fabs(o.Speed) * half_t) * (1 + 1e-9) + 1e-6;
+                        if (fabs(rx) < o.a + reach_i && fabs(ry) < o.b + reach_i) mask |= 1ull << i;
+                    }
+                    ok = ok && (mask == 0);
+                } else {
+                    float bound = 0.f;
+#pragma unroll 1
+                    for (int i = 0; i < n_obs; i++) {
+                        const ObstacleD& o = s_obs[i];
+                        const double q = obstacle_quadform(o, x, y, t_mid);
+                        const double reach_i = (rad + fabs(o.Speed) * half_t) * (1 + 1e-9) + 1e-6;
+                        // sqrt(q) is a norm of the relative position: it cannot shrink faster than cull * displacement
+                        const float sq = __fsqrt_rd(__double2float_rd(fmax(q, 0.0)));
+                        const float m = fmaxf(sq - __double2float_ru(reach_i * o.cull), 0.f) * 0.9999f;
+                        const float arg = -0.5f * (m * m) * 0.9999f;                 // >= the true exponent
+                        const float e = __expf(arg) * 1.001f + 1e-37f;               // >= exp(arg)
+                        const float b_i = __double2float_ru(o.norm) * e * 1.0001f;   // >= max pdf over the chunk
+                        if (b_i >= 1e-26f) mask |= 1ull << i;
+                        bound += b_i;
+                    }
+                    ok = ok && (bound * 1.001f < 1e-5f);
+                }
+            }
+        }
+    }
+    *safe_out = ok;
+    *mask_out = mask;
+}
+
 // One edge, one warp.  Per-edge scalars that every lane would hold identically live in the warp's
-// shared-memory copy of the prepared record (`pe`); lane i of a chunk owns sample index base + i.
-// The pose evaluation, the ribbon cover and the end-state sample each exist exactly once in the
-// instruction stream: the truncated end state (Edge.cpp:177-178) and the final cover (:182-191)
-// run as one extra "tail" pass through the same loop body.
-__device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge, const PreparedEdge* __restrict__ prep,
-                             ppe_edge_result* __restrict__ result, const ObstacleD* s_obs, double4* bufA, double4* bufB,
-                             double* pe, int lane, double* out_f) {
+// shared-memory copy of the prepared record (`pe`) and in the time table (`tt`).  The sample loop of
+// Edge.cpp:125-175 runs in chunks of 32 consecutive samples:
+//   * a chunk the probe pass proved clean is not evaluated at all -- only its ribbon check-points are,
+//     from directly evaluated poses;
+//   * any other chunk is evaluated exactly, lane i owning sample base + i, against the chunk's candidate
+//     obstacles.
+// The two kinds share one check-point loop and one loop-exit block through `sample_pose`, which hands
+// back the pose of a sample index either from the lanes (shuffle) or by direct evaluation.
+__device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* __restrict__ edge,
+                             const PreparedEdge* __restrict__ prep, ppe_edge_result* __restrict__ result,
+                             const ObstacleD* s_obs, double4* bufA, double4* bufB, double* pe, TimeTable* tt, int lane,
+                             double* out_f) {
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width;
     const double inc = cfg.collision_checking_increment;
@@ -395,88 +678,119 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
     double penalty = 0;
     bool infeasible = src_t >= endTime;
     const double dt = w.dt;
-    const double t0 = src_t + fmod(src_t - cfg.start_state_time, dt);
+    const double t0 = pe[kT0];
     int next_cp = 0; // sample index of the next ribbon check-point (toCoverDistance starts at 0)
-    double carry_x = edge->src[0], carry_y = edge->src[1], carry_h = edge->src[2]; // `intermediate` before the chunk
-    double P_x = carry_x, P_y = carry_y, P_h = carry_h, lastHeading = carry_h, t_exit = t0;
-    double ex = 0, ey = 0, eh = 0;
-    int n_samples = 0, n_cp = 0;
+    // `intermediate` and `lastHeading` when the loop exits (Edge.cpp:96,174); before any sample: the source state
+    double P_x = edge->src[0], P_y = edge->src[1], P_h = edge->src[2], lastHeading = edge->src[2], t_exit = t0;
+    int n_samples = 0, n_cp = 0, n_culled = 0;
     {
         const double span = (endTime - t0) / dt;
         if (!((dt > 0) && (span < (double)kMaxSamples || !(t0 < endTime)))) status = PPE_EDGE_ERR_END_SAMPLE;
     }
 
     if (status == PPE_EDGE_OK) {
-        TimeWalker tw;
-        tw.init(t0, dt);
-        bool tail = false;
-        for (int base = 0;;) {
-            // ---- pose at this lane's time (tail pass: every lane at the truncated end time) ------------------
-            const double t_i = tail ? endTime : tw.at(base + lane);
-            bool valid = tail || (t_i < endTime);
-            const double w_start = pe[kWStart];
-            const bool in_time = (w_start <= t_i) && (pe[kWEnd] >= t_i); // DubinsWrapper::containsTime
-            double dist = (t_i - w_start) * pe[kWSpeed];
-            bool sample_ok = true;
-            {
-                const double length = pe[kLength];
-                if (dist < 0 || dist > length) { // EDUBPARAM -> one retry at distance - 1e-5 (DubinsWrapper.cpp:39-42)
-                    dist = dist - 1e-5;
-                    sample_ok = !(dist < 0 || dist > length);
-                }
-            }
-            const double tprime = dist * pe[kInvRho];
-            const double p1 = pe[kP1];
-            const int k = tprime < p1 ? 0 : (tprime < pe[kP12] ? 1 : 2);
-            const double tl = k == 0 ? tprime : (k == 1 ? tprime - p1 : tprime - p1 - pe[kP2]);
-            const double sg = pe[kSgn + k], bth = pe[kBth + k], bs = pe[kBs + k], bc = pe[kBc + k];
-            const double ang = sg * tl + bth; // L: t + th, R: -t + th, S: 0 + th  (dubins_segment)
-            double sn, cs;
-            sincos_bounded(ang, &sn, &cs);
-            const double qx = (sg == 0.0 ? bc * tl : sg * (sn - bs)) + pe[kBx + k];
-            const double qy = (sg == 0.0 ? bs * tl : -sg * (cs - bc)) + pe[kBy + k];
-            const double rho = pe[kRho];
-            const double x = qx * rho + pe[kX0];
-            const double y = qy * rho + pe[kY0];
-            const double yaw = ang - kTwoPi * floor(ang * 0x1.45f306dc9c883p-3);
-            double hd = kPi2 - yaw; // State::setYaw
-            if (hd < 0) hd += kTwoPi;
+        time_table_build(tt, t0, dt, endTime, lane);
+        const double w_speed = pe[kWSpeed];
+        const double rad_max = 0.5 * kChunk * inc * 1.001 + 1e-6; // the reach the safe map was dilated for
+        const bool probing = !tt->overflow && (w_speed > 0) && (w_speed * dt <= inc * 1.0005);
+        int probe_base = -1;          // chunk 0 of the last probe pass; -1: no valid probe results
+        bool p_safe = false;          // this lane's chunk of that pass: proved clean
+        unsigned long long p_mask = ~0ull;
+        int run = 0;                  // time-table run of sample `base`
+        int last_cp = -2;             // index and heading of the last check-point
+        double last_ch = 0;
 
-            int limit = 0, fstop = 32;
+        unsigned p_clean = 0;         // ballot of p_safe over the 32 chunks of that pass
+        for (int base = 0;; base += kChunk) {
+            if (base > kMaxSamples) { status = PPE_EDGE_ERR_END_SAMPLE; break; }
+            // ---- what the probe pass knows about this chunk (one pass covers 32 chunks) ---------------------
+            bool clean = false;
+            unsigned long long omask = ~0ull;
+            bool use_mask = false;
+            if (probing) {
+                int m = probe_base >= 0 ? (base - probe_base) / kChunk : 32;
+                if (m >= 32) {
+                    probe_chunks(ws, pe, tt, s_obs, base, lane, endTime, rad_max, &p_safe, &p_mask);
+                    p_clean = __ballot_sync(kFull, p_safe);
+                    probe_base = base;
+                    m = 0;
+                }
+                // a run of clean chunks with no check-point inside is skipped in one step
+                const unsigned dirty = ~(p_clean >> m);
+                int nskip = dirty ? __ffs(dirty) - 1 : 32;          // clean chunks from m on (bit 32 - m of `dirty` is set for m > 0)
+                const int to_cp = (next_cp - base) / kChunk;        // whole chunks before the next check-point's chunk
+                nskip = nskip < to_cp ? nskip : to_cp;
+                if (nskip > 0) {
+                    n_samples += nskip * kChunk;
+                    n_culled += nskip;
+                    base += (nskip - 1) * kChunk;
+                    continue;
+                }
+                clean = (p_clean >> m) & 1u;
+                omask = shfl_u64(p_mask, m);
+                use_mask = w.obs_cull_ok != 0;
+            }
+            while (run + 1 < tt->n && base >= tt->i0[run + 1]) run++;
+
+            // ---- lane data of an evaluated chunk ----------------------------------------------------------
+            double t_i = 0, x = 0, y = 0, ang = 0;
+            bool valid = true, blocked = false;
+            int limit = kChunk, fstop = kChunk;
             unsigned m_stop = 0;
-            bool blocked = false;
-            if (!tail) {
+            n_culled += clean ? 1 : 0;
+            if (!clean) {
+                t_i = time_at_from(tt, base + lane, run, dt);
+                valid = t_i < endTime;
+                bool in_time;
+                const bool sample_ok = pose_eval(pe, t_i, &x, &y, &ang, &in_time);
                 if (valid && in_time && sample_ok) blocked = map_blocked(w, x, y);
                 const unsigned m_valid = __ballot_sync(kFull, valid);
                 m_stop = __ballot_sync(kFull, valid && (!in_time || blocked));
                 if (__any_sync(kFull, valid && in_time && !sample_ok)) sample_fault = true;
                 const int nvalid = __popc(m_valid); // valid lanes form a prefix (times increase)
-                fstop = m_stop ? (__ffs(m_stop) - 1) : 32;
-                limit = nvalid < fstop ? nvalid : fstop; // lanes [0, limit) execute the full loop body
-            } else {
-                if (!in_time) status = PPE_EDGE_ERR_END_SAMPLE; // sample(end state) throws, DubinsWrapper.cpp:30-35
-                if (!sample_ok) sample_fault = true;
-                ex = x; ey = y; eh = hd;
+                fstop = m_stop ? (__ffs(m_stop) - 1) : kChunk;
+                limit = nvalid < fstop ? nvalid : fstop; // samples [base, base + limit) execute the full loop body
             }
 
-            // ---- ribbon check-points of this chunk, in order (Edge.cpp:153-172); tail: the final cover (:182-191)
-            for (;;) {
-                if (!tail && !(next_cp < base + limit)) break;
-                const int l = tail ? 0 : next_cp - base;
-                double cx = __shfl_sync(kFull, x, l);
-                double cy = __shfl_sync(kFull, y, l);
-                double ch = __shfl_sync(kFull, hd, l);
-                double ct = __shfl_sync(kFull, t_i, l);
-                const double ph_prev = __shfl_sync(kFull, hd, l > 0 ? l - 1 : 0);
-                double ph = l > 0 ? ph_prev : carry_h;
-                double toCover = 0;
-                if (tail) {
-                    cx = P_x; cy = P_y; ch = P_h; ct = t_exit; ph = lastHeading;
-                } else {
-                    n_cp++;
-                    toCover = warp_min_distance_from(cur, nr, cx, cy, W, lane);
+            // ---- ribbon check-points of this chunk, in order (Edge.cpp:153-172) ---------------------------------
+            while (next_cp < base + limit) {
+                const int l = next_cp - base;
+                if (nr == 0 && cct != -1 && !(cct + cfg.time_minimum < endTime)) {
+                    // coverage is complete and the end time has settled: every remaining executed sample of the
+                    // chunk is a check-point that only refreshes ribbonsDoneTime = (int) t (Edge.cpp:163-170)
+                    const int lastl = limit - 1;
+                    const double ct_last = clean ? time_at(tt, base + lastl, dt) : __shfl_sync(kFull, t_i, lastl);
+                    n_cp += limit - l;
+                    ribbonsDoneTime = (int)ct_last;
+                    next_cp = base + limit;
+                    break;
                 }
-                if (cov || ph == ch) {
+                // the check-point's pose, and (non-coverage edges) the heading of the sample before it, in the
+                // reference's operation order
+                const double ct = clean ? time_at(tt, next_cp, dt) : __shfl_sync(kFull, t_i, l);
+                double cx, cy, cang;
+                bool it_;
+                pose_eval_ref(pe, ct, &cx, &cy, &cang, &it_);
+                const double ch = heading_of(cang);
+                n_cp++;
+                const double toCover = warp_min_distance_from(cur, nr, cx, cy, W, lane);
+                bool do_cover = cov;
+                if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159
+                    double ph;
+                    if (next_cp == 0) {
+                        ph = edge->src[2];
+                    } else if (next_cp - 1 == last_cp) {
+                        ph = last_ch; // consecutive check-points: the previous sample's heading is at hand
+                    } else {
+                        double px_, py_, pa_;
+                        pose_eval_ref(pe, time_at(tt, next_cp - 1, dt), &px_, &py_, &pa_, &it_);
+                        ph = heading_of(pa_);
+                    }
+                    do_cover = (ph == ch);
+                }
+                last_cp = next_cp;
+                last_ch = ch;
+                if (do_cover) {
                     bool changed = false;
                     const int nn = warp_cover(cur, alt, nr, cap, cx, cy, W, lane, &changed, &overflow);
                     if (changed) {
@@ -488,57 +802,89 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
                 if (nr == 0) {
                     if (cct == -1) cct = ct;
                     ribbonsDoneTime = (int)ct;
-                    if (!tail) {
-                        endTime = fmin(endTime, cct + cfg.time_minimum);
+                    const double newEnd = fmin(endTime, cct + cfg.time_minimum);
+                    if (newEnd < endTime || clean) {
+                        endTime = newEnd;
+                        probe_base = -1; // the end moved: probe results are stale
+                        if (clean) t_i = time_at_from(tt, base + lane, run, dt);
                         valid = t_i < endTime;
                         const int nvalid = __popc(__ballot_sync(kFull, valid));
                         limit = nvalid < fstop ? nvalid : fstop;
                         if (limit < l + 1) limit = l + 1; // the check-point's own iteration has already run
                     }
                 }
-                if (tail) break;
                 next_cp = next_cp + 1 + skip_count(toCover, inc, kSkipCap);
             }
-            if (tail) break;
 
             // ---- dynamic-obstacle penalty of the executed iterations (Edge.cpp:150-151), in sample order
-            if (w.obs_kind != kObsNone && w.n_obs > 0) {
+            if (!clean && w.obs_kind != kObsNone && w.n_obs > 0 && (!use_mask || omask != 0)) {
                 double p = 0;
-                if (lane < limit) p = collision_exists(w.obs_kind, w.n_obs, s_obs, x, y, t_i) * cfg.collision_penalty_factor;
+                if (lane < limit)
+                    p = collision_exists(w.obs_kind, w.n_obs, s_obs, omask, use_mask, x, y, t_i) * cfg.collision_penalty_factor;
                 if (__any_sync(kFull, p != 0)) {
                     for (int q = 0; q < limit; q++) penalty += __shfl_sync(kFull, p, q);
                 }
             }
 
             n_samples += limit;
-            if (limit < 32) {
-                // the loop ends inside this chunk.  The iteration at lane `limit` was entered and broke
-                // out only if that lane is still inside the (possibly truncated) end time.
-                const bool stop_lane_valid = __shfl_sync(kFull, (int)valid, limit) != 0;
-                const bool stopped = (fstop == limit) && ((m_stop >> fstop) & 1u) && stop_lane_valid;
-                const int lp = limit > 0 ? limit - 1 : 0;
-                const double px = __shfl_sync(kFull, x, lp), py = __shfl_sync(kFull, y, lp), ph = __shfl_sync(kFull, hd, lp);
-                const double prev_x = limit > 0 ? px : carry_x, prev_y = limit > 0 ? py : carry_y,
-                             prev_h = limit > 0 ? ph : carry_h;
-                const double sx_ = __shfl_sync(kFull, x, limit), sy_ = __shfl_sync(kFull, y, limit),
-                             sh_ = __shfl_sync(kFull, hd, limit);
-                const bool stop_blocked = __shfl_sync(kFull, (int)blocked, limit) != 0;
-                t_exit = __shfl_sync(kFull, t_i, limit);
-                lastHeading = prev_h;
-                P_x = prev_x; P_y = prev_y; P_h = prev_h;
+            if (limit < kChunk) {
+                // the loop ends inside this chunk.  The iteration at sample `limit` was entered and broke
+                // out only if that sample is still inside the (possibly truncated) end time.
+                bool stopped = false, stop_blocked = false;
+                if (!clean) {
+                    const bool stop_lane_valid = __shfl_sync(kFull, (int)valid, limit) != 0;
+                    stopped = (fstop == limit) && ((m_stop >> fstop) & 1u) && stop_lane_valid;
+                    stop_blocked = __shfl_sync(kFull, (int)blocked, limit) != 0;
+                    t_exit = __shfl_sync(kFull, t_i, limit);
+                } else {
+                    t_exit = time_at(tt, base + limit, dt);
+                }
+                // pose of the last executed sample (`intermediate`), or the source state when none ran
+                const int last = base + limit - 1;
+                bool it_;
+                if (last >= 0) {
+                    double lx, ly, la;
+                    pose_eval_ref(pe, time_at(tt, last, dt), &lx, &ly, &la, &it_);
+                    P_x = lx; P_y = ly; P_h = heading_of(la);
+                    lastHeading = P_h;
+                }
                 if (stopped) {
                     infeasible = true;
                     n_samples += 1; // the breaking iteration was entered
-                    if (stop_blocked) { P_x = sx_; P_y = sy_; P_h = sh_; } // `intermediate` holds the blocked sample
+                    if (stop_blocked) { // `intermediate` holds the blocked sample
+                        double sx_, sy_, sa_;
+                        pose_eval_ref(pe, t_exit, &sx_, &sy_, &sa_, &it_);
+                        P_x = sx_; P_y = sy_; P_h = heading_of(sa_);
+                    }
                 }
-                tail = true;
-                continue;
+                break;
             }
-            carry_x = __shfl_sync(kFull, x, 31);
-            carry_y = __shfl_sync(kFull, y, 31);
-            carry_h = __shfl_sync(kFull, hd, 31);
-            base += 32;
-            if (base > kMaxSamples) { status = PPE_EDGE_ERR_END_SAMPLE; break; }
+        }
+    }
+
+    // ---- truncated end state (Edge.cpp:177-179) and the final cover (:182-191) ----------------------------------------
+    double ex = 0, ey = 0, eh = 0;
+    if (status == PPE_EDGE_OK) {
+        double ea;
+        bool in_time;
+        const bool sample_ok = pose_eval_ref(pe, endTime, &ex, &ey, &ea, &in_time);
+        eh = heading_of(ea);
+        if (!in_time) status = PPE_EDGE_ERR_END_SAMPLE; // sample(end state) throws, DubinsWrapper.cpp:30-35
+        if (!sample_ok) sample_fault = true;
+    }
+    if (status == PPE_EDGE_OK) {
+        if (cov || lastHeading == P_h) {
+            bool changed = false;
+            const int nn = warp_cover(cur, alt, nr, cap, P_x, P_y, W, lane, &changed, &overflow);
+            if (changed) {
+                double4* tmp = cur; cur = alt; alt = tmp;
+                nr = nn;
+                modified = true;
+            }
+        }
+        if (nr == 0) {
+            if (cct == -1) cct = t_exit;
+            ribbonsDoneTime = (int)t_exit;
         }
     }
 
@@ -600,7 +946,7 @@ __device__ void process_edge(const WorldD& w, const ppe_edge* __restrict__ edge,
         r->n_checkpoints = ok ? n_cp : 0;
         r->n_ribbons_after = ok ? nr : 0;
         r->ribbons_changed = (ok && modified) ? 1 : 0;
-        r->reserved = 0;
+        r->reserved = n_culled; // instrumentation: chunks the probe pass proved clean
     }
     if (!infeasible && status == PPE_EDGE_OK && h >= 0) *out_f = g + h;
 }
@@ -615,8 +961,9 @@ k2a_prepare(const ppe_config cfg, const long long n, const ppe_edge* __restrict_
 
 // K2b: one warp per edge, persistent CTAs pulling edges from a global counter
 __global__ void __launch_bounds__(kBlockThreads, PPE_K2_MIN_BLOCKS)
-k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edges, const PreparedEdge* __restrict__ prepared,
-             ppe_edge_result* __restrict__ results, unsigned long long* work_counter, BestD* block_best) {
+k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
+             const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
+             unsigned long long* work_counter, BestD* block_best) {
     extern __shared__ double4 smem4[];
     ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
     double4* s_rib = smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4));
@@ -625,6 +972,7 @@ k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edg
     double4* bufA = s_rib + (size_t)warp * 2 * w.ribbon_cap;
     double4* bufB = bufA + w.ribbon_cap;
     __shared__ double s_pe[kWarpsPerBlock][kPrepDoubles];
+    __shared__ TimeTable s_tt[kWarpsPerBlock];
     double* pe = s_pe[warp];
 
     {
@@ -643,7 +991,7 @@ k2_true_cost(const WorldD w, const long long n, const ppe_edge* __restrict__ edg
         ei = __shfl_sync(kFull, ei, 0);
         if (ei >= (unsigned long long)n) break;
         double f;
-        process_edge(w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, lane, &f);
+        process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], lane, &f);
         if (f < best_f || (f == best_f && (long long)ei < best_idx)) { best_f = f; best_idx = (long long)ei; }
         __syncwarp();
     }
@@ -711,6 +1059,36 @@ k1_dubins_batch(const long long n, const double* __restrict__ q0, const double* 
     err[i] = e;
 }
 
+// ---- chunk-culling support: dilated free-space bitmap -------------------------------------------------------------------
+// pass 1: rowfree[r][c] = cells (r, c - R .. c + R) all in bounds and free; pass 2: safe[r][c] = rowfree[r - R .. r + R][c]
+// all set (rows out of bounds count as blocked).  One thread per cell, one ballot per 32 cells; the maps are a few MiB.
+__global__ void k_safe_rows(const uint32_t* __restrict__ bits, uint32_t* __restrict__ out, int rows, int cols, int stride, int R) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    bool ok = false;
+    if (c < cols && c - R >= 0 && c + R < cols) {
+        ok = true;
+        const uint32_t* row = bits + (size_t)r * stride;
+        for (int k = c - R; k <= c + R; k++)
+            if ((row[k >> 5] >> (k & 31)) & 1u) { ok = false; break; }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && (c >> 5) < stride) out[(size_t)r * stride + (c >> 5)] = b;
+}
+
+__global__ void k_safe_cols(const uint32_t* __restrict__ rowfree, uint32_t* __restrict__ out, int rows, int cols, int stride, int R) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    bool ok = false;
+    if (c < cols && r - R >= 0 && r + R < rows) {
+        ok = true;
+        for (int k = r - R; k <= r + R; k++)
+            if (!((rowfree[(size_t)k * stride + (c >> 5)] >> (c & 31)) & 1u)) { ok = false; break; }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && (c >> 5) < stride) out[(size_t)r * stride + (c >> 5)] = b;
+}
+
 // FP64 FMA throughput probe: the roofline denominator for K2 (MEASURED_PEAKS.json has no fp64 entry)
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -726,6 +1104,16 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
 } // namespace
 
 int true_cost_block_threads() { return kBlockThreads; }
+int true_cost_chunk_samples() { return kChunk; }
+
+cudaError_t launch_safe_map(const uint32_t* map_bits, uint32_t* scratch_rows, uint32_t* safe_bits, int rows, int cols,
+                            int stride_words, int radius, cudaStream_t stream) {
+    const dim3 block(128, 1, 1);
+    const dim3 grid((unsigned)((stride_words * 32 + 127) / 128), (unsigned)rows, 1);
+    k_safe_rows<<<grid, block, 0, stream>>>(map_bits, scratch_rows, rows, cols, stride_words, radius);
+    k_safe_cols<<<grid, block, 0, stream>>>(scratch_rows, safe_bits, rows, cols, stride_words, radius);
+    return cudaGetLastError();
+}
 
 size_t true_cost_smem_bytes(int ribbon_cap, int n_obs) {
     return (size_t)n_obs * sizeof(ObstacleD) + (size_t)kWarpsPerBlock * 2 * (size_t)ribbon_cap * sizeof(double4);

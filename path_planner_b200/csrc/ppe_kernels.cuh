@@ -18,7 +18,9 @@ struct ObstacleD {
     // gaussian: a..d = inverse covariance i00, i10, i01, i11; norm = 1/(2 pi)/sqrt(det)
     double a, b, c, d;
     double norm;
-    double pad;
+    // chunk-culling bound (host-computed): gaussian: sqrt(lambda_max) of the symmetric part of the inverse
+    // covariance, so that sqrt(q(v + e)) >= sqrt(q(v)) - |e| * cull; unused for binary obstacles
+    double cull;
 };
 static_assert(sizeof(ObstacleD) == 96, "ObstacleD layout");
 
@@ -32,8 +34,14 @@ struct WorldD {
     double horizon_end;   // timeHorizon + 1e-12 + startStateTime        (Edge.cpp:90)
     // static map: rows x stride_words 32-bit words, bit c of row r = blocked[r][c]
     const uint32_t* map_bits;
+    // same layout: bit = every cell within `safe_radius_cells` (Chebyshev) is in bounds and free; nullptr when
+    // the radius is too large to be useful (chunk culling then never skips map look-ups)
+    const uint32_t* safe_bits;
     int map_kind, rows, cols, stride_words;
     double resolution;
+    double inv_resolution;    // exact when the resolution is a power of two (res_pow2): x / res == x * inv
+    int res_pow2;
+    int obs_cull_ok;          // obstacle set admits the chunk bound (SPD symmetric covariances, <= 64 obstacles)
     // dynamic obstacles
     const ObstacleD* obstacles;
     int obs_kind, n_obs;
@@ -63,6 +71,11 @@ cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edg
                                    int max_blocks, BestD* best, int sm_count, cudaStream_t stream, int* launches);
 size_t prepared_edge_bytes();
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t stream);
+// safe[r][c] = all cells within Chebyshev distance `radius` of (r, c) are in bounds and free
+cudaError_t launch_safe_map(const uint32_t* map_bits, uint32_t* scratch_rows, uint32_t* safe_bits, int rows, int cols,
+                            int stride_words, int radius, cudaStream_t stream);
+// samples per chunk of the K2b walker (the unit of culling); the safe-map radius is derived from it
+int true_cost_chunk_samples();
 size_t true_cost_smem_bytes(int ribbon_cap, int n_obs);
 int true_cost_block_threads();
 

@@ -243,6 +243,16 @@ PPE_HD bool wrapper_sample_pose(const PathSampler& s, double w_start, double w_s
 // rounding then depends on the parity of t; those binades are stepped one true addition at a
 // time).  Inside a binade t_i = t_s + (i - s) * D is exact.  A walker therefore hands every lane
 // its own t_i in O(#binades) work; binade crossings are done with one true addition.
+// floor(a / b) for integer-valued doubles 0 <= a < 2^53, 1 <= b < 2^53: one fp64 division and an exact integer
+// correction instead of an emulated 64-bit integer division.
+PPE_HD int64_t floor_div_53(double a, double b) {
+    int64_t q = (int64_t)(a / b);
+    const int64_t ai = (int64_t)a, bi = (int64_t)b;
+    if (q * bi > ai) q--;
+    else if ((q + 1) * bi <= ai) q++;
+    return q;
+}
+
 struct TimeWalker {
     double dt;
     double base, D;     // current run: t_i = base + (i - i0) * D for i0 <= i < i0 + cnt
@@ -260,15 +270,15 @@ struct TimeWalker {
         if (t > 0 && ebits != 0x7ff && ebits - 1023 > edt && ebits > 60) {
             const int e = ebits - 1023;
             const double u = f64_pow2(e - 52);
-            const double kq = floor(dt / u);          // exact: power-of-two scaling
+            const double iu = f64_pow2(52 - e);       // 1 / u: scaling by a power of two is exact
+            const double kq = floor(dt * iu);
             const double r = dt - kq * u;             // exact remainder, 0 <= r < u
             if (r != 0.5 * u) {                       // no tie: rounding is parity independent
                 const double Dd = kq * u + (r > 0.5 * u ? u : 0.0);
                 const double lim = f64_pow2(e + 1) - u; // steps with t_j + D <= lim cannot leave the binade
                 if (Dd > 0 && t + Dd <= lim) {
-                    const int64_t mt = (int64_t)((lim - t) / u);
-                    const int64_t mD = (int64_t)(Dd / u);
-                    int64_t nn = mt / mD;
+                    // floor((lim - t) / Dd) on integers < 2^53 held exactly in doubles
+                    int64_t nn = floor_div_53((lim - t) * iu, Dd * iu);
                     if (nn > 1000000) nn = 1000000;
                     n = (int)nn;
                     D = Dd;
@@ -304,8 +314,9 @@ struct TimeWalker {
 // ---- exact replay of the toCoverDistance skip counter (Edge.cpp:153-154) ----------------------------
 // Number of loop iterations that take the `toCover > inc ? toCover -= inc` branch after a
 // check-point that set toCover = x, i.e. the count of successive fp subtractions until the value
-// is <= c.  Same binade argument as TimeWalker, walking downwards; capped at kmax.
-PPE_HD int skip_count(double x, double c, int kmax) {
+// is <= c.  skip_count_walk replays the subtractions binade by binade (same argument as TimeWalker,
+// walking downwards; capped at kmax).
+PPE_HD_NOINLINE int skip_count_walk(double x, double c, int kmax) {
     int k = 0;
     if (!(c > 0)) return (x > c) ? kmax : 0;
     const int ec = f64_exponent(c);
@@ -316,15 +327,14 @@ PPE_HD int skip_count(double x, double c, int kmax) {
         const int e = ebits - 1023;
         if (e >= ec + 1 && ebits > 60) {
             const double u = f64_pow2(e - 52);
-            const double kq = floor(c / u);
+            const double iu = f64_pow2(52 - e);
+            const double kq = floor(c * iu);
             const double r = c - kq * u;
             if (r != 0.5 * u) {
                 const double D = kq * u + (r > 0.5 * u ? u : 0.0);
                 const double lo = f64_pow2(e) + u; // results >= lo stay in the binade (and > c)
                 if (D > 0 && x - D >= lo) {
-                    const int64_t mx = (int64_t)((x - lo) / u);
-                    const int64_t mD = (int64_t)(D / u);
-                    int64_t n = mx / mD;
+                    int64_t n = floor_div_53((x - lo) * iu, D * iu);
                     if (n > (int64_t)(kmax - k)) n = kmax - k;
                     x = x - (double)n * D;
                     k += (int)n;
@@ -336,6 +346,24 @@ PPE_HD int skip_count(double x, double c, int kmax) {
         k++;
     }
     return k;
+}
+
+// In exact arithmetic the count is ceil(x / c) - 1.  Every rounded subtraction is off by at most half an ulp of
+// its result (<= ulp(x) / 2), so after k steps the value differs from x - k c by less than k ulp(x) / 2: the
+// count can only differ from the exact-arithmetic one when x / c lies within k ulp(x) / (2 c) (plus the
+// rounding of the quotient itself) of an integer.  Outside that margin -- taken 8x wider here -- the closed
+// form IS the replayed count; inside it (probability ~1e-9 per call) the subtractions are replayed.
+PPE_HD int skip_count(double x, double c, int kmax) {
+    if (!(x > c)) return 0;       // also NaN
+    if (!(c > 0) || !(x < 1e300)) return skip_count_walk(x, c, kmax);
+    const double q = x / c;
+    if (!(q < (double)kmax)) return kmax;
+    const double f = floor(q);
+    const double frac = q - f;    // exact
+    const double ulp_x = f64_pow2(f64_exponent(x) - 52);
+    const double margin = 4.0 * q * (ulp_x / c) + 8.0 * q * 0x1p-52;
+    if (frac > margin && (1.0 - frac) > margin) return (int)f; // ceil(q) - 1 = floor(q) for non-integer q
+    return skip_count_walk(x, c, kmax);
 }
 
 // ---- Ribbon primitives (Ribbon.h / Ribbon.cpp) -------------------------------------------------------

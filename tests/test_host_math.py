@@ -92,6 +92,20 @@ def test_skip_count_replays_repeated_subtraction(host_helpers):
                 k += 1
             assert hh.hh_skip_count(x, c, 1 << 28) == k, (x, c)
     assert hh.hh_skip_count(1e9, 0.05, 1000) == 1000  # capped
+    # adversarial: distances within a few ulps of an integer multiple of the increment, where the closed form
+    # (ceil(x / c) - 1) must hand over to the exact replay
+    for c in (0.05, 0.1, 0.03, 0.01):
+        for m in list(rng.integers(1, 6000, 300)) + [1, 2, 3, 1500, 1501]:
+            x0 = float(m) * c
+            for d in (-3, -2, -1, 0, 1, 2, 3):
+                x = x0
+                for _ in range(abs(d)):
+                    x = float(np.nextafter(x, np.inf if d > 0 else -np.inf))
+                v, k = x, 0
+                while v > c:
+                    v -= c
+                    k += 1
+                assert hh.hh_skip_count(x, c, 1 << 28) == k, (x, c, m, d)
 
 
 def test_hoisted_sampler_matches_dubins_path_sample(host_helpers):

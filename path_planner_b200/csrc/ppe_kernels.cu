@@ -23,11 +23,10 @@ namespace ppe {
 
 namespace {
 
-#ifndef PPE_K2_MIN_BLOCKS
-#define PPE_K2_MIN_BLOCKS 4
-#endif
-constexpr int kWarpsPerBlock = 4;
-constexpr int kBlockThreads = kWarpsPerBlock * 32;
+// K2b CTA shapes: 4 warps x 4 CTAs per SM by default (128 registers per thread fill the register file either
+// way); 16-warp CTAs stage the obstacle list once per SM instead of four times (-DPPE_K2_FORCE_NARROW=0).
+// Measured equal within noise on C2 / C3 (profiles/), so the shape with the larger ribbon capacity is the default.
+constexpr int kWarpsWide = 16, kWarpsNarrow = 4;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kChunk = 32; // samples per chunk of the K2b walker = one per lane
 constexpr int kSkipCap = 1 << 28;
@@ -42,13 +41,13 @@ __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
     return v;
 }
 
-__device__ __forceinline__ double warp_min(double v) {
+__device__ __noinline__ double warp_min(double v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, d));
     return v;
 }
 
-__device__ __forceinline__ double warp_max(double v) {
+__device__ __noinline__ double warp_max(double v) {
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, d));
     return v;
@@ -162,6 +161,7 @@ __device__ __noinline__ double warp_min_distance_from(const double4* cur, int nr
     if (nr == 0) return 0;
     double mn = DBL_MAX;
     bool inside = false;
+#pragma unroll 1
     for (int r = lane; r < nr; r += 32) {
         const RibbonD rb = load_ribbon(cur + r);
         double px, py;
@@ -183,6 +183,7 @@ __device__ __noinline__ int warp_cover(const double4* cur, double4* alt, int nr,
                                           double W, int lane, bool* changed, bool* overflow) {
     int out_base = 0;
     bool any_change = false;
+#pragma unroll 1
     for (int base = 0; base < nr; base += 32) {
         const int r = base + lane;
         const bool active = r < nr;
@@ -226,6 +227,7 @@ __device__ __noinline__ int warp_cover(const double4* cur, double4* alt, int nr,
 __device__ __noinline__ double warp_max_distance(const double4* cur, int nr, double x, double y, double W,
                                                     int lane, double* scratch) {
     double mn = DBL_MAX, mx = 0;
+#pragma unroll 1
     for (int r = lane; r < nr; r += 32) {
         const RibbonD rb = load_ribbon(cur + r);
         scratch[r] = sqrt(ribbon_sqlen(rb)) - 2 * W;
@@ -236,6 +238,7 @@ __device__ __noinline__ double warp_max_distance(const double4* cur, int nr, dou
     }
     __syncwarp();
     double sumLength = 0;
+#pragma unroll 1
     for (int r = 0; r < nr; r++) sumLength += scratch[r]; // list order, as the reference sums
     __syncwarp();
     mn = warp_min(mn);
@@ -960,7 +963,8 @@ k2a_prepare(const ppe_config cfg, const long long n, const ppe_edge* __restrict_
 }
 
 // K2b: one warp per edge, persistent CTAs pulling edges from a global counter
-__global__ void __launch_bounds__(kBlockThreads, PPE_K2_MIN_BLOCKS)
+template <int kWarpsPerBlock>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 16 / kWarpsPerBlock)
 k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
              const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
              unsigned long long* work_counter, BestD* block_best) {
@@ -1103,7 +1107,7 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
 
 } // namespace
 
-int true_cost_block_threads() { return kBlockThreads; }
+int true_cost_block_threads() { return kWarpsWide * 32; }
 int true_cost_chunk_samples() { return kChunk; }
 
 cudaError_t launch_safe_map(const uint32_t* map_bits, uint32_t* scratch_rows, uint32_t* safe_bits, int rows, int cols,
@@ -1115,9 +1119,12 @@ cudaError_t launch_safe_map(const uint32_t* map_bits, uint32_t* scratch_rows, ui
     return cudaGetLastError();
 }
 
-size_t true_cost_smem_bytes(int ribbon_cap, int n_obs) {
-    return (size_t)n_obs * sizeof(ObstacleD) + (size_t)kWarpsPerBlock * 2 * (size_t)ribbon_cap * sizeof(double4);
+static size_t k2_smem_bytes(int warps, int ribbon_cap, int n_obs) {
+    return (size_t)n_obs * sizeof(ObstacleD) + (size_t)warps * 2 * (size_t)ribbon_cap * sizeof(double4);
 }
+
+// dynamic shared memory of the configuration that will be launched (the narrow one is the limit that matters)
+size_t true_cost_smem_bytes(int ribbon_cap, int n_obs) { return k2_smem_bytes(kWarpsNarrow, ribbon_cap, n_obs); }
 
 cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type,
                                 double* param, double* length, int32_t* err, cudaStream_t stream) {
@@ -1130,40 +1137,55 @@ cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, c
 
 size_t prepared_edge_bytes() { return sizeof(PreparedEdge); }
 
-cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
-                                   ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best,
-                                   int max_blocks, BestD* best, int sm_count, cudaStream_t stream, int* launches) {
-    PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
-    const size_t smem = true_cost_smem_bytes(world.ribbon_cap, world.n_obs);
+template <int kW>
+static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edges, const PreparedEdge* prepared,
+                             ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best, int max_blocks,
+                             int sm_count, cudaStream_t stream, int* blocks_out) {
+    const size_t smem = k2_smem_bytes(kW, world.ribbon_cap, world.n_obs);
     static size_t configured = 0;
     cudaError_t e;
     if (smem > configured) {
-        e = cudaFuncSetAttribute(k2_true_cost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k2_true_cost<kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_true_cost, kBlockThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_true_cost<kW>, kW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     // persistent grid: a multiple of the SM count, never more warps than edges
     long long blocks = (long long)sm_count * per_sm;
-    const long long needed = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long needed = (n + kW - 1) / kW;
     if (blocks > needed) blocks = needed;
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
-    e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    k2_true_cost<kW><<<(unsigned)blocks, kW * 32, smem, stream>>>(world, (long long)n, edges, prepared, results, work_counter,
+                                                                 block_best);
+    *blocks_out = (int)blocks;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
+                                   ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best,
+                                   int max_blocks, BestD* best, int sm_count, cudaStream_t stream, int* launches) {
+    PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(world.out_count, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     k2a_prepare<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(world.cfg, (long long)n, edges, prepared);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k2_true_cost<<<(unsigned)blocks, kBlockThreads, smem, stream>>>(world, (long long)n, edges, prepared, results,
-                                                                   work_counter, block_best);
-    e = cudaGetLastError();
+    int blocks = 1;
+#ifndef PPE_K2_FORCE_NARROW
+#define PPE_K2_FORCE_NARROW 1
+#endif
+    if (!PPE_K2_FORCE_NARROW && k2_smem_bytes(kWarpsWide, world.ribbon_cap, world.n_obs) <= 190 * 1024)
+        e = launch_k2<kWarpsWide>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, &blocks);
+    else
+        e = launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, &blocks);
     if (e != cudaSuccess) return e;
-    k3_best_final<<<1, 256, 0, stream>>>(block_best, (int)blocks, best);
+    k3_best_final<<<1, 256, 0, stream>>>(block_best, blocks, best);
     if (launches) *launches += 3;
     return cudaGetLastError();
 }

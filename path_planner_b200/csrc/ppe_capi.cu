@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -22,6 +23,20 @@ struct ppe_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    // host-buffer batches are pipelined in slices: H2D, kernels and D2H of different slices overlap, and the
+    // kernels of consecutive slices run on two alternating lanes so that the tail of one slice (a few edges that
+    // spend their whole length on a ribbon) overlaps the bulk of the next
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        unsigned char* d_prepared = nullptr;
+        size_t cap_prepared = 0;
+        unsigned long long* d_work = nullptr;
+        BestD* d_block_best = nullptr;
+        cudaEvent_t ev_k3 = nullptr; // K3 of the lane's previous slice has consumed d_block_best
+        bool used = false;
+    } lanes[2];
+    std::vector<cudaEvent_t> ev_in, ev_k2, ev_done;
     std::string err;
 
     ppe_config cfg{};
@@ -72,9 +87,9 @@ struct ppe_ctx {
     BestD* d_best = nullptr;
     int max_blocks = 0;
 
-    // bookkeeping of the last true-cost batch (for ppe_get_ribbons_after / ppe_best)
-    std::vector<int64_t> last_off;
-    std::vector<int32_t> last_n, last_set, last_changed;
+    // bookkeeping of the last true-cost batch (for ppe_get_ribbons_after / ppe_best): the device copies of
+    // its edges and results stay valid until the next batch, records are fetched on demand
+    int64_t last_count = 0;
     std::vector<double> h_out_ribbons;
     bool out_downloaded = false;
     unsigned long long last_out_count = 0;
@@ -252,12 +267,20 @@ int ppe_create(int device, ppe_ctx** out) {
     ppe_ctx* ctx = new ppe_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PPE_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PPE_ERR_CUDA; }
     ctx->max_blocks = ctx->sm_count * 32;
     bool ok = cudaMalloc((void**)&ctx->d_work, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_out_count, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_block_best, (size_t)ctx->max_blocks * sizeof(BestD)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_best, sizeof(BestD)) == cudaSuccess;
+    for (auto& ln : ctx->lanes) {
+        ok = ok && cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaMalloc((void**)&ln.d_work, sizeof(unsigned long long)) == cudaSuccess &&
+             cudaMalloc((void**)&ln.d_block_best, (size_t)ctx->max_blocks * sizeof(BestD)) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ln.ev_k3, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) { ppe_destroy(ctx); return PPE_ERR_CUDA; }
     *out = ctx;
     return PPE_OK;
@@ -273,6 +296,16 @@ void ppe_destroy(ppe_ctx* ctx) {
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
     cudaFree(ctx->d_work); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
+    if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
+    for (auto& ln : ctx->lanes) {
+        if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+        cudaFree(ln.d_prepared); cudaFree(ln.d_work); cudaFree(ln.d_block_best);
+        if (ln.ev_k3) cudaEventDestroy(ln.ev_k3);
+    }
+    for (cudaEvent_t e : ctx->ev_k2) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->ev_done) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -474,6 +507,19 @@ int ppe_dubins_batch(ppe_ctx* ctx, int64_t n, const double* q0, const double* q1
 }
 
 // ---- K2 / K3 ----------------------------------------------------------------------------------------
+// one launch group (K2a, K2b, K3) over the edges of a device-resident batch, all on `stream`
+static int run_batch_device(ppe_ctx* ctx, const WorldD& w, int64_t n, const ppe_edge* d_edges, ppe_edge_result* d_results,
+                            cudaStream_t stream) {
+    int rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, (size_t)n * prepared_edge_bytes());
+    if (rc != PPE_OK) return rc;
+    int blocks = 1;
+    PPE_CUDA(ctx, launch_true_cost_kernels(w, n, d_edges, ctx->d_prepared, d_results, ctx->d_work, ctx->d_block_best,
+                                           ctx->max_blocks, ctx->sm_count, stream, true, &blocks));
+    PPE_CUDA(ctx, launch_best_final(ctx->d_block_best, blocks, ctx->d_best, 0, false, stream));
+    ctx->launches += 3;
+    return PPE_OK;
+}
+
 int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges, ppe_edge_result* d_results, void* stream) {
     if (!ctx || n < 0) return PPE_ERR_INVALID;
     PPE_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -483,13 +529,7 @@ int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges,
     ctx->have_batch = false;
     ctx->out_downloaded = false;
     if (n == 0) return PPE_OK;
-    int launches = 0;
-    rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, (size_t)n * prepared_edge_bytes());
-    if (rc != PPE_OK) return rc;
-    PPE_CUDA(ctx, launch_true_cost_batch(w, n, d_edges, ctx->d_prepared, d_results, ctx->d_work, ctx->d_block_best,
-                                         ctx->max_blocks, ctx->d_best, ctx->sm_count, (cudaStream_t)stream, &launches));
-    ctx->launches += launches;
-    return PPE_OK;
+    return run_batch_device(ctx, w, n, d_edges, d_results, (cudaStream_t)stream);
 }
 
 int ppe_best_device(ppe_ctx* ctx, double* f, int64_t* edge_index, void* stream) {
@@ -513,61 +553,94 @@ int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, void* stream) {
 int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge_result* results) {
     if (!ctx || n < 0 || (n > 0 && (!edges || !results))) return fail(ctx, PPE_ERR_INVALID, "ppe_true_cost_batch: bad arguments");
     PPE_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (n == 0) { ctx->have_batch = false; return PPE_OK; }
+    ctx->have_batch = false;
+    if (n == 0) return PPE_OK;
     {
         int rc = grow(ctx, &ctx->d_edges, &ctx->cap_edges, (size_t)n);
         if (rc != PPE_OK) return rc;
         rc = grow(ctx, &ctx->d_results, &ctx->cap_results, (size_t)n);
         if (rc != PPE_OK) return rc;
     }
-    cudaStream_t s = ctx->stream;
-    PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_edges, edges, (size_t)n * sizeof(ppe_edge), cudaMemcpyHostToDevice, s));
+    WorldD w;
+    int rc = make_world(ctx, &w);
+    if (rc != PPE_OK) return rc;
+    ctx->out_downloaded = false;
+    // Slices of the batch flow through the streams: H2D of slice k + 1 (copy engine), the kernels of slices k and
+    // k - 1 (two lanes) and D2H of finished slices (second copy engine) run concurrently; K3 accumulates the best
+    // record slice by slice on the context stream.  Small batches are one slice.
+    const int64_t slice = n <= 196608 ? n : 131072;
+    const int64_t n_slices = (n + slice - 1) / slice;
+    while ((int64_t)ctx->ev_in.size() < n_slices) {
+        cudaEvent_t a, b, c;
+        PPE_CUDA(ctx, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        PPE_CUDA(ctx, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        PPE_CUDA(ctx, cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+        ctx->ev_in.push_back(a);
+        ctx->ev_k2.push_back(b);
+        ctx->ev_done.push_back(c);
+    }
     for (int attempt = 0; attempt < 2; attempt++) {
-        int rc = ppe_true_cost_batch_device(ctx, n, ctx->d_edges, ctx->d_results, s);
-        if (rc != PPE_OK) return rc;
-        PPE_CUDA(ctx, cudaMemcpyAsync(results, ctx->d_results, (size_t)n * sizeof(ppe_edge_result), cudaMemcpyDeviceToHost, s));
-        PPE_CUDA(ctx, cudaMemcpyAsync(&ctx->last_out_count, ctx->d_out_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        PPE_CUDA(ctx, cudaStreamSynchronize(s));
+        for (auto& ln : ctx->lanes) ln.used = false;
+        // the ribbons-after pool counter runs over all slices: reset once, ahead of slice 0's copy
+        PPE_CUDA(ctx, cudaMemsetAsync(ctx->d_out_count, 0, sizeof(unsigned long long), ctx->stream_in));
+        for (int64_t k = 0; k < n_slices; k++) {
+            const int64_t lo = k * slice, cnt = (lo + slice <= n) ? slice : n - lo;
+            ppe_ctx::Lane& ln = ctx->lanes[k & 1];
+            rc = grow(ctx, &ln.d_prepared, &ln.cap_prepared, (size_t)cnt * prepared_edge_bytes());
+            if (rc != PPE_OK) return rc;
+            PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_edges + lo, edges + lo, (size_t)cnt * sizeof(ppe_edge), cudaMemcpyHostToDevice, ctx->stream_in));
+            PPE_CUDA(ctx, cudaEventRecord(ctx->ev_in[k], ctx->stream_in));
+            PPE_CUDA(ctx, cudaStreamWaitEvent(ln.stream, ctx->ev_in[k], 0));
+            if (ln.used) PPE_CUDA(ctx, cudaStreamWaitEvent(ln.stream, ln.ev_k3, 0)); // its block_best has been consumed
+            int blocks = 1;
+            PPE_CUDA(ctx, launch_true_cost_kernels(w, cnt, ctx->d_edges + lo, ln.d_prepared, ctx->d_results + lo, ln.d_work,
+                                                   ln.d_block_best, ctx->max_blocks, ctx->sm_count, ln.stream, false, &blocks));
+            PPE_CUDA(ctx, cudaEventRecord(ctx->ev_k2[k], ln.stream));
+            PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_k2[k], 0));
+            PPE_CUDA(ctx, launch_best_final(ln.d_block_best, blocks, ctx->d_best, lo, k > 0, ctx->stream));
+            PPE_CUDA(ctx, cudaEventRecord(ln.ev_k3, ctx->stream));
+            ln.used = true;
+            ctx->launches += 3;
+            PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_out, ctx->ev_k2[k], 0));
+            PPE_CUDA(ctx, cudaMemcpyAsync(results + lo, ctx->d_results + lo, (size_t)cnt * sizeof(ppe_edge_result), cudaMemcpyDeviceToHost, ctx->stream_out));
+        }
+        PPE_CUDA(ctx, cudaMemcpyAsync(&ctx->last_out_count, ctx->d_out_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream_out));
         if (ctx->last_out_count <= ctx->out_cap) break;
         // the ribbons-after pool was too small for this batch: grow it and run the batch again
         rc = ensure_pool(ctx, (size_t)(ctx->last_out_count + ctx->last_out_count / 4 + 1024));
         if (rc != PPE_OK) return rc;
+        rc = make_world(ctx, &w);
+        if (rc != PPE_OK) return rc;
     }
-    ctx->last_off.resize((size_t)n); ctx->last_n.resize((size_t)n); ctx->last_set.resize((size_t)n); ctx->last_changed.resize((size_t)n);
-    for (int64_t i = 0; i < n; i++) {
-        ctx->last_off[i] = results[i].ribbons_offset;
-        ctx->last_n[i] = results[i].n_ribbons_after;
-        ctx->last_set[i] = edges[i].ribbon_set;
-        ctx->last_changed[i] = results[i].ribbons_changed;
-    }
+    ctx->last_count = n;
     ctx->have_batch = true;
     ctx->out_downloaded = false;
     return PPE_OK;
 }
 
 int ppe_get_ribbons_after(ppe_ctx* ctx, int64_t i, double* xyxy, int cap) {
-    if (!ctx || !ctx->have_batch || i < 0 || (size_t)i >= ctx->last_n.size() || (cap > 0 && !xyxy))
+    if (!ctx || !ctx->have_batch || i < 0 || i >= ctx->last_count || (cap > 0 && !xyxy))
         return fail(ctx, PPE_ERR_INVALID, "ppe_get_ribbons_after: no such edge in the last ppe_true_cost_batch");
-    if (!ctx->last_changed[i]) {
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the batch's device copies are still in place: fetch this edge's record (and its parent set id) on demand
+    ppe_edge_result r;
+    PPE_CUDA(ctx, cudaMemcpy(&r, ctx->d_results + i, sizeof r, cudaMemcpyDeviceToHost));
+    if (!r.ribbons_changed) {
         // identical to the parent's interned set
-        const int set = ctx->last_set[i];
+        int32_t set = -1;
+        PPE_CUDA(ctx, cudaMemcpy(&set, (const char*)(ctx->d_edges + i) + offsetof(ppe_edge, ribbon_set), sizeof set, cudaMemcpyDeviceToHost));
         if (set < 0 || (size_t)set >= ctx->h_cnt.size()) return fail(ctx, PPE_ERR_INVALID, "unknown ribbon set");
         const int n = ctx->h_cnt[set];
         const double* src = ctx->h_ribbons.data() + (size_t)ctx->h_off[set] * 4;
         for (int k = 0; k < n && k < cap; k++) memcpy(xyxy + 4 * k, src + 4 * k, 4 * sizeof(double));
         return n;
     }
-    if (ctx->last_off[i] < 0) return fail(ctx, PPE_ERR_CAPACITY, "ribbons-after of this edge were not materialised");
-    if (!ctx->out_downloaded) {
-        PPE_CUDA(ctx, cudaSetDevice(ctx->device));
-        const size_t cnt = (size_t)(ctx->last_out_count < ctx->out_cap ? ctx->last_out_count : ctx->out_cap);
-        ctx->h_out_ribbons.resize(cnt * 4);
-        if (cnt) PPE_CUDA(ctx, cudaMemcpy(ctx->h_out_ribbons.data(), ctx->d_out_ribbons, cnt * sizeof(double4), cudaMemcpyDeviceToHost));
-        ctx->out_downloaded = true;
-    }
-    const int n = ctx->last_n[i];
-    const double* src = ctx->h_out_ribbons.data() + (size_t)ctx->last_off[i] * 4;
-    for (int k = 0; k < n && k < cap; k++) memcpy(xyxy + 4 * k, src + 4 * k, 4 * sizeof(double));
+    if (r.ribbons_offset < 0) return fail(ctx, PPE_ERR_CAPACITY, "ribbons-after of this edge were not materialised");
+    const int n = r.n_ribbons_after;
+    const int m = n < cap ? n : cap;
+    if (m > 0) PPE_CUDA(ctx, cudaMemcpy(xyxy, ctx->d_out_ribbons + r.ribbons_offset, (size_t)m * sizeof(double4), cudaMemcpyDeviceToHost));
     return n;
 }
 

@@ -1016,13 +1016,17 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
     }
 }
 
-__global__ void k3_best_final(const BestD* block_best, int nblocks, BestD* out) {
+// `index_base` turns the slice-local edge indices of one launch into batch indices; with `accumulate` the
+// record of the earlier slices of the same batch (already in *out) takes part in the reduction.
+__global__ void k3_best_final(const BestD* block_best, int nblocks, BestD* out, long long index_base, int accumulate) {
     __shared__ double s_f[256];
     __shared__ long long s_i[256];
     double bf = INFINITY;
     long long bi = -1;
+    if (threadIdx.x == 0 && accumulate) { bf = out->f; bi = out->idx; }
     for (int k = threadIdx.x; k < nblocks; k += blockDim.x) {
-        const BestD b = block_best[k];
+        BestD b = block_best[k];
+        if (b.idx >= 0) b.idx += index_base;
         if (b.idx >= 0 && (bi < 0 || b.f < bf || (b.f == bf && b.idx < bi))) { bf = b.f; bi = b.idx; }
     }
     s_f[threadIdx.x] = bf;
@@ -1165,28 +1169,32 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
     return cudaGetLastError();
 }
 
-cudaError_t launch_true_cost_batch(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
-                                   ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best,
-                                   int max_blocks, BestD* best, int sm_count, cudaStream_t stream, int* launches) {
+// K2a + K2b over one range of edges on `stream`; leaves one BestD per CTA in block_best (*blocks_out of them).
+cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
+                                     ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best,
+                                     int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool, int* blocks_out) {
     PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(world.out_count, 0, sizeof(unsigned long long), stream);
-    if (e != cudaSuccess) return e;
+    if (reset_pool) { // the ribbons-after pool runs over all slices of a batch
+        e = cudaMemsetAsync(world.out_count, 0, sizeof(unsigned long long), stream);
+        if (e != cudaSuccess) return e;
+    }
     k2a_prepare<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(world.cfg, (long long)n, edges, prepared);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int blocks = 1;
 #ifndef PPE_K2_FORCE_NARROW
 #define PPE_K2_FORCE_NARROW 1
 #endif
     if (!PPE_K2_FORCE_NARROW && k2_smem_bytes(kWarpsWide, world.ribbon_cap, world.n_obs) <= 190 * 1024)
-        e = launch_k2<kWarpsWide>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, &blocks);
-    else
-        e = launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, &blocks);
-    if (e != cudaSuccess) return e;
-    k3_best_final<<<1, 256, 0, stream>>>(block_best, blocks, best);
-    if (launches) *launches += 3;
+        return launch_k2<kWarpsWide>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, blocks_out);
+    return launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, blocks_out);
+}
+
+// K3: reduce the per-CTA records of one range into *best; `accumulate` keeps what earlier ranges of the batch left there
+cudaError_t launch_best_final(const BestD* block_best, int blocks, BestD* best, int64_t index_base, bool accumulate,
+                              cudaStream_t stream) {
+    k3_best_final<<<1, 256, 0, stream>>>(block_best, blocks, best, (long long)index_base, accumulate ? 1 : 0);
     return cudaGetLastError();
 }
 

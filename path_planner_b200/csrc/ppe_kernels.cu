@@ -155,32 +155,17 @@ __device__ __noinline__ double collision_exists(int kind, int n_obs, const Obsta
     return sum;
 }
 
-// RibbonManager::minDistanceFrom (RibbonManager.cpp:142-152): lanes over ribbons.
-__device__ __noinline__ double warp_min_distance_from(const double4* cur, int nr, double x, double y, double W,
-                                                         int lane) {
-    if (nr == 0) return 0;
+// One ribbon check-point = RibbonManager::minDistanceFrom (RibbonManager.cpp:142-152) on the list as it stands,
+// then -- when `do_cover` -- RibbonManager::cover(x, y, strict = true) (RibbonManager.cpp:14-22 with Ribbon::split,
+// Ribbon.cpp:9-17, and add, RibbonManager.cpp:154-158), in ONE pass over the ribbons, lanes parallel over ribbons:
+// both need the projection of (x, y) on every ribbon and its distance to the line.  Every ribbon is split
+// independently; list order is kept by a warp prefix sum over the 0 / 1 / 2 pieces each ribbon leaves behind.
+// The new list goes to `alt`; the caller swaps the buffers when something changed.  Returns the new count and the
+// pre-cover minDistanceFrom in *to_cover (0 as soon as any ribbon contains the point, else the nearest endpoint).
+__device__ __noinline__ int warp_checkpoint(const double4* cur, double4* alt, int nr, int cap, double x, double y, double W,
+                                            bool do_cover, int lane, double* to_cover, bool* changed, bool* overflow) {
     double mn = DBL_MAX;
     bool inside = false;
-#pragma unroll 1
-    for (int r = lane; r < nr; r += 32) {
-        const RibbonD rb = load_ribbon(cur + r);
-        double px, py;
-        ribbon_projection(rb, x, y, &px, &py);
-        if (ribbon_contains(rb, x, y, px, py, false, W)) inside = true;
-        const double dStart = point_distance(rb.sx, rb.sy, x, y);
-        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
-        mn = fmin(fmin(mn, dEnd), dStart);
-    }
-    if (__any_sync(kFull, inside)) return 0;
-    return warp_min(mn);
-}
-
-// RibbonManager::cover(x, y, strict = true) (RibbonManager.cpp:14-22 with Ribbon::split,
-// Ribbon.cpp:9-17 and add, RibbonManager.cpp:154-158): every ribbon is split independently; list
-// order is kept by a warp prefix sum over the 0/1/2 pieces each ribbon leaves behind.  Writes the
-// new list into `alt`; the caller swaps the buffers when something changed.
-__device__ __noinline__ int warp_cover(const double4* cur, double4* alt, int nr, int cap, double x, double y,
-                                          double W, int lane, bool* changed, bool* overflow) {
     int out_base = 0;
     bool any_change = false;
 #pragma unroll 1
@@ -193,31 +178,41 @@ __device__ __noinline__ int warp_cover(const double4* cur, double4* alt, int nr,
         if (active) {
             rb = load_ribbon(cur + r);
             ribbon_projection(rb, x, y, &px, &py);
-            contained = ribbon_contains(rb, x, y, px, py, true, W);
+            if (ribbon_contains_projection(rb, px, py)) {   // Ribbon::contains, Ribbon.cpp:39-43
+                const double d = ribbon_distance(rb, x, y);
+                inside = inside || (d < W);                  // non-strict: minDistanceFrom
+                contained = d < W / 2.0;                     // strict: cover
+            }
+            const double dStart = point_distance(rb.sx, rb.sy, x, y);
+            const double dEnd = point_distance(rb.ex, rb.ey, x, y);
+            mn = fmin(fmin(mn, dEnd), dStart);
         }
-        RibbonD piece = {0, 0, 0, 0};
-        RibbonD rest = rb;
-        if (contained) {
-            piece.sx = rb.sx; piece.sy = rb.sy; piece.ex = px; piece.ey = py;
-            rest.sx = px; rest.sy = py;
+        if (do_cover) {
+            RibbonD piece = {0, 0, 0, 0};
+            RibbonD rest = rb;
+            if (contained) {
+                piece.sx = rb.sx; piece.sy = rb.sy; piece.ex = px; piece.ey = py;
+                rest.sx = px; rest.sy = py;
+            }
+            const bool keep_piece = active && contained && !ribbon_covered(piece, true, W);
+            const bool keep_rest = active && !ribbon_covered(rest, true, W);
+            const int cnt = (keep_piece ? 1 : 0) + (keep_rest ? 1 : 0);
+            const int incl = warp_incl_scan(cnt, lane);
+            int off = out_base + incl - cnt;
+            if (keep_piece) {
+                if (off < cap) alt[off] = pack_ribbon(piece.sx, piece.sy, piece.ex, piece.ey);
+                off++;
+            }
+            if (keep_rest) {
+                if (off < cap) alt[off] = pack_ribbon(rest.sx, rest.sy, rest.ex, rest.ey);
+            }
+            const bool ch = active && (contained ? (keep_piece || !keep_rest || px != rb.sx || py != rb.sy) : !keep_rest);
+            any_change |= __any_sync(kFull, ch);
+            out_base += __shfl_sync(kFull, incl, 31);
         }
-        const bool keep_piece = active && contained && !ribbon_covered(piece, true, W);
-        const bool keep_rest = active && !ribbon_covered(rest, true, W);
-        const int cnt = (keep_piece ? 1 : 0) + (keep_rest ? 1 : 0);
-        const int incl = warp_incl_scan(cnt, lane);
-        int off = out_base + incl - cnt;
-        if (keep_piece) {
-            if (off < cap) alt[off] = pack_ribbon(piece.sx, piece.sy, piece.ex, piece.ey);
-            off++;
-        }
-        if (keep_rest) {
-            if (off < cap) alt[off] = pack_ribbon(rest.sx, rest.sy, rest.ex, rest.ey);
-        }
-        const bool ch = active && (contained ? (keep_piece || !keep_rest || px != rb.sx || py != rb.sy) : !keep_rest);
-        any_change |= __any_sync(kFull, ch);
-        out_base += __shfl_sync(kFull, incl, 31);
     }
     __syncwarp();
+    *to_cover = (nr == 0 || __any_sync(kFull, inside)) ? 0.0 : warp_min(mn);
     if (out_base > cap) *overflow = true;
     *changed = any_change;
     return any_change ? (out_base > cap ? cap : out_base) : nr;
@@ -256,15 +251,14 @@ __device__ __noinline__ double warp_max_distance(const double4* cur, int nr, dou
 // holding ~60 registers of per-edge state.
 enum PrepSlot {
     // per segment k = 0..2 (three entries each): start of the segment in normalised path length, turn sign
-    // (+1 L, -1 R, 0 S), base angle, and the affine form of dubins_segment scaled to the world frame:
-    //   x = Ax * sin(ang) + Bx * tl + Cx,   y = Ay * cos(ang) + By * tl + Cy,   ang = sg * tl + bth
-    kOff = 0, kSgn = 3, kBth = 6, kAx = 9, kBx = 12, kCx = 15, kAy = 18, kBy = 21, kCy = 24,
-    kInvRho = 27, kLength, kWStart, kWSpeed, kWEnd, kApprox, kRho, kX0, kY0, kYaw0,
-    kParam0 = 37, kParam1, kParam2, kType, kStatus, kSampleFault,
-    // reference-order segment constants (pose_eval_ref): base x, y and sin / cos of the base angle per segment
-    kRefBx = 43, kRefBy = 46, kRefBs = 49, kRefBc = 52,
-    kT0 = 55,      // first sample time: src time nudged by fmod(t - startStateTime, dt), Edge.cpp:118-120
-    kPrepDoubles = 56
+    // (+1 L, -1 R, 0 S), base angle
+    kOff = 0, kSgn = 3, kBth = 6,
+    // base x, y and sin / cos of the base angle per segment (dubins_segment constants)
+    kRefBx = 9, kRefBy = 12, kRefBs = 15, kRefBc = 18,
+    kInvRho = 21, kLength, kWStart, kWSpeed, kWEnd, kApprox, kRho, kX0, kY0, kYaw0,
+    kParam0 = 31, kParam1, kParam2, kType, kStatus, kSampleFault,
+    kT0 = 37,      // first sample time: src time nudged by fmod(t - startStateTime, dt), Edge.cpp:118-120
+    kPrepDoubles = 40
 };
 struct PreparedEdge {
     double v[kPrepDoubles];
@@ -340,7 +334,7 @@ __device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__
     if (status == PPE_EDGE_OK && approx < 0) status = PPE_EDGE_ERR_NO_PATH; // Edge.cpp:85
 
     double* v = out->v;
-    const double rho_ = path.rho, x0 = path.qi[0], y0 = path.qi[1];
+    const double x0 = path.qi[0], y0 = path.qi[1];
     v[kOff] = 0.0; v[kOff + 1] = smp.p1; v[kOff + 2] = smp.p12;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -348,13 +342,6 @@ __device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__
         v[kSgn + k] = sg;
         v[kBth + k] = smp.bth[k];
         v[kRefBx + k] = smp.bx[k]; v[kRefBy + k] = smp.by[k]; v[kRefBs + k] = smp.bs[k]; v[kRefBc + k] = smp.bc[k];
-        if (sg != 0.0) { // arc: q = (sg (sin - bs) + bx, -sg (cos - bc) + by)
-            v[kAx + k] = rho_ * sg;  v[kBx + k] = 0.0; v[kCx + k] = rho_ * (smp.bx[k] - sg * smp.bs[k]) + x0;
-            v[kAy + k] = -rho_ * sg; v[kBy + k] = 0.0; v[kCy + k] = rho_ * (smp.by[k] + sg * smp.bc[k]) + y0;
-        } else {         // straight: q = (bc tl + bx, bs tl + by)
-            v[kAx + k] = 0.0; v[kBx + k] = rho_ * smp.bc[k]; v[kCx + k] = rho_ * smp.bx[k] + x0;
-            v[kAy + k] = 0.0; v[kBy + k] = rho_ * smp.bs[k]; v[kCy + k] = rho_ * smp.by[k] + y0;
-        }
     }
     v[kInvRho] = 1.0 / path.rho; v[kLength] = smp.length;
     v[kWStart] = w_start; v[kWSpeed] = w_speed; v[kWEnd] = w_end;
@@ -365,6 +352,7 @@ __device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__
     v[kStatus] = (double)status;
     v[kSampleFault] = sample_fault ? 1.0 : 0.0;
     v[kT0] = src_t + fmod(src_t - cfg.start_state_time, cfg.collision_checking_increment / cfg.max_speed);
+    v[kT0 + 1] = 0.0; v[kT0 + 2] = 0.0;
 }
 
 // sin and cos for |x| up to a few thousand (path angles stay within a few turns): three-constant
@@ -470,9 +458,12 @@ __device__ __forceinline__ double time_at_from(const TimeTable* tt, int i, int r
 // out of line: check-points of culled chunks, loop exit, probe pass
 __device__ __noinline__ double time_at(const TimeTable* tt, int i, double dt) { return time_at_from(tt, i, 0, dt); }
 
-// DubinsWrapper::sample (DubinsWrapper.cpp:29-49) with the per-path constants of the prepared record:
-// pose at time t.  `ang` is the un-wrapped path angle; the heading is derived from it only where it is
-// needed (check-points, loop exit).  Returns false when both dubins_path_sample attempts fail.
+// DubinsWrapper::sample (DubinsWrapper.cpp:29-49) with the per-path constants of the prepared record: pose at
+// time t in the reference's operation order (dubins_segment / dubins_path_sample: q = segment(tl) + base,
+// x = q.x * rho + x0).  On straight segments this is the reference's arithmetic bit for bit, which keeps exact
+// f-ties (straight survey lines produce many) breaking the same way; on arcs it differs from glibc by the ~1 ulp
+// of sincos_bounded.  `ang` is the un-wrapped path angle; the heading is derived from it only where it is needed
+// (check-points, loop exit).  Returns false when both dubins_path_sample attempts fail.
 __device__ __forceinline__ bool pose_eval(const double* pe, double t, double* x_out, double* y_out, double* ang_out,
                                           bool* in_time) {
     const double w_start = pe[kWStart];
@@ -487,52 +478,27 @@ __device__ __forceinline__ bool pose_eval(const double* pe, double t, double* x_
         }
     }
     const double tprime = dist * pe[kInvRho];
-    const int k = (tprime < pe[kOff + 1] ? 0 : 1) + (tprime < pe[kOff + 2] ? 0 : 1);
-    const double* seg = pe + k;
-    const double tl = tprime - seg[kOff];
-    const double ang = seg[kSgn] * tl + seg[kBth]; // L: t + th, R: -t + th, S: 0 + th  (dubins_segment)
-    double sn, cs;
-    sincos_bounded(ang, &sn, &cs);
-    *x_out = (seg[kAx] * sn + seg[kBx] * tl) + seg[kCx];
-    *y_out = (seg[kAy] * cs + seg[kBy] * tl) + seg[kCy];
-    *ang_out = ang;
-    return sample_ok;
-}
-
-// The same pose in the reference's operation order (dubins_segment / dubins_path_sample: q = segment(t) + base,
-// x = q.x * rho + x0), out of line.  Everything that reaches an output or a ribbon decision -- check-point
-// poses, the pose the loop exits with, the truncated end state -- is evaluated with THIS function: on straight
-// segments its arithmetic is the reference's bit for bit, which is what keeps exact f-ties (straight survey
-// lines produce many) breaking the same way.  pose_eval above (affine form, 1e-16-class differences) only
-// decides map cells and obstacle sums.
-__device__ __noinline__ bool pose_eval_ref(const double* pe, double t, double* x_out, double* y_out, double* ang_out,
-                                           bool* in_time) {
-    const double w_start = pe[kWStart];
-    *in_time = (w_start <= t) && (pe[kWEnd] >= t);
-    double dist = (t - w_start) * pe[kWSpeed];
-    bool sample_ok = true;
-    {
-        const double length = pe[kLength];
-        if (dist < 0 || dist > length) {
-            dist = dist - 1e-5;
-            sample_ok = !(dist < 0 || dist > length);
-        }
-    }
-    const double tprime = dist * pe[kInvRho];
     const double p1 = pe[kOff + 1];
     const int k = tprime < p1 ? 0 : (tprime < pe[kOff + 2] ? 1 : 2);
     const double tl = k == 0 ? tprime : (k == 1 ? tprime - p1 : tprime - p1 - pe[kParam1]);
-    const double sg = pe[kSgn + k], bth = pe[kBth + k], bs = pe[kRefBs + k], bc = pe[kRefBc + k];
-    const double ang = sg * tl + bth;
+    const double* seg = pe + k;
+    const double sg = seg[kSgn], bth = seg[kBth], bs = seg[kRefBs], bc = seg[kRefBc];
+    const double ang = sg * tl + bth; // L: t + th, R: -t + th, S: 0 + th  (dubins_segment)
     double sn, cs;
     sincos_bounded(ang, &sn, &cs);
-    const double qx = (sg == 0.0 ? bc * tl : sg * (sn - bs)) + pe[kRefBx + k];
-    const double qy = (sg == 0.0 ? bs * tl : -sg * (cs - bc)) + pe[kRefBy + k];
+    const double qx = (sg == 0.0 ? bc * tl : sg * (sn - bs)) + seg[kRefBx];
+    const double qy = (sg == 0.0 ? bs * tl : -sg * (cs - bc)) + seg[kRefBy];
     const double rho = pe[kRho];
     *x_out = qx * rho + pe[kX0];
     *y_out = qy * rho + pe[kY0];
     *ang_out = ang;
     return sample_ok;
+}
+
+// out-of-line copy for the uniform evaluations (loop exit, end state, a check-point on a chunk's first sample)
+__device__ __noinline__ bool pose_eval_ref(const double* pe, double t, double* x_out, double* y_out, double* ang_out,
+                                           bool* in_time) {
+    return pose_eval(pe, t, x_out, y_out, ang_out, in_time);
 }
 
 // mod2pi + State::setYaw (State.h:51-65): heading of a path angle
@@ -700,8 +666,6 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
         bool p_safe = false;          // this lane's chunk of that pass: proved clean
         unsigned long long p_mask = ~0ull;
         int run = 0;                  // time-table run of sample `base`
-        int last_cp = -2;             // index and heading of the last check-point
-        double last_ch = 0;
 
         unsigned p_clean = 0;         // ballot of p_safe over the 32 chunks of that pass
         for (int base = 0;; base += kChunk) {
@@ -735,24 +699,28 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             }
             while (run + 1 < tt->n && base >= tt->i0[run + 1]) run++;
 
-            // ---- lane data of an evaluated chunk ----------------------------------------------------------
-            double t_i = 0, x = 0, y = 0, ang = 0;
-            bool valid = true, blocked = false;
+            // ---- lane data: every chunk that gets here is evaluated, lane i = sample base + i --------------------
+            // (a clean chunk only gets here because a check-point falls into it: its lanes need times and poses,
+            // not map or obstacle look-ups)
+            double x, y, ang;
+            bool valid, blocked = false;
             int limit = kChunk, fstop = kChunk;
             unsigned m_stop = 0;
             n_culled += clean ? 1 : 0;
-            if (!clean) {
-                t_i = time_at_from(tt, base + lane, run, dt);
-                valid = t_i < endTime;
+            const double t_i = time_at_from(tt, base + lane, run, dt);
+            valid = clean || (t_i < endTime);
+            {
                 bool in_time;
                 const bool sample_ok = pose_eval(pe, t_i, &x, &y, &ang, &in_time);
-                if (valid && in_time && sample_ok) blocked = map_blocked(w, x, y);
-                const unsigned m_valid = __ballot_sync(kFull, valid);
-                m_stop = __ballot_sync(kFull, valid && (!in_time || blocked));
-                if (__any_sync(kFull, valid && in_time && !sample_ok)) sample_fault = true;
-                const int nvalid = __popc(m_valid); // valid lanes form a prefix (times increase)
-                fstop = m_stop ? (__ffs(m_stop) - 1) : kChunk;
-                limit = nvalid < fstop ? nvalid : fstop; // samples [base, base + limit) execute the full loop body
+                if (!clean) {
+                    if (valid && in_time && sample_ok) blocked = map_blocked(w, x, y);
+                    const unsigned m_valid = __ballot_sync(kFull, valid);
+                    m_stop = __ballot_sync(kFull, valid && (!in_time || blocked));
+                    if (__any_sync(kFull, valid && in_time && !sample_ok)) sample_fault = true;
+                    const int nvalid = __popc(m_valid); // valid lanes form a prefix (times increase)
+                    fstop = m_stop ? (__ffs(m_stop) - 1) : kChunk;
+                    limit = nvalid < fstop ? nvalid : fstop; // samples [base, base + limit) execute the full loop body
+                }
             }
 
             // ---- ribbon check-points of this chunk, in order (Edge.cpp:153-172) ---------------------------------
@@ -761,55 +729,46 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 if (nr == 0 && cct != -1 && !(cct + cfg.time_minimum < endTime)) {
                     // coverage is complete and the end time has settled: every remaining executed sample of the
                     // chunk is a check-point that only refreshes ribbonsDoneTime = (int) t (Edge.cpp:163-170)
-                    const int lastl = limit - 1;
-                    const double ct_last = clean ? time_at(tt, base + lastl, dt) : __shfl_sync(kFull, t_i, lastl);
                     n_cp += limit - l;
-                    ribbonsDoneTime = (int)ct_last;
+                    ribbonsDoneTime = (int)__shfl_sync(kFull, t_i, limit - 1);
                     next_cp = base + limit;
                     break;
                 }
-                // the check-point's pose, and (non-coverage edges) the heading of the sample before it, in the
-                // reference's operation order
-                const double ct = clean ? time_at(tt, next_cp, dt) : __shfl_sync(kFull, t_i, l);
-                double cx, cy, cang;
-                bool it_;
-                pose_eval_ref(pe, ct, &cx, &cy, &cang, &it_);
-                const double ch = heading_of(cang);
+                const double cx = __shfl_sync(kFull, x, l), cy = __shfl_sync(kFull, y, l);
+                const double ct = __shfl_sync(kFull, t_i, l);
+                const double ch = heading_of(__shfl_sync(kFull, ang, l));
+                const double pang = __shfl_sync(kFull, ang, l > 0 ? l - 1 : 0);
                 n_cp++;
-                const double toCover = warp_min_distance_from(cur, nr, cx, cy, W, lane);
                 bool do_cover = cov;
-                if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159
+                if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159: heading of the sample before
                     double ph;
                     if (next_cp == 0) {
                         ph = edge->src[2];
-                    } else if (next_cp - 1 == last_cp) {
-                        ph = last_ch; // consecutive check-points: the previous sample's heading is at hand
-                    } else {
+                    } else if (l > 0) {
+                        ph = heading_of(pang);
+                    } else { // the last sample of the previous chunk
                         double px_, py_, pa_;
+                        bool it_;
                         pose_eval_ref(pe, time_at(tt, next_cp - 1, dt), &px_, &py_, &pa_, &it_);
                         ph = heading_of(pa_);
                     }
                     do_cover = (ph == ch);
                 }
-                last_cp = next_cp;
-                last_ch = ch;
-                if (do_cover) {
-                    bool changed = false;
-                    const int nn = warp_cover(cur, alt, nr, cap, cx, cy, W, lane, &changed, &overflow);
-                    if (changed) {
-                        double4* tmp = cur; cur = alt; alt = tmp;
-                        nr = nn;
-                        modified = true;
-                    }
+                double toCover;
+                bool changed = false;
+                const int nn = warp_checkpoint(cur, alt, nr, cap, cx, cy, W, do_cover, lane, &toCover, &changed, &overflow);
+                if (changed) {
+                    double4* tmp = cur; cur = alt; alt = tmp;
+                    nr = nn;
+                    modified = true;
                 }
                 if (nr == 0) {
                     if (cct == -1) cct = ct;
                     ribbonsDoneTime = (int)ct;
                     const double newEnd = fmin(endTime, cct + cfg.time_minimum);
-                    if (newEnd < endTime || clean) {
+                    if (newEnd < endTime) {
                         endTime = newEnd;
                         probe_base = -1; // the end moved: probe results are stale
-                        if (clean) t_i = time_at_from(tt, base + lane, run, dt);
                         valid = t_i < endTime;
                         const int nvalid = __popc(__ballot_sync(kFull, valid));
                         limit = nvalid < fstop ? nvalid : fstop;
@@ -833,31 +792,30 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             if (limit < kChunk) {
                 // the loop ends inside this chunk.  The iteration at sample `limit` was entered and broke
                 // out only if that sample is still inside the (possibly truncated) end time.
-                bool stopped = false, stop_blocked = false;
+                bool stopped = false;
+                t_exit = __shfl_sync(kFull, t_i, limit);
                 if (!clean) {
                     const bool stop_lane_valid = __shfl_sync(kFull, (int)valid, limit) != 0;
                     stopped = (fstop == limit) && ((m_stop >> fstop) & 1u) && stop_lane_valid;
-                    stop_blocked = __shfl_sync(kFull, (int)blocked, limit) != 0;
-                    t_exit = __shfl_sync(kFull, t_i, limit);
-                } else {
-                    t_exit = time_at(tt, base + limit, dt);
                 }
                 // pose of the last executed sample (`intermediate`), or the source state when none ran
-                const int last = base + limit - 1;
-                bool it_;
-                if (last >= 0) {
-                    double lx, ly, la;
-                    pose_eval_ref(pe, time_at(tt, last, dt), &lx, &ly, &la, &it_);
-                    P_x = lx; P_y = ly; P_h = heading_of(la);
+                if (limit > 0) {
+                    P_x = __shfl_sync(kFull, x, limit - 1); P_y = __shfl_sync(kFull, y, limit - 1);
+                    P_h = heading_of(__shfl_sync(kFull, ang, limit - 1));
+                    lastHeading = P_h;
+                } else if (base > 0) {
+                    double la;
+                    bool it_;
+                    pose_eval_ref(pe, time_at(tt, base - 1, dt), &P_x, &P_y, &la, &it_);
+                    P_h = heading_of(la);
                     lastHeading = P_h;
                 }
                 if (stopped) {
                     infeasible = true;
                     n_samples += 1; // the breaking iteration was entered
-                    if (stop_blocked) { // `intermediate` holds the blocked sample
-                        double sx_, sy_, sa_;
-                        pose_eval_ref(pe, t_exit, &sx_, &sy_, &sa_, &it_);
-                        P_x = sx_; P_y = sy_; P_h = heading_of(sa_);
+                    if (__shfl_sync(kFull, (int)blocked, limit) != 0) { // `intermediate` holds the blocked sample
+                        P_x = __shfl_sync(kFull, x, limit); P_y = __shfl_sync(kFull, y, limit);
+                        P_h = heading_of(__shfl_sync(kFull, ang, limit));
                     }
                 }
                 break;
@@ -878,7 +836,8 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
     if (status == PPE_EDGE_OK) {
         if (cov || lastHeading == P_h) {
             bool changed = false;
-            const int nn = warp_cover(cur, alt, nr, cap, P_x, P_y, W, lane, &changed, &overflow);
+            double unused;
+            const int nn = warp_checkpoint(cur, alt, nr, cap, P_x, P_y, W, true, lane, &unused, &changed, &overflow);
             if (changed) {
                 double4* tmp = cur; cur = alt; alt = tmp;
                 nr = nn;

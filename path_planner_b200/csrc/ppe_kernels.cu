@@ -125,6 +125,55 @@ __device__ __forceinline__ double obstacle_quadform(const ObstacleD& o, double x
     return r0 * d0 + r1 * d1;
 }
 
+// exp(x) for the Gaussian pdf exponent (x = -q / 2 <= 0): Cody-Waite reduction by ln 2, degree-13 Taylor kernel on
+// |r| <= ln2 / 2 with the coefficients in constant memory, scaling by exponent arithmetic.  <= 1.5 ulp -- the same
+// class as libdevice's exp against glibc's, at a fifth of its instruction count under -fmad=false.  Results below
+// 1e-304 are flushed to 0 (they cannot reach the 1e-5 threshold of collisionExists nor change a sum above it).
+__constant__ double c_exp[12] = {0x1.0000000000000p-1, 0x1.5555555555555p-3, 0x1.5555555555555p-5, 0x1.1111111111111p-7,
+                                 0x1.6c16c16c16c17p-10, 0x1.a01a01a01a01ap-13, 0x1.a01a01a01a01ap-16, 0x1.71de3a556c734p-19,
+                                 0x1.27e4fb7789f5cp-22, 0x1.ae64567f544e4p-26, 0x1.1eed8eff8d898p-29, 0x1.6124613a86d09p-33};
+__constant__ double c_ln2[3] = {0x1.71547652b82fep+0, 0x1.62e42fee00000p-1, 0x1.a39ef35793c76p-33};
+
+__device__ __forceinline__ double exp_pdf(double x) {
+    if (!(x <= 0.0)) return exp(x);    // positive (non positive-definite covariance) or NaN: the library function
+    if (x < -700.0) return 0.0;
+    const double kd = rint(x * c_ln2[0]);
+    double r = __fma_rn(-kd, c_ln2[1], x);
+    r = __fma_rn(-kd, c_ln2[2], r);
+    double p = c_exp[11];
+#pragma unroll
+    for (int j = 10; j >= 0; j--) p = __fma_rn(p, r, c_exp[j]);
+    p = __fma_rn(p * r, r, r) + 1.0;
+    return p * __longlong_as_double((long long)((int)kd + 1023) << 52);
+}
+
+// Upper bound of obstacle i's contribution to collisionExists over a set of samples that all lie within `reach`
+// metres and `half_t` seconds of the probe (x, y, t): binary -- 1 if the inflated rectangle can be reached at all,
+// else 0; gaussian -- an upper bound of the pdf (sqrt(q) is a norm of the relative position: it cannot shrink
+// faster than cull * displacement).  Every rounding goes the safe way.
+__device__ __forceinline__ float obstacle_bound(int kind, const ObstacleD& o, double x, double y, double t, double reach,
+                                                double half_t) {
+    const double reach_i = (reach + fabs(o.Speed) * half_t) * (1 + 1e-9) + 1e-6; // sample moves <= reach, obstacle <= |v| half_t
+    if (kind == kObsBinary) {
+        const double dtm = t - o.Time;
+        const double X = o.X + o.Speed * dtm * o.cosYaw, Y = o.Y + o.Speed * dtm * o.sinYaw;
+        const double tx = x - X, ty = y - Y;
+        const double rx = tx * o.cosYaw - ty * o.sinYaw;
+        const double ry = tx * o.sinYaw + ty * o.cosYaw;
+        return (fabs(rx) < o.a + reach_i && fabs(ry) < o.b + reach_i) ? 1.f : 0.f;
+    }
+    const double q = obstacle_quadform(o, x, y, t);
+    const float sq = __fsqrt_rd(__double2float_rd(fmax(q, 0.0)));
+    const float m = fmaxf(sq - __double2float_ru(reach_i * o.cull), 0.f) * 0.9999f;
+    const float arg = -0.5f * (m * m) * 0.9999f;                 // >= the true exponent
+    const float e = __expf(arg) * 1.001f + 1e-37f;               // >= exp(arg)
+    return __double2float_ru(o.norm) * e * 1.0001f;              // >= max pdf over the set
+}
+
+// obstacles that can matter at all for such a set: bound above the threshold below which a term cannot change a sum
+// that reaches 1e-5 (gaussian), or reachable rectangle (binary)
+constexpr float kCandidateBound = 1e-26f;
+
 __device__ __noinline__ double collision_exists(int kind, int n_obs, const ObstacleD* __restrict__ obs,
                                                    unsigned long long mask, bool use_mask, double x, double y, double time) {
     double sum = 0;
@@ -140,7 +189,7 @@ __device__ __noinline__ double collision_exists(int kind, int n_obs, const Obsta
         while (mask) {
             const int i = __ffsll((long long)mask) - 1;
             mask &= mask - 1;
-            sum += obs[i].norm * exp(-0.5 * obstacle_quadform(obs[i], x, y, time));
+            sum += obs[i].norm * exp_pdf(-0.5 * obstacle_quadform(obs[i], x, y, time));
         }
     } else {
         if (kind == kObsBinary) {
@@ -149,7 +198,7 @@ __device__ __noinline__ double collision_exists(int kind, int n_obs, const Obsta
             return sum;
         }
 #pragma unroll 1
-        for (int i = 0; i < n_obs; i++) sum += obs[i].norm * exp(-0.5 * obstacle_quadform(obs[i], x, y, time));
+        for (int i = 0; i < n_obs; i++) sum += obs[i].norm * exp_pdf(-0.5 * obstacle_quadform(obs[i], x, y, time));
     }
     if (sum < 1e-5) return 0;
     return sum;
@@ -526,8 +575,8 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
 // A proved chunk costs nothing but its check-points.  For the others the lane reports which obstacles can matter
 // at all in the chunk (candidate mask), so the exact per-sample evaluation touches a few obstacles, not all.
 __device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, const TimeTable* tt, const ObstacleD* s_obs,
-                                          int base, int lane, double end_time, double rad, bool* safe_out,
-                                          unsigned long long* mask_out) {
+                                          int base, int lane, double end_time, double rad, unsigned long long edge_mask,
+                                          bool* safe_out, unsigned long long* mask_out) {
     const WorldD& w = *wp;
     const int c0 = base + lane * kChunk;
     const double dt = w.dt;
@@ -548,45 +597,26 @@ __device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, co
     unsigned long long mask = ~0ull;
     if (ok) {
         ok = map_safe(w, x, y);
-        const int n_obs = w.n_obs;
-        if (w.obs_kind != kObsNone && n_obs > 0) {
+        if (w.obs_kind != kObsNone && w.n_obs > 0) {
             if (!w.obs_cull_ok) {
                 ok = false;
             } else {
                 const double half_t = fmax(t_mid - t_first, t_last - t_mid) * (1 + 1e-9);
+                const double reach_m = reach * (1 + 1e-9) + 1e-9;
+                const int kind = w.obs_kind;
+                unsigned long long todo = edge_mask; // obstacles that can matter anywhere on this edge
+                float bound = 0.f;
                 mask = 0;
-                if (w.obs_kind == kObsBinary) {
 #pragma unroll 1
-                    for (int i = 0; i < n_obs; i++) {
-                        const ObstacleD& o = s_obs[i];
-                        const double dtm = t_mid - o.Time;
-                        const double X = o.X + o.Speed * dtm * o.cosYaw, Y = o.Y + o.Speed * dtm * o.sinYaw;
-                        const double tx = x - X, ty = y - Y;
-                        const double rx = tx * o.cosYaw - ty * o.sinYaw;
-                        const double ry = tx * o.sinYaw + ty * o.cosYaw;
-                        // relative displacement over the chunk: the sample moves <= rad, the obstacle <= |v| * half_t
-                        const double reach_i = (rad + fabs(o.Speed) * half_t) * (1 + 1e-9) + 1e-6;
-                        if (fabs(rx) < o.a + reach_i && fabs(ry) < o.b + reach_i) mask |= 1ull << i;
-                    }
-                    ok = ok && (mask == 0);
-                } else {
-                    float bound = 0.f;
-#pragma unroll 1
-                    for (int i = 0; i < n_obs; i++) {
-                        const ObstacleD& o = s_obs[i];
-                        const double q = obstacle_quadform(o, x, y, t_mid);
-                        const double reach_i = (rad + fabs(o.Speed) * half_t) * (1 + 1e-9) + 1e-6;
-                        // sqrt(q) is a norm of the relative position: it cannot shrink faster than cull * displacement
-                        const float sq = __fsqrt_rd(__double2float_rd(fmax(q, 0.0)));
-                        const float m = fmaxf(sq - __double2float_ru(reach_i * o.cull), 0.f) * 0.9999f;
-                        const float arg = -0.5f * (m * m) * 0.9999f;                 // >= the true exponent
-                        const float e = __expf(arg) * 1.001f + 1e-37f;               // >= exp(arg)
-                        const float b_i = __double2float_ru(o.norm) * e * 1.0001f;   // >= max pdf over the chunk
-                        if (b_i >= 1e-26f) mask |= 1ull << i;
-                        bound += b_i;
-                    }
-                    ok = ok && (bound * 1.001f < 1e-5f);
+                while (todo) {
+                    const int i = __ffsll((long long)todo) - 1;
+                    todo &= todo - 1;
+                    const float b_i = obstacle_bound(kind, s_obs[i], x, y, t_mid, reach_m, half_t);
+                    if (b_i >= kCandidateBound) mask |= 1ull << i;
+                    bound += b_i;
                 }
+                // binary: no reachable rectangle; gaussian: the sum of the upper bounds stays below the threshold
+                ok = ok && (kind == kObsBinary ? (mask == 0) : (bound * 1.001f < 1e-5f));
             }
         }
     }
@@ -662,6 +692,23 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
         const double w_speed = pe[kWSpeed];
         const double rad_max = 0.5 * kChunk * inc * 1.001 + 1e-6; // the reach the safe map was dilated for
         const bool probing = !tt->overflow && (w_speed > 0) && (w_speed * dt <= inc * 1.0005);
+        // obstacles that can matter anywhere on this edge (lanes over obstacles): all executed samples lie within
+        // half the travelled arc length and half the time span of the pose at the middle time
+        unsigned long long edge_mask = ~0ull;
+        if (probing && w.obs_kind != kObsNone && w.n_obs > 0 && w.obs_cull_ok) {
+            const double t_c = 0.5 * (t0 + endTime), half_T = (0.5 * (endTime - t0)) * (1 + 1e-9) + 1e-9;
+            double cx_, cy_, ca_;
+            bool it_;
+            const bool okc = pose_eval_ref(pe, t_c, &cx_, &cy_, &ca_, &it_) && it_ && (t0 < endTime);
+            const double reach_e = half_T * w_speed * (1 + 1e-9) + 1e-3;
+            float b0 = 1.f, b1 = 0.f;
+            if (okc) {
+                b0 = lane < w.n_obs ? obstacle_bound(w.obs_kind, s_obs[lane], cx_, cy_, t_c, reach_e, half_T) : 0.f;
+                b1 = lane + 32 < w.n_obs ? obstacle_bound(w.obs_kind, s_obs[lane + 32], cx_, cy_, t_c, reach_e, half_T) : 0.f;
+            }
+            const unsigned lo = __ballot_sync(kFull, b0 >= kCandidateBound), hi = __ballot_sync(kFull, b1 >= kCandidateBound);
+            if (okc) edge_mask = ((unsigned long long)hi << 32) | lo;
+        }
         int probe_base = -1;          // chunk 0 of the last probe pass; -1: no valid probe results
         bool p_safe = false;          // this lane's chunk of that pass: proved clean
         unsigned long long p_mask = ~0ull;
@@ -677,7 +724,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             if (probing) {
                 int m = probe_base >= 0 ? (base - probe_base) / kChunk : 32;
                 if (m >= 32) {
-                    probe_chunks(ws, pe, tt, s_obs, base, lane, endTime, rad_max, &p_safe, &p_mask);
+                    probe_chunks(ws, pe, tt, s_obs, base, lane, endTime, rad_max, edge_mask, &p_safe, &p_mask);
                     p_clean = __ballot_sync(kFull, p_safe);
                     probe_base = base;
                     m = 0;

@@ -16,6 +16,10 @@ grid map with static obstacles and 10 survey ribbons -- as a 2^20-edge sweep per
             (tensor cores are not used; HBM is not the bound -- its fraction is reported too).
   cpu_baseline  the compiled reference (oracle/_ref/libref_planner.so, kind "reference") or the C
             restatement (kind "port") single-threaded on this host, on a bounded sample.
+  dubins    secondary line: K1 Dubins solves per second (HBM-resident), BASELINE metric part (ii).
+  plan      BASELINE metric part (iii), "plan cost at 1 s budget": the reference's AStarPlanner (CPU) and the
+            product's BatchedAStarPlanner (this GPU) each get the same world, start state and a REAL 1.0 s
+            wall-clock budget; f-value of the returned plan (lower is better) and search effort of both.
 """
 import argparse
 import ctypes as C
@@ -129,6 +133,76 @@ def cpu_rate(world, edges, budget_s, threads):
     return n / dt, kind, n, dt
 
 
+PLAN_SCENARIOS = (("c1", None), ("c2", None), ("c2", (470.0, 610.0, 3.0, 2.5, 1.0)), ("c3", (420.0, 395.0, 0.0, 2.5, 1.0)),
+                  ("c3b", (420.0, 395.0, 0.0, 2.5, 1.0)))
+
+
+def plan_at_budget(budget_s, device):
+    """Reference AStarPlanner vs BatchedAStarPlanner with a real wall-clock budget (tick = 0 -> real clock) on
+    the BASELINE worlds C1-C3 (the start states of tests/plan_cases.py)."""
+    from path_planner_b200 import synth
+    from tests import common
+    if not common.have_harness():
+        return {"unavailable": "oracle/_ref/libppe_harness.so not built (needs the reference sources at build time)"}
+    lib = common.load_harness()
+    out = {"budget_s": budget_s, "unit": "f = g + h of the returned plan, seconds (lower is better)", "scenarios": []}
+    for wname, start in PLAN_SCENARIOS:
+        world = synth.WORLDS[wname]()
+        sid = world.upload_ref(lib)
+        st0 = world.start if start is None else np.array(start, dtype=np.float64)
+        rec = {"world": wname, "start": [float(v) for v in st0]}
+        for which in ("ref", "harness"):
+            t0 = time.perf_counter()
+            plan, st = common.run_plan(lib, which, sid, st0, budget_s, 0.0, 0.0, 100, device=device)
+            dt = time.perf_counter() - t0
+            rec["reference_cpu" if which == "ref" else "engine"] = {
+                "f": st["f"] if len(plan) else None, "plan_edges": len(plan), "expanded": int(st["expanded"]),
+                "generated": int(st["generated"]), "samples": int(st["samples"]), "iterations": int(st["iterations"]),
+                "wall_s": round(dt, 3)}
+        out["scenarios"].append(rec)
+    return out
+
+
+def dubins_rate(eng, torch, dev, sh, n=1 << 22, steps=5):
+    """K1: solves/s with inputs resident in HBM (same pose distribution as the edge sweep)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    q0 = torch.rand((n, 3), dtype=torch.float64, device=dev, generator=g) * torch.tensor([200.0, 200.0, 2 * math.pi], dtype=torch.float64, device=dev)
+    q1 = q0.clone()
+    q1[:, :2] += (torch.rand((n, 2), dtype=torch.float64, device=dev, generator=g) - 0.5) * 150.0
+    q1[:, 2] = torch.rand(n, dtype=torch.float64, device=dev, generator=g) * 2 * math.pi
+    rho = torch.full((n,), 8.0, dtype=torch.float64, device=dev)
+    rho[1::2] = 16.0
+    typ = torch.empty(n, dtype=torch.int32, device=dev)
+    err = torch.empty(n, dtype=torch.int32, device=dev)
+    par = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    length = torch.empty(n, dtype=torch.float64, device=dev)
+    args = (n, q0.data_ptr(), q1.data_ptr(), rho.data_ptr(), typ.data_ptr(), par.data_ptr(), length.data_ptr(), err.data_ptr(), sh)
+    for _ in range(2):
+        eng.dubins_batch_device(*args)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        eng.dubins_batch_device(*args)
+    b.record()
+    torch.cuda.synchronize()
+    return n * steps / (a.elapsed_time(b) * 1e-3)
+
+
+def measured_traffic(workload, n):
+    """DRAM bytes of one k2_true_cost launch from the committed `ncu --set full` capture of this very command
+    (profiles/r01_k2_traffic.json), or None when the capture is for another workload / batch size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")) as f:
+            t = json.load(f)
+        for rec in t.get("captures", []):
+            if rec.get("workload") == workload and rec.get("edges") == n:
+                return rec.get("dram_bytes_read", 0) + rec.get("dram_bytes_write", 0)
+    except (OSError, ValueError):
+        pass
+    return None
+
+
 def run_reference(args, world, edges_fn):
     """--impl reference: the reference's CPU implementation, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -181,6 +255,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--near-ribbons", type=float, default=0.0)
+    ap.add_argument("--no-plan", action="store_true", help="skip the plan-cost-at-1-s-budget comparison")
+    ap.add_argument("--plan-budget", type=float, default=1.0)
     args = ap.parse_args()
 
     from path_planner_b200 import abi, synth
@@ -264,6 +340,7 @@ def main():
 
     # per-batch work counters from the result records (int32 columns 47 / 48 = n_samples / n_checkpoints)
     r32 = d_results.view(torch.int32).reshape(n, abi.RESULT_DTYPE.itemsize // 4)
+    culled_chunks = int(r32[:, 51].to(torch.int64).sum().item())  # `reserved`: chunks proved clean by the probe pass
     sum_samples = int(r32[:, 47].to(torch.int64).sum().item())
     sum_cp = int(r32[:, 48].to(torch.int64).sum().item())
     infeasible = int(r32[:, 45].to(torch.int64).sum().item())
@@ -319,6 +396,7 @@ def main():
                        (n * (abi.EDGE_DTYPE.itemsize + abi.RESULT_DTYPE.itemsize) / 1e6),
                        "mean_samples_per_edge": sum_samples / n, "mean_checkpoints_per_edge": sum_cp / n,
                        "infeasible_edges": infeasible, "edges_with_status": bad_status,
+                       "culled_sample_fraction": 32.0 * culled_chunks / max(1, sum_samples),
                        "parallelism": "edges sharded over %d GPU(s), one process per GPU" % world_size},
             "e2e": {"value": world_size * n * e2e_steps / e2e_s_max, "unit": "edges/s",
                     "h2d_bytes_per_step": n * abi.EDGE_DTYPE.itemsize, "d2h_bytes_per_step": n * abi.RESULT_DTYPE.itemsize + 8,
@@ -329,12 +407,22 @@ def main():
                 "bound": "fp64", "kernel": "k2_true_cost", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
                 "peak_source": "measured live: ppe_measure_fp64_peak (DFMA chain, 2 flop/FMA) -- MEASURED_PEAKS.json has no fp64 entry",
-                "flops_per_launch": flops, "traffic": None,
+                "flops_per_launch": flops, "traffic": measured_traffic(args.workload, n),
+                "note": "achieved = ALGORITHMIC flops (SURVEY 8d: every executed sample point of the reference loop) / launch time; "
+                        "the kernel proves config.culled_sample_fraction of the sample points clean in 32-sample chunks and does "
+                        "not evaluate them, so frac measures work done per second in the reference's units and can exceed 1",
                 "hbm": {"achieved": bytes_alg / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                         "bytes_moved_per_launch": n * (abi.EDGE_DTYPE.itemsize + abi.RESULT_DTYPE.itemsize)},
             },
         }
+        line["dubins"] = {"metric": "dubins_solves_per_sec", "value": dubins_rate(eng, torch, dev, sh), "unit": "solves/s",
+                          "n": 1 << 22, "note": "K1, one GPU, HBM-resident, correctly rounded transcendentals"}
+        if world_size == 1 and not args.no_plan:
+            try:
+                line["plan"] = plan_at_budget(args.plan_budget, local_rank)
+            except Exception as ex:  # the comparison is auxiliary: never lose the bench line over it
+                line["plan"] = {"unavailable": "%s: %s" % (type(ex).__name__, ex)}
         if world_size == 1 and not args.no_cpu_baseline:
             rate, kind, ns, dt = cpu_rate(world, edges, args.cpu_seconds, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "edges/s", "cores": 1, "kind": kind,

@@ -31,7 +31,9 @@ struct ppe_ctx {
         cudaStream_t stream = nullptr;
         unsigned char* d_prepared = nullptr;
         size_t cap_prepared = 0;
-        unsigned long long* d_work = nullptr;
+        unsigned int* d_heavy = nullptr;   // heavy list of the lane's slice (K2t -> K2b)
+        size_t cap_heavy = 0;
+        unsigned long long* d_work = nullptr; // [0] K2b work counter, [1] heavy-list length
         BestD* d_block_best = nullptr;
         cudaEvent_t ev_k3 = nullptr; // K3 of the lane's previous slice has consumed d_block_best
         bool used = false;
@@ -82,7 +84,10 @@ struct ppe_ctx {
     unsigned long long* d_out_count = nullptr;
     size_t out_cap = 0;
 
-    unsigned long long* d_work = nullptr;
+    unsigned long long* d_work = nullptr; // [0] K2b work counter, [1] heavy-list length
+    unsigned int* d_heavy = nullptr;
+    size_t cap_heavy = 0;
+    bool thread_walker = true;            // PPE_THREAD_WALKER=0: the warp walker evaluates every edge
     BestD* d_block_best = nullptr;
     BestD* d_best = nullptr;
     int max_blocks = 0;
@@ -271,13 +276,17 @@ int ppe_create(int device, ppe_ctx** out) {
         cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PPE_ERR_CUDA; }
     ctx->max_blocks = ctx->sm_count * 32;
-    bool ok = cudaMalloc((void**)&ctx->d_work, sizeof(unsigned long long)) == cudaSuccess &&
+    {
+        const char* env = getenv("PPE_THREAD_WALKER");
+        if (env && env[0] == '0') ctx->thread_walker = false;
+    }
+    bool ok = cudaMalloc((void**)&ctx->d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_out_count, sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_block_best, (size_t)ctx->max_blocks * sizeof(BestD)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_best, sizeof(BestD)) == cudaSuccess;
     for (auto& ln : ctx->lanes) {
         ok = ok && cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaMalloc((void**)&ln.d_work, sizeof(unsigned long long)) == cudaSuccess &&
+             cudaMalloc((void**)&ln.d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
              cudaMalloc((void**)&ln.d_block_best, (size_t)ctx->max_blocks * sizeof(BestD)) == cudaSuccess &&
              cudaEventCreateWithFlags(&ln.ev_k3, cudaEventDisableTiming) == cudaSuccess;
     }
@@ -294,13 +303,13 @@ void ppe_destroy(ppe_ctx* ctx) {
     cudaFree(ctx->d_ribbons); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct);
     cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_prepared); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
-    cudaFree(ctx->d_work); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_heavy); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
     for (auto& ln : ctx->lanes) {
         if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
-        cudaFree(ln.d_prepared); cudaFree(ln.d_work); cudaFree(ln.d_block_best);
+        cudaFree(ln.d_prepared); cudaFree(ln.d_heavy); cudaFree(ln.d_work); cudaFree(ln.d_block_best);
         if (ln.ev_k3) cudaEventDestroy(ln.ev_k3);
     }
     for (cudaEvent_t e : ctx->ev_k2) cudaEventDestroy(e);
@@ -512,11 +521,16 @@ static int run_batch_device(ppe_ctx* ctx, const WorldD& w, int64_t n, const ppe_
                             cudaStream_t stream) {
     int rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, (size_t)n * prepared_edge_bytes());
     if (rc != PPE_OK) return rc;
-    int blocks = 1;
-    PPE_CUDA(ctx, launch_true_cost_kernels(w, n, d_edges, ctx->d_prepared, d_results, ctx->d_work, ctx->d_block_best,
-                                           ctx->max_blocks, ctx->sm_count, stream, true, &blocks));
+    if (ctx->thread_walker) {
+        rc = grow(ctx, &ctx->d_heavy, &ctx->cap_heavy, (size_t)n);
+        if (rc != PPE_OK) return rc;
+    }
+    int blocks = 1, launches = 0;
+    PPE_CUDA(ctx, launch_true_cost_kernels(w, n, d_edges, ctx->d_prepared, d_results, ctx->d_work,
+                                           ctx->thread_walker ? ctx->d_heavy : nullptr, ctx->d_block_best, ctx->max_blocks,
+                                           ctx->sm_count, stream, true, &blocks, &launches));
     PPE_CUDA(ctx, launch_best_final(ctx->d_block_best, blocks, ctx->d_best, 0, false, stream));
-    ctx->launches += 3;
+    ctx->launches += launches + 1;
     return PPE_OK;
 }
 
@@ -588,19 +602,24 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
             ppe_ctx::Lane& ln = ctx->lanes[k & 1];
             rc = grow(ctx, &ln.d_prepared, &ln.cap_prepared, (size_t)cnt * prepared_edge_bytes());
             if (rc != PPE_OK) return rc;
+            if (ctx->thread_walker) {
+                rc = grow(ctx, &ln.d_heavy, &ln.cap_heavy, (size_t)cnt);
+                if (rc != PPE_OK) return rc;
+            }
             PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_edges + lo, edges + lo, (size_t)cnt * sizeof(ppe_edge), cudaMemcpyHostToDevice, ctx->stream_in));
             PPE_CUDA(ctx, cudaEventRecord(ctx->ev_in[k], ctx->stream_in));
             PPE_CUDA(ctx, cudaStreamWaitEvent(ln.stream, ctx->ev_in[k], 0));
             if (ln.used) PPE_CUDA(ctx, cudaStreamWaitEvent(ln.stream, ln.ev_k3, 0)); // its block_best has been consumed
-            int blocks = 1;
+            int blocks = 1, launches = 0;
             PPE_CUDA(ctx, launch_true_cost_kernels(w, cnt, ctx->d_edges + lo, ln.d_prepared, ctx->d_results + lo, ln.d_work,
-                                                   ln.d_block_best, ctx->max_blocks, ctx->sm_count, ln.stream, false, &blocks));
+                                                   ctx->thread_walker ? ln.d_heavy : nullptr, ln.d_block_best, ctx->max_blocks,
+                                                   ctx->sm_count, ln.stream, false, &blocks, &launches));
             PPE_CUDA(ctx, cudaEventRecord(ctx->ev_k2[k], ln.stream));
             PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_k2[k], 0));
             PPE_CUDA(ctx, launch_best_final(ln.d_block_best, blocks, ctx->d_best, lo, k > 0, ctx->stream));
             PPE_CUDA(ctx, cudaEventRecord(ln.ev_k3, ctx->stream));
             ln.used = true;
-            ctx->launches += 3;
+            ctx->launches += launches + 1;
             PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_out, ctx->ev_k2[k], 0));
             PPE_CUDA(ctx, cudaMemcpyAsync(results + lo, ctx->d_results + lo, (size_t)cnt * sizeof(ppe_edge_result), cudaMemcpyDeviceToHost, ctx->stream_out));
         }

@@ -309,12 +309,22 @@ enum PrepSlot {
     kT0 = 37,      // first sample time: src time nudged by fmod(t - startStateTime, dt), Edge.cpp:118-120
     kPrepDoubles = 40
 };
+// + the edge's sample-time table (see TimeTable below), built by K2a when it fits kPrepRuns runs
+constexpr int kPrepRuns = 8;
 struct PreparedEdge {
     double v[kPrepDoubles];
+    double run_base[kPrepRuns];
+    double run_D[kPrepRuns];
+    double t_after;
+    int run_i0[kPrepRuns];
+    int n_runs;   // 0: needs more runs than fit here -- the warp walker builds its own table
+    int i_after;
+    int pad_[2];
 };
 
 // Edge.cpp:73-85, Edge::setEnd :208-215, DubinsWrapper.cpp:9-17,84-93 -- scalar, one thread.
-__device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__ edge, PreparedEdge* __restrict__ out) {
+__device__ void prepare_edge(const ppe_config& cfg, double dt, double horizon_end, const ppe_edge* __restrict__ edge,
+                             PreparedEdge* __restrict__ out) {
     const double src_x = edge->src[0], src_y = edge->src[1], src_h = edge->src[2], src_speed = edge->src[3],
                  src_t = edge->src[4];
     const bool has_path = edge->has_path != 0;
@@ -400,8 +410,34 @@ __device__ void prepare_edge(const ppe_config& cfg, const ppe_edge* __restrict__
     v[kType] = (double)path.type;
     v[kStatus] = (double)status;
     v[kSampleFault] = sample_fault ? 1.0 : 0.0;
-    v[kT0] = src_t + fmod(src_t - cfg.start_state_time, cfg.collision_checking_increment / cfg.max_speed);
+    const double t0 = src_t + fmod(src_t - cfg.start_state_time, dt);
+    v[kT0] = t0;
     v[kT0 + 1] = 0.0; v[kT0 + 2] = 0.0;
+
+    // sample-time table (exact replay of `t += dt`): runs until one STARTS at or beyond the end time
+    {
+        const double end_time = fmin(horizon_end, w_end);
+        const int edt = (dt > 0) ? f64_exponent(dt) : -2000;
+        double t = t0;
+        int i = 0, n = 0;
+        bool fits = (status == PPE_EDGE_OK) && (dt > 0);
+        while (fits) {
+            TimeWalker tw;
+            tw.dt = dt; tw.edt = edt; tw.base = t; tw.i0 = 0;
+            tw.build();
+            out->run_base[n] = t; out->run_D[n] = tw.D; out->run_i0[n] = i;
+            n++;
+            const bool past = !(t < end_time);
+            i += tw.cnt;
+            t = tw.t_next;
+            if (past) break;
+            if (n == kPrepRuns || i > (1 << 22)) fits = false;
+        }
+        out->n_runs = fits ? n : 0;
+        out->i_after = i;
+        out->t_after = t;
+        out->pad_[0] = out->pad_[1] = 0;
+    }
 }
 
 // sin and cos for |x| up to a few thousand (path angles stay within a few turns): three-constant
@@ -574,29 +610,26 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
 //     collisionExists returns exactly 0 for every sample.
 // A proved chunk costs nothing but its check-points.  For the others the lane reports which obstacles can matter
 // at all in the chunk (candidate mask), so the exact per-sample evaluation touches a few obstacles, not all.
-__device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, const TimeTable* tt, const ObstacleD* s_obs,
-                                          int base, int lane, double end_time, double rad, unsigned long long edge_mask,
-                                          bool* safe_out, unsigned long long* mask_out) {
-    const WorldD& w = *wp;
-    const int c0 = base + lane * kChunk;
-    const double dt = w.dt;
-    const double t_first = time_at(tt, c0, dt);
-    const double t_mid = time_at(tt, c0 + kChunk / 2, dt);
-    const double t_last = time_at(tt, c0 + kChunk - 1, dt);
+// the proof for ONE chunk, given the times of its first, middle and last sample; shared by the warp walker (lane m
+// probes chunk m of the next 32) and the thread walker (a thread probes its edge's chunks one after the other)
+__device__ __forceinline__ bool probe_one(const WorldD& w, const double* pe, double t_first, double t_mid, double t_last,
+                                          const ObstacleD* s_obs, double end_time, double rad, unsigned long long edge_mask,
+                                          unsigned long long* mask_out) {
     const double w_start = pe[kWStart], w_speed = pe[kWSpeed];
-    bool ok = (t_last < end_time) && (w_start <= t_first) && (pe[kWEnd] >= t_last) && (t_first <= t_mid) && (t_mid <= t_last);
+    bool ok = (t_last < end_time) && (w_start <= t_first) && (pe[kWEnd] >= t_last);
     const double d_first = (t_first - w_start) * w_speed, d_last = (t_last - w_start) * w_speed;
     ok = ok && !(d_first < 0) && !(d_last > pe[kLength]);
     // arc length between the probe and either end of the chunk, from the actual sample times
     const double reach = fmax(t_mid - t_first, t_last - t_mid) * w_speed;
-    ok = ok && (reach * (1 + 1e-9) + 1e-9 <= rad);
+    bool near = (t_first <= t_mid) && (t_mid <= t_last) && (reach * (1 + 1e-9) + 1e-9 <= rad);
     double x = 0, y = 0, ang = 0;
     bool in_time = false;
     const bool sample_ok = pose_eval(pe, t_mid, &x, &y, &ang, &in_time);
-    ok = ok && sample_ok && in_time;
-    unsigned long long mask = ~0ull;
-    if (ok) {
-        ok = map_safe(w, x, y);
+    near = near && sample_ok && in_time; // every sample of the chunk lies within `reach` of a valid probe pose
+    ok = ok && near;
+    unsigned long long mask = w.n_obs >= 64 ? ~0ull : ((1ull << w.n_obs) - 1ull); // no bound: every obstacle is a candidate
+    if (near) {
+        ok = ok && map_safe(w, x, y);
         if (w.obs_kind != kObsNone && w.n_obs > 0) {
             if (!w.obs_cull_ok) {
                 ok = false;
@@ -620,8 +653,19 @@ __device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, co
             }
         }
     }
-    *safe_out = ok;
     *mask_out = mask;
+    return ok;
+}
+
+__device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, const TimeTable* tt, const ObstacleD* s_obs,
+                                          int base, int lane, double end_time, double rad, unsigned long long edge_mask,
+                                          bool* safe_out, unsigned long long* mask_out) {
+    const int c0 = base + lane * kChunk;
+    const double dt = wp->dt;
+    const double t_first = time_at(tt, c0, dt);
+    const double t_mid = time_at(tt, c0 + kChunk / 2, dt);
+    const double t_last = time_at(tt, c0 + kChunk - 1, dt);
+    *safe_out = probe_one(*wp, pe, t_first, t_mid, t_last, s_obs, end_time, rad, edge_mask, mask_out);
 }
 
 // One edge, one warp.  Per-edge scalars that every lane would hold identically live in the warp's
@@ -688,13 +732,19 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
     }
 
     if (status == PPE_EDGE_OK) {
-        time_table_build(tt, t0, dt, endTime, lane);
+        if (prep->n_runs > 0) { // built by K2a
+            if (lane < kPrepRuns) { tt->base[lane] = prep->run_base[lane]; tt->D[lane] = prep->run_D[lane]; tt->i0[lane] = prep->run_i0[lane]; }
+            if (lane == 0) { tt->n = prep->n_runs; tt->i_after = prep->i_after; tt->t_after = prep->t_after; tt->overflow = 0; }
+            __syncwarp();
+        } else {
+            time_table_build(tt, t0, dt, endTime, lane);
+        }
         const double w_speed = pe[kWSpeed];
         const double rad_max = 0.5 * kChunk * inc * 1.001 + 1e-6; // the reach the safe map was dilated for
         const bool probing = !tt->overflow && (w_speed > 0) && (w_speed * dt <= inc * 1.0005);
         // obstacles that can matter anywhere on this edge (lanes over obstacles): all executed samples lie within
         // half the travelled arc length and half the time span of the pose at the middle time
-        unsigned long long edge_mask = ~0ull;
+        unsigned long long edge_mask = w.n_obs >= 64 ? ~0ull : ((1ull << w.n_obs) - 1ull);
         if (probing && w.obs_kind != kObsNone && w.n_obs > 0 && w.obs_cull_ok) {
             const double t_c = 0.5 * (t0 + endTime), half_T = (0.5 * (endTime - t0)) * (1 + 1e-9) + 1e-9;
             double cx_, cy_, ca_;
@@ -960,20 +1010,309 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
     if (!infeasible && status == PPE_EDGE_OK && h >= 0) *out_f = g + h;
 }
 
-// K2a: one thread per edge
-__global__ void __launch_bounds__(128)
-k2a_prepare(const ppe_config cfg, const long long n, const ppe_edge* __restrict__ edges, PreparedEdge* __restrict__ prepared) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    prepare_edge(cfg, edges + i, prepared + i);
+// ---- K2t: the thread walker -------------------------------------------------------------------------------------------
+// Once the probe pass removes ~95 % of the per-sample work, what is left of a typical edge is SEQUENTIAL: a handful of
+// ribbon check-points, the loop exit, the end state, cost and heuristic.  A warp spends 32 lanes on that uniform work;
+// one thread per edge spends one, and 32 edges share every instruction fetch.  K2t therefore walks each edge in one
+// thread -- the same loop, the same device functions (time table, pose_eval, probe_one, collision_exists, skip_count,
+// Ribbon primitives), chunks proved clean skipped, the others evaluated sample by sample -- as long as the edge stays
+// SIMPLE: the parent's ribbon list is never changed (so it is read in place from the interned pool and `cover` reduces
+// to "would it change anything?") and the check-point budget is not exceeded.  Anything else (a cover that splits or
+// erases a ribbon, coverage already complete, a non-OK status, unusual time scales) puts the edge on the heavy list and
+// the warp walker K2b evaluates it from scratch; both paths produce the same bits.
+constexpr int kThreadCheckpointBudget = 24;
+constexpr int kThreadDirtyBudget = 6; // chunks a thread evaluates sample by sample before handing the edge over
+
+struct SeqTime { // cursor over the prepared run table
+    const PreparedEdge* p;
+    int r;
+    __device__ __forceinline__ double at(int i) {
+        while (r + 1 < p->n_runs && i >= p->run_i0[r + 1]) r++;
+        while (r > 0 && i < p->run_i0[r]) r--;
+        return p->run_base[r] + (double)(i - p->run_i0[r]) * p->run_D[r];
+    }
+};
+
+// minDistanceFrom + "would cover(x, y, strict) change the list?" over the parent's ribbons, in place
+__device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib, int nr, double x, double y, double W,
+                                                 bool* would_change) {
+    double mn = DBL_MAX;
+    bool inside = false, change = false;
+#pragma unroll 1
+    for (int r = 0; r < nr; r++) {
+        const RibbonD rb = load_ribbon(rib + r);
+        double px, py;
+        ribbon_projection(rb, x, y, &px, &py);
+        bool contained = false;
+        if (ribbon_contains_projection(rb, px, py)) {
+            const double d = ribbon_distance(rb, x, y);
+            inside = inside || (d < W);
+            contained = d < W / 2.0;
+        }
+        // cover leaves a ribbon as it is iff it is not (strictly) contained and not already short enough to erase
+        change = change || contained || ribbon_covered(rb, true, W);
+        const double dStart = point_distance(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart);
+    }
+    *would_change = change;
+    return inside ? 0.0 : mn;
 }
 
-// K2b: one warp per edge, persistent CTAs pulling edges from a global counter
+__device__ __forceinline__ double seq_max_distance(const double4* __restrict__ rib, int nr, double x, double y, double W) {
+    double sumLength = 0, mn = DBL_MAX, mx = 0;
+#pragma unroll 1
+    for (int r = 0; r < nr; r++) { // list order, as the reference sums (RibbonManager.cpp:234-248)
+        const RibbonD rb = load_ribbon(rib + r);
+        sumLength += sqrt(ribbon_sqlen(rb)) - 2 * W;
+        const double dStart = point_distance(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart);
+        mx = fmax(fmax(mx, dEnd), dStart);
+    }
+    return fmax(sumLength + mn, mx);
+}
+
+__global__ void __launch_bounds__(128)
+k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
+                const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
+                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count) {
+    extern __shared__ double4 smem4[];
+    ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
+    {
+        const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
+        double* dst = reinterpret_cast<double*>(s_obs);
+        const double* src = reinterpret_cast<const double*>(w.obstacles);
+        for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const long long ei = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ei >= n) return;
+    const ppe_edge* edge = edges + ei;
+    const PreparedEdge* prep = prepared + ei;
+    const double* pe = prep->v;
+    const ppe_config& cfg = w.cfg;
+    const double W = cfg.ribbon_width, inc = cfg.collision_checking_increment, dt = w.dt;
+
+    // ---- is this edge simple at all? -------------------------------------------------------------------------------
+    const int set = edge->ribbon_set;
+    bool heavy = !(set >= 0 && set < w.n_sets) || pe[kStatus] != 0.0 || pe[kSampleFault] != 0.0 || prep->n_runs <= 0;
+    int nr = 0;
+    double cct = -1;
+    const double4* rib = nullptr;
+    if (!heavy) {
+        nr = w.set_count[set];
+        cct = w.set_cct[set];
+        rib = w.ribbons + w.set_offset[set];
+        heavy = nr <= 0 || nr > w.ribbon_cap; // coverage already complete: every sample is a check-point (warp walker)
+    }
+    const double src_t = edge->src[4];
+    const bool cov = edge->coverage_allowed != 0;
+    const double endTime = fmin(w.horizon_end, pe[kWEnd]);
+    const double t0 = pe[kT0];
+    const double w_speed = pe[kWSpeed];
+    if (!heavy) {
+        const double span = (endTime - t0) / dt;
+        heavy = !((dt > 0) && (span < (double)kMaxSamples || !(t0 < endTime))) || !((w_speed > 0) && (w_speed * dt <= inc * 1.0005)) ||
+                (w.obs_kind != kObsNone && w.n_obs > 0 && !w.obs_cull_ok);
+    }
+
+    double penalty = 0;
+    bool infeasible = src_t >= endTime;
+    int n_samples = 0, n_cp = 0, n_culled = 0;
+    double P_x = edge->src[0], P_y = edge->src[1], P_h = edge->src[2], lastHeading = edge->src[2];
+    double ex = 0, ey = 0, eh = 0;
+    const int status = PPE_EDGE_OK;
+    bool blocked_exit = false;
+
+    if (!heavy) {
+        SeqTime tm{prep, 0};
+        const double rad_max = 0.5 * kChunk * inc * 1.001 + 1e-6;
+        // obstacles that can matter anywhere on this edge
+        unsigned long long edge_mask = w.n_obs >= 64 ? ~0ull : ((1ull << w.n_obs) - 1ull);
+        if (w.obs_kind != kObsNone && w.n_obs > 0) {
+            const double t_c = 0.5 * (t0 + endTime), half_T = (0.5 * (endTime - t0)) * (1 + 1e-9) + 1e-9;
+            double cx_, cy_, ca_;
+            bool it_;
+            if (pose_eval(pe, t_c, &cx_, &cy_, &ca_, &it_) && it_ && (t0 < endTime)) {
+                const double reach_e = half_T * w_speed * (1 + 1e-9) + 1e-3;
+                edge_mask = 0;
+#pragma unroll 1
+                for (int i = 0; i < w.n_obs; i++)
+                    if (obstacle_bound(w.obs_kind, s_obs[i], cx_, cy_, t_c, reach_e, half_T) >= kCandidateBound) edge_mask |= 1ull << i;
+            }
+        }
+
+        int next_cp = 0;
+        int i = 0;                 // next sample index
+        double prev_ang = 0;       // path angle of sample i - 1 when have_prev
+        bool have_prev = false;
+        double lx = 0, ly = 0, la = 0; // pose of the last executed sample when have_last
+        bool have_last = false;
+        unsigned long long omask = 0;
+        int n_dirty = 0;
+
+        // one ribbon check-point (Edge.cpp:155-171) at sample `idx` with pose (x, y, ang); false: the edge is not simple
+        auto checkpoint = [&](int idx, double x, double y, double ang) -> bool {
+            if (++n_cp > kThreadCheckpointBudget) return false;
+            bool would_change;
+            const double toCover = seq_checkpoint(rib, nr, x, y, W, &would_change);
+            bool do_cover = cov;
+            if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159
+                double ph;
+                if (idx == 0) ph = edge->src[2];
+                else if (have_prev) ph = heading_of(prev_ang);
+                else {
+                    double px_, py_, pa_;
+                    bool it_;
+                    pose_eval(pe, tm.at(idx - 1), &px_, &py_, &pa_, &it_);
+                    ph = heading_of(pa_);
+                }
+                do_cover = (ph == heading_of(ang));
+            }
+            if (do_cover && would_change) return false;
+            next_cp = idx + 1 + skip_count(toCover, inc, kSkipCap);
+            return true;
+        };
+
+        for (;;) {
+            if (i > kMaxSamples) { heavy = true; break; }
+            if ((i & (kChunk - 1)) == 0) { // chunk boundary: probe
+                const double t_first = tm.at(i), t_mid = tm.at(i + kChunk / 2), t_last = tm.at(i + kChunk - 1);
+                if (probe_one(w, pe, t_first, t_mid, t_last, s_obs, endTime, rad_max, edge_mask, &omask)) {
+                    // a clean chunk: all 32 samples run, nothing discrete happens; only its check-points are evaluated
+                    n_culled++;
+                    have_prev = false;
+                    while (next_cp < i + kChunk) {
+                        double x, y, ang;
+                        bool it_;
+                        const int idx = next_cp;
+                        pose_eval(pe, tm.at(idx), &x, &y, &ang, &it_);
+                        if (!checkpoint(idx, x, y, ang)) { heavy = true; break; }
+                        prev_ang = ang;
+                        have_prev = (next_cp == idx + 1); // only consecutive check-points reuse it
+                    }
+                    if (heavy) break;
+                    have_prev = false;
+                    have_last = false;
+                    i += kChunk;
+                    n_samples += kChunk;
+                    continue;
+                }
+                if (++n_dirty > kThreadDirtyBudget) { heavy = true; break; } // per-sample work belongs to the warp walker
+            }
+            // ---- one iteration of the loop (Edge.cpp:125-175) for sample i of an evaluated chunk -------------------------
+            const double t_i = tm.at(i);
+            if (!(t_i < endTime)) break;
+            double x, y, ang;
+            bool in_time;
+            const bool sample_ok = pose_eval(pe, t_i, &x, &y, &ang, &in_time);
+            if (!in_time) { infeasible = true; n_samples++; break; }                          // sample() throws, Edge.cpp:126-133
+            if (!sample_ok) { heavy = true; break; }                                          // stale-pose corner: warp walker
+            if (map_blocked(w, x, y)) {                                                       // Edge.cpp:144-147
+                infeasible = true;
+                n_samples++;
+                // `intermediate` holds the blocked sample; lastHeading is still the heading of the sample before
+                if (i > 0) {
+                    if (!have_prev) {
+                        double px_, py_;
+                        bool it_;
+                        pose_eval(pe, tm.at(i - 1), &px_, &py_, &prev_ang, &it_);
+                    }
+                    lastHeading = heading_of(prev_ang);
+                }
+                P_x = x; P_y = y; P_h = heading_of(ang);
+                blocked_exit = true;
+                break;
+            }
+            if (w.obs_kind != kObsNone && w.n_obs > 0 && omask != 0)
+                penalty += collision_exists(w.obs_kind, w.n_obs, s_obs, omask, true, x, y, t_i) * cfg.collision_penalty_factor;
+            if (i == next_cp && !checkpoint(i, x, y, ang)) { heavy = true; break; }
+            prev_ang = ang; have_prev = true;
+            lx = x; ly = y; la = ang; have_last = true;
+            n_samples++;
+            i++;
+        }
+        if (!heavy && !blocked_exit && i > 0) {
+            // the loop ended at sample i (its time is at or beyond the end time, or its sample throws): `intermediate` is
+            // the last executed sample
+            if (!have_last) {
+                bool it_;
+                pose_eval(pe, tm.at(i - 1), &lx, &ly, &la, &it_);
+            }
+            P_x = lx; P_y = ly; P_h = heading_of(la);
+            lastHeading = P_h;
+        }
+        if (!heavy) {
+            // ---- truncated end state (Edge.cpp:177-179) and the final cover (:182-191) ----------------------------------
+            double ea;
+            bool in_time;
+            const bool sample_ok = pose_eval(pe, endTime, &ex, &ey, &ea, &in_time);
+            eh = heading_of(ea);
+            if (!in_time || !sample_ok) heavy = true; // the reference throws / stale pose: let the warp walker report it
+            if (!heavy && (cov || lastHeading == P_h)) {
+                bool would_change;
+                seq_checkpoint(rib, nr, P_x, P_y, W, &would_change);
+                if (would_change) heavy = true;
+            }
+        }
+    }
+
+    if (heavy) {
+        const unsigned int k = atomicAdd(heavy_count, 1u);
+        heavy_list[k] = (unsigned int)ei;
+        return;
+    }
+
+    // ---- cost, g, h and the result record (Edge.cpp:193-203); ribbons unchanged, coverage not complete -----------------
+    const double netTime = endTime - src_t;
+    const double T = fmax(netTime - 0.0, 0.0);
+    const double true_cost = T * cfg.time_penalty_factor + penalty;
+    const double g = edge->src_g + true_cost;
+    double h = -1;
+    if (cfg.heuristic == PPE_H_MAX_DISTANCE) h = seq_max_distance(rib, nr, ex, ey, W) / cfg.max_speed * cfg.time_penalty_factor;
+    ppe_edge_result* r = results + ei;
+    r->true_cost = true_cost;
+    r->collision_penalty = penalty;
+    r->approx_cost = pe[kApprox];
+    r->end[0] = ex; r->end[1] = ey; r->end[2] = eh; r->end[3] = w_speed; r->end[4] = endTime;
+    r->g = g;
+    r->h = h;
+    r->coverage_completed_time = cct;
+    r->path_qi[0] = pe[kX0]; r->path_qi[1] = pe[kY0]; r->path_qi[2] = pe[kYaw0];
+    r->path_param[0] = pe[kParam0]; r->path_param[1] = pe[kParam1]; r->path_param[2] = pe[kParam2];
+    r->path_rho = pe[kRho];
+    r->w_speed = w_speed;
+    r->w_start_time = pe[kWStart];
+    r->w_end_time = endTime;
+    r->ribbons_offset = -1;
+    r->path_type = (int)pe[kType];
+    r->infeasible = infeasible ? 1 : 0;
+    r->status = status;
+    r->n_samples = n_samples;
+    r->n_checkpoints = n_cp;
+    r->n_ribbons_after = nr;
+    r->ribbons_changed = 0;
+    r->reserved = n_culled;
+}
+
+// K2a: one thread per edge
+__global__ void __launch_bounds__(128)
+k2a_prepare(const ppe_config cfg, const double dt, const double horizon_end, const long long n,
+            const ppe_edge* __restrict__ edges, PreparedEdge* __restrict__ prepared) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    prepare_edge(cfg, dt, horizon_end, edges + i, prepared + i);
+}
+
+// K2b: one warp per edge, persistent CTAs pulling work from a global counter: the edges on the heavy list that
+// K2t left behind, or (heavy_list == nullptr) every edge of the batch
 template <int kWarpsPerBlock>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 16 / kWarpsPerBlock)
 k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
              const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
-             unsigned long long* work_counter, BestD* block_best) {
+             unsigned long long* work_counter, const unsigned int* __restrict__ heavy_list,
+             const unsigned int* __restrict__ heavy_count) {
     extern __shared__ double4 smem4[];
     ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
     double4* s_rib = smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4));
@@ -985,6 +1324,8 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
     __shared__ TimeTable s_tt[kWarpsPerBlock];
     double* pe = s_pe[warp];
 
+    const unsigned long long todo = heavy_list ? (unsigned long long)*heavy_count : (unsigned long long)n;
+    if ((unsigned long long)blockIdx.x * kWarpsPerBlock >= todo) return; // nothing for this CTA: skip the staging
     {
         const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
         double* dst = reinterpret_cast<double*>(s_obs);
@@ -993,33 +1334,47 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
     }
     __syncthreads();
 
-    double best_f = INFINITY;
-    long long best_idx = -1;
     for (;;) {
-        unsigned long long ei = 0;
-        if (lane == 0) ei = atomicAdd(work_counter, 1ULL);
-        ei = __shfl_sync(kFull, ei, 0);
-        if (ei >= (unsigned long long)n) break;
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(work_counter, 1ULL);
+        k = __shfl_sync(kFull, k, 0);
+        if (k >= todo) break;
+        const unsigned long long ei = heavy_list ? (unsigned long long)heavy_list[k] : k;
         double f;
         process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], lane, &f);
-        if (f < best_f || (f == best_f && (long long)ei < best_idx)) { best_f = f; best_idx = (long long)ei; }
         __syncwarp();
     }
+}
 
-    // K3 epilogue: block-level best (f, edge index); ties go to the smaller index
-    __shared__ double s_f[kWarpsPerBlock];
-    __shared__ long long s_i[kWarpsPerBlock];
-    if (lane == 0) { s_f[warp] = best_f; s_i[warp] = best_idx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double bf = INFINITY;
-        long long bi = -1;
-        for (int k = 0; k < kWarpsPerBlock; k++) {
-            if (s_i[k] >= 0 && (s_f[k] < bf || (s_f[k] == bf && s_i[k] < bi) || bi < 0)) { bf = s_f[k]; bi = s_i[k]; }
+// K3a: best feasible f = g + h over the result records of one range (the prune record of pushVertexQueue,
+// SamplingBasedPlanner.cpp:11-13); ties go to the smaller edge index.  One BestD per CTA.
+__global__ void __launch_bounds__(256) k3_best_scan(const ppe_edge_result* __restrict__ results, const long long n, BestD* block_best) {
+    __shared__ double s_f[256];
+    __shared__ long long s_i[256];
+    double bf = INFINITY;
+    long long bi = -1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const ppe_edge_result* r = results + i;
+        if (r->infeasible == 0 && r->status == PPE_EDGE_OK && r->h >= 0) {
+            const double f = r->g + r->h;
+            if (bi < 0 || f < bf) { bf = f; bi = i; } // i increases per thread: the first minimum is the smaller index
         }
-        block_best[blockIdx.x].f = bf;
-        block_best[blockIdx.x].idx = bi;
     }
+    s_f[threadIdx.x] = bf;
+    s_i[threadIdx.x] = bi;
+    __syncthreads();
+    for (int s2 = blockDim.x / 2; s2 > 0; s2 >>= 1) {
+        if (threadIdx.x < s2) {
+            const double of = s_f[threadIdx.x + s2];
+            const long long oi = s_i[threadIdx.x + s2];
+            if (oi >= 0 && (s_i[threadIdx.x] < 0 || of < s_f[threadIdx.x] || (of == s_f[threadIdx.x] && oi < s_i[threadIdx.x]))) {
+                s_f[threadIdx.x] = of;
+                s_i[threadIdx.x] = oi;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { block_best[blockIdx.x].f = s_f[0]; block_best[blockIdx.x].idx = s_i[0]; }
 }
 
 // `index_base` turns the slice-local edge indices of one launch into batch indices; with `accumulate` the
@@ -1149,8 +1504,8 @@ size_t prepared_edge_bytes() { return sizeof(PreparedEdge); }
 
 template <int kW>
 static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edges, const PreparedEdge* prepared,
-                             ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best, int max_blocks,
-                             int sm_count, cudaStream_t stream, int* blocks_out) {
+                             ppe_edge_result* results, unsigned long long* work_counter, const unsigned int* heavy_list,
+                             const unsigned int* heavy_count, int max_blocks, int sm_count, cudaStream_t stream) {
     const size_t smem = k2_smem_bytes(kW, world.ribbon_cap, world.n_obs);
     static size_t configured = 0;
     cudaError_t e;
@@ -1170,31 +1525,55 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     k2_true_cost<kW><<<(unsigned)blocks, kW * 32, smem, stream>>>(world, (long long)n, edges, prepared, results, work_counter,
-                                                                 block_best);
-    *blocks_out = (int)blocks;
+                                                                 heavy_list, heavy_count);
     return cudaGetLastError();
 }
 
-// K2a + K2b over one range of edges on `stream`; leaves one BestD per CTA in block_best (*blocks_out of them).
+// K2a + (K2t) + K2b + K3a over one range of edges on `stream`; leaves one BestD per K3a CTA in block_best
+// (*blocks_out of them).  `counters`: [0] 64-bit work counter of K2b, [1] 32-bit heavy-list length.
+// heavy_list == nullptr selects the warp walker for every edge.
 cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
-                                     ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best,
-                                     int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool, int* blocks_out) {
+                                     ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
+                                     BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool,
+                                     int* blocks_out, int* launches_out) {
     PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
-    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     if (reset_pool) { // the ribbons-after pool runs over all slices of a batch
         e = cudaMemsetAsync(world.out_count, 0, sizeof(unsigned long long), stream);
         if (e != cudaSuccess) return e;
     }
-    k2a_prepare<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(world.cfg, (long long)n, edges, prepared);
+    int launches = 0;
+    k2a_prepare<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(world.cfg, world.dt, world.horizon_end, (long long)n, edges, prepared);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    launches++;
+    unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
+    if (heavy_list) {
+        const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD);
+        k2t_thread_walk<<<(unsigned)((n + 127) / 128), 128, smem_t, stream>>>(world, (long long)n, edges, prepared, results, heavy_list,
+                                                                             heavy_count);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        launches++;
+    }
 #ifndef PPE_K2_FORCE_NARROW
 #define PPE_K2_FORCE_NARROW 1
 #endif
     if (!PPE_K2_FORCE_NARROW && k2_smem_bytes(kWarpsWide, world.ribbon_cap, world.n_obs) <= 190 * 1024)
-        return launch_k2<kWarpsWide>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, blocks_out);
-    return launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, work_counter, block_best, max_blocks, sm_count, stream, blocks_out);
+        e = launch_k2<kWarpsWide>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, max_blocks, sm_count, stream);
+    else
+        e = launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, max_blocks, sm_count, stream);
+    if (e != cudaSuccess) return e;
+    launches++;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    if (blocks > max_blocks) blocks = max_blocks;
+    k3_best_scan<<<(unsigned)blocks, 256, 0, stream>>>(results, (long long)n, block_best);
+    launches++;
+    *blocks_out = (int)blocks;
+    if (launches_out) *launches_out = launches;
+    return cudaGetLastError();
 }
 
 // K3: reduce the per-CTA records of one range into *best; `accumulate` keeps what earlier ranges of the batch left there

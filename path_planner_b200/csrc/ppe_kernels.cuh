@@ -67,8 +67,9 @@ struct BestD {
 cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type,
                                 double* param, double* length, int32_t* err, cudaStream_t stream);
 cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
-                                     ppe_edge_result* results, unsigned long long* work_counter, BestD* block_best,
-                                     int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool, int* blocks_out);
+                                     ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
+                                     BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool,
+                                     int* blocks_out, int* launches_out);
 cudaError_t launch_best_final(const BestD* block_best, int blocks, BestD* best, int64_t index_base, bool accumulate,
                               cudaStream_t stream);
 size_t prepared_edge_bytes();

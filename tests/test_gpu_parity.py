@@ -12,9 +12,23 @@ from tests import common
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine():
-    return EdgeEngine(0)
+@pytest.fixture(scope="module", params=["thread+warp", "warp-only"])
+def engine(request):
+    """Both evaluation paths must produce the oracle's bits: the default pipeline (K2t thread walker for simple edges,
+    K2b warp walker for the heavy list) and the warp walker alone (PPE_THREAD_WALKER=0, read at ppe_create)."""
+    import os
+    old = os.environ.get("PPE_THREAD_WALKER")
+    if request.param == "warp-only":
+        os.environ["PPE_THREAD_WALKER"] = "0"
+    else:
+        os.environ.pop("PPE_THREAD_WALKER", None)
+    try:
+        return EdgeEngine(0)
+    finally:
+        if old is None:
+            os.environ.pop("PPE_THREAD_WALKER", None)
+        else:
+            os.environ["PPE_THREAD_WALKER"] = old
 
 
 @pytest.fixture(scope="module")

@@ -1124,6 +1124,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     double ex = 0, ey = 0, eh = 0;
     const int status = PPE_EDGE_OK;
     bool blocked_exit = false;
+    bool long_run = false; // bailed out while covering a ribbon
 
     if (!heavy) {
         SeqTime tm{prep, 0};
@@ -1154,7 +1155,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
 
         // one ribbon check-point (Edge.cpp:155-171) at sample `idx` with pose (x, y, ang); false: the edge is not simple
         auto checkpoint = [&](int idx, double x, double y, double ang) -> bool {
-            if (++n_cp > kThreadCheckpointBudget) return false;
+            if (++n_cp > kThreadCheckpointBudget) { long_run = true; return false; }
             bool would_change;
             const double toCover = seq_checkpoint(rib, nr, x, y, W, &would_change);
             bool do_cover = cov;
@@ -1170,7 +1171,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
                 }
                 do_cover = (ph == heading_of(ang));
             }
-            if (do_cover && would_change) return false;
+            if (do_cover && would_change) { long_run = true; return false; }
             next_cp = idx + 1 + skip_count(toCover, inc, kSkipCap);
             return true;
         };
@@ -1259,8 +1260,16 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     }
 
     if (heavy) {
-        const unsigned int k = atomicAdd(heavy_count, 1u);
-        heavy_list[k] = (unsigned int)ei;
+        // The heavy list is filled from both ends: edges that were caught covering a ribbon (they tend to run along
+        // it for hundreds of check-points, milliseconds of strictly sequential work) from the front, the rest from
+        // the back.  K2b takes the front first, so the longest items start first and the batch does not end on one.
+        if (long_run) {
+            const unsigned int k = atomicAdd(heavy_count, 1u);
+            heavy_list[k] = (unsigned int)ei;
+        } else {
+            const unsigned int k = atomicAdd(heavy_count + 1, 1u);
+            heavy_list[n - 1 - k] = (unsigned int)ei;
+        }
         return;
     }
 
@@ -1293,7 +1302,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     r->n_checkpoints = n_cp;
     r->n_ribbons_after = nr;
     r->ribbons_changed = 0;
-    r->reserved = n_culled;
+    r->reserved = n_culled | (1 << 20); // instrumentation: culled chunks; bit 20 = walked by a thread (K2t)
 }
 
 // K2a: one thread per edge
@@ -1324,7 +1333,8 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
     __shared__ TimeTable s_tt[kWarpsPerBlock];
     double* pe = s_pe[warp];
 
-    const unsigned long long todo = heavy_list ? (unsigned long long)*heavy_count : (unsigned long long)n;
+    const unsigned long long n_front = heavy_list ? (unsigned long long)heavy_count[0] : 0ull;
+    const unsigned long long todo = heavy_list ? n_front + (unsigned long long)heavy_count[1] : (unsigned long long)n;
     if ((unsigned long long)blockIdx.x * kWarpsPerBlock >= todo) return; // nothing for this CTA: skip the staging
     {
         const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
@@ -1339,7 +1349,7 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
         if (lane == 0) k = atomicAdd(work_counter, 1ULL);
         k = __shfl_sync(kFull, k, 0);
         if (k >= todo) break;
-        const unsigned long long ei = heavy_list ? (unsigned long long)heavy_list[k] : k;
+        const unsigned long long ei = !heavy_list ? k : (unsigned long long)(k < n_front ? heavy_list[k] : heavy_list[n - 1 - (k - n_front)]);
         double f;
         process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], lane, &f);
         __syncwarp();
@@ -1530,7 +1540,7 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
 }
 
 // K2a + (K2t) + K2b + K3a over one range of edges on `stream`; leaves one BestD per K3a CTA in block_best
-// (*blocks_out of them).  `counters`: [0] 64-bit work counter of K2b, [1] 32-bit heavy-list length.
+// (*blocks_out of them).  `counters`: [0] 64-bit work counter of K2b, [1] two 32-bit heavy-list lengths (front, back).
 // heavy_list == nullptr selects the warp walker for every edge.
 cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
                                      ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,

@@ -340,7 +340,8 @@ def main():
 
     # per-batch work counters from the result records (int32 columns 47 / 48 = n_samples / n_checkpoints)
     r32 = d_results.view(torch.int32).reshape(n, abi.RESULT_DTYPE.itemsize // 4)
-    culled_chunks = int(r32[:, 51].to(torch.int64).sum().item())  # `reserved`: chunks proved clean by the probe pass
+    culled_chunks = int((r32[:, 51] & 0xFFFFF).to(torch.int64).sum().item())  # `reserved` low bits: chunks proved clean by the probe pass
+    thread_walked = int(((r32[:, 51] >> 20) & 1).to(torch.int64).sum().item())  # bit 20: walked by a K2t thread
     sum_samples = int(r32[:, 47].to(torch.int64).sum().item())
     sum_cp = int(r32[:, 48].to(torch.int64).sum().item())
     infeasible = int(r32[:, 45].to(torch.int64).sum().item())
@@ -397,6 +398,7 @@ def main():
                        "mean_samples_per_edge": sum_samples / n, "mean_checkpoints_per_edge": sum_cp / n,
                        "infeasible_edges": infeasible, "edges_with_status": bad_status,
                        "culled_sample_fraction": 32.0 * culled_chunks / max(1, sum_samples),
+                       "thread_walked_edge_fraction": thread_walked / n,
                        "parallelism": "edges sharded over %d GPU(s), one process per GPU" % world_size},
             "e2e": {"value": world_size * n * e2e_steps / e2e_s_max, "unit": "edges/s",
                     "h2d_bytes_per_step": n * abi.EDGE_DTYPE.itemsize, "d2h_bytes_per_step": n * abi.RESULT_DTYPE.itemsize + 8,

@@ -582,7 +582,12 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
     // Slices of the batch flow through the streams: H2D of slice k + 1 (copy engine), the kernels of slices k and
     // k - 1 (two lanes) and D2H of finished slices (second copy engine) run concurrently; K3 accumulates the best
     // record slice by slice on the context stream.  Small batches are one slice.
-    const int64_t slice = n <= 196608 ? n : 131072;
+    int64_t slice_edges = 262144;
+    {
+        const char* env = getenv("PPE_SLICE_EDGES");
+        if (env && atoll(env) >= 1024) slice_edges = atoll(env);
+    }
+    const int64_t slice = n <= slice_edges + slice_edges / 2 ? n : slice_edges;
     const int64_t n_slices = (n + slice - 1) / slice;
     while ((int64_t)ctx->ev_in.size() < n_slices) {
         cudaEvent_t a, b, c;

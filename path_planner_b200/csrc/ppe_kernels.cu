@@ -436,7 +436,29 @@ __device__ void prepare_edge(const ppe_config& cfg, double dt, double horizon_en
         out->n_runs = fits ? n : 0;
         out->i_after = i;
         out->t_after = t;
-        out->pad_[0] = out->pad_[1] = 0;
+        // number of samples with t_i < end_time (the loop bound of Edge.cpp:125 before any truncation)
+        int n_valid = -1;
+        if (fits) {
+            n_valid = 0;
+            for (int r = 0; r < n; r++) {
+                const double b = out->run_base[r], D = out->run_D[r];
+                const int i0 = out->run_i0[r];
+                const int cnt = (r + 1 < n ? out->run_i0[r + 1] : i) - i0;
+                if (!(b < end_time)) break;
+                if (D > 0) {
+                    // smallest k with b + k D >= end_time (k D is exact inside the run)
+                    int k = (int)fmin(floor((end_time - b) / D), (double)cnt);
+                    while (k < cnt && b + (double)k * D < end_time) k++;
+                    while (k > 0 && !(b + (double)(k - 1) * D < end_time)) k--;
+                    n_valid = i0 + k;
+                    if (k < cnt) break;
+                } else {
+                    n_valid = i0 + 1; // single-step run whose only sample is below the end time
+                }
+            }
+        }
+        out->pad_[0] = n_valid;
+        out->pad_[1] = 0;
     }
 }
 
@@ -1123,9 +1145,14 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     double P_x = edge->src[0], P_y = edge->src[1], P_h = edge->src[2], lastHeading = edge->src[2];
     double ex = 0, ey = 0, eh = 0;
     const int status = PPE_EDGE_OK;
-    bool blocked_exit = false;
     bool long_run = false; // bailed out while covering a ribbon
+    const int n_valid = prep->pad_[0]; // samples with t_i < endTime
+    heavy = heavy || n_valid < 0 || n_valid > 64 * kChunk;
 
+    // The walk is organised in phases that keep the 32 edges of a warp on the same instructions: every thread probes
+    // ALL its chunks first (uniform, cheap); then the few chunks that were not proved clean are evaluated sample by
+    // sample -- thread k's j-th such chunk runs in lockstep with every other thread's j-th, instead of the whole warp
+    // waiting whenever any one of its threads meets a dirty chunk; then the check-points; then the tail.
     if (!heavy) {
         SeqTime tm{prep, 0};
         const double rad_max = 0.5 * kChunk * inc * 1.001 + 1e-6;
@@ -1144,108 +1171,109 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             }
         }
 
-        int next_cp = 0;
-        int i = 0;                 // next sample index
-        double prev_ang = 0;       // path angle of sample i - 1 when have_prev
-        bool have_prev = false;
-        double lx = 0, ly = 0, la = 0; // pose of the last executed sample when have_last
-        bool have_last = false;
-        unsigned long long omask = 0;
+        // ---- phase A: probe every chunk (the last one over its valid samples only) -------------------------------------
+        const int n_chunks = (n_valid + kChunk - 1) / kChunk;
+        unsigned long long dirty = 0;      // bit c: chunk c must be evaluated
+        unsigned long long dmask[kThreadDirtyBudget]; // its candidate obstacles, in order of appearance
         int n_dirty = 0;
-
-        // one ribbon check-point (Edge.cpp:155-171) at sample `idx` with pose (x, y, ang); false: the edge is not simple
-        auto checkpoint = [&](int idx, double x, double y, double ang) -> bool {
-            if (++n_cp > kThreadCheckpointBudget) { long_run = true; return false; }
-            bool would_change;
-            const double toCover = seq_checkpoint(rib, nr, x, y, W, &would_change);
-            bool do_cover = cov;
-            if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159
-                double ph;
-                if (idx == 0) ph = edge->src[2];
-                else if (have_prev) ph = heading_of(prev_ang);
-                else {
-                    double px_, py_, pa_;
-                    bool it_;
-                    pose_eval(pe, tm.at(idx - 1), &px_, &py_, &pa_, &it_);
-                    ph = heading_of(pa_);
-                }
-                do_cover = (ph == heading_of(ang));
+        bool more_dirty = false;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; c++) {
+            const int c0 = c * kChunk;
+            const int last = (c0 + kChunk - 1 < n_valid - 1) ? c0 + kChunk - 1 : n_valid - 1;
+            const double t_first = tm.at(c0), t_mid = tm.at(c0 + (last - c0 + 1) / 2), t_last = tm.at(last);
+            unsigned long long om;
+            if (!probe_one(w, pe, t_first, t_mid, t_last, s_obs, endTime, rad_max, edge_mask, &om)) {
+                // more dirty chunks than the budget only matter if the loop gets that far (an edge that runs into a
+                // blocked area is dirty from there on, but stops at its first blocked sample)
+                if (n_dirty == kThreadDirtyBudget) { more_dirty = true; break; }
+                dirty |= 1ull << c;
+                dmask[n_dirty++] = om;
             }
-            if (do_cover && would_change) { long_run = true; return false; }
-            next_cp = idx + 1 + skip_count(toCover, inc, kSkipCap);
-            return true;
-        };
-
-        for (;;) {
-            if (i > kMaxSamples) { heavy = true; break; }
-            if ((i & (kChunk - 1)) == 0) { // chunk boundary: probe
-                const double t_first = tm.at(i), t_mid = tm.at(i + kChunk / 2), t_last = tm.at(i + kChunk - 1);
-                if (probe_one(w, pe, t_first, t_mid, t_last, s_obs, endTime, rad_max, edge_mask, &omask)) {
-                    // a clean chunk: all 32 samples run, nothing discrete happens; only its check-points are evaluated
-                    n_culled++;
-                    have_prev = false;
-                    while (next_cp < i + kChunk) {
-                        double x, y, ang;
-                        bool it_;
-                        const int idx = next_cp;
-                        pose_eval(pe, tm.at(idx), &x, &y, &ang, &it_);
-                        if (!checkpoint(idx, x, y, ang)) { heavy = true; break; }
-                        prev_ang = ang;
-                        have_prev = (next_cp == idx + 1); // only consecutive check-points reuse it
-                    }
-                    if (heavy) break;
-                    have_prev = false;
-                    have_last = false;
-                    i += kChunk;
-                    n_samples += kChunk;
-                    continue;
-                }
-                if (++n_dirty > kThreadDirtyBudget) { heavy = true; break; } // per-sample work belongs to the warp walker
-            }
-            // ---- one iteration of the loop (Edge.cpp:125-175) for sample i of an evaluated chunk -------------------------
-            const double t_i = tm.at(i);
-            if (!(t_i < endTime)) break;
-            double x, y, ang;
-            bool in_time;
-            const bool sample_ok = pose_eval(pe, t_i, &x, &y, &ang, &in_time);
-            if (!in_time) { infeasible = true; n_samples++; break; }                          // sample() throws, Edge.cpp:126-133
-            if (!sample_ok) { heavy = true; break; }                                          // stale-pose corner: warp walker
-            if (map_blocked(w, x, y)) {                                                       // Edge.cpp:144-147
-                infeasible = true;
-                n_samples++;
-                // `intermediate` holds the blocked sample; lastHeading is still the heading of the sample before
-                if (i > 0) {
-                    if (!have_prev) {
-                        double px_, py_;
-                        bool it_;
-                        pose_eval(pe, tm.at(i - 1), &px_, &py_, &prev_ang, &it_);
-                    }
-                    lastHeading = heading_of(prev_ang);
-                }
-                P_x = x; P_y = y; P_h = heading_of(ang);
-                blocked_exit = true;
-                break;
-            }
-            if (w.obs_kind != kObsNone && w.n_obs > 0 && omask != 0)
-                penalty += collision_exists(w.obs_kind, w.n_obs, s_obs, omask, true, x, y, t_i) * cfg.collision_penalty_factor;
-            if (i == next_cp && !checkpoint(i, x, y, ang)) { heavy = true; break; }
-            prev_ang = ang; have_prev = true;
-            lx = x; ly = y; la = ang; have_last = true;
-            n_samples++;
-            i++;
         }
-        if (!heavy && !blocked_exit && i > 0) {
-            // the loop ended at sample i (its time is at or beyond the end time, or its sample throws): `intermediate` is
-            // the last executed sample
-            if (!have_last) {
-                bool it_;
-                pose_eval(pe, tm.at(i - 1), &lx, &ly, &la, &it_);
-            }
-            P_x = lx; P_y = ly; P_h = heading_of(la);
-            lastHeading = P_h;
-        }
+
+        // ---- phase B: the dirty chunks, sample by sample, in order (Edge.cpp:126-151) until the loop would stop --------------
+        int n_exec = n_valid;      // samples that run the full loop body
+        bool blocked_exit = false;
         if (!heavy) {
-            // ---- truncated end state (Edge.cpp:177-179) and the final cover (:182-191) ----------------------------------
+            tm.r = 0;
+            int j = 0;
+            unsigned long long todo = dirty;
+#pragma unroll 1
+            while (todo && n_exec == n_valid && !heavy) {
+                const int c = __ffsll((long long)todo) - 1;
+                todo &= todo - 1;
+                const unsigned long long omask = dmask[j++];
+                const int c0 = c * kChunk;
+                const int last = (c0 + kChunk - 1 < n_valid - 1) ? c0 + kChunk - 1 : n_valid - 1;
+#pragma unroll 1
+                for (int i = c0; i <= last; i++) {
+                    const double t_i = tm.at(i);
+                    double x, y, ang;
+                    bool in_time;
+                    const bool sample_ok = pose_eval(pe, t_i, &x, &y, &ang, &in_time);
+                    if (!in_time) { infeasible = true; n_exec = i; break; }                        // sample() throws, Edge.cpp:126-133
+                    if (!sample_ok) { heavy = true; break; }                                      // stale-pose corner: warp walker
+                    if (map_blocked(w, x, y)) {                                                   // Edge.cpp:144-147
+                        infeasible = true;
+                        n_exec = i;
+                        blocked_exit = true;
+                        P_x = x; P_y = y; P_h = heading_of(ang); // `intermediate` holds the blocked sample
+                        break;
+                    }
+                    if (w.obs_kind != kObsNone && w.n_obs > 0 && omask != 0)
+                        penalty += collision_exists(w.obs_kind, w.n_obs, s_obs, omask, true, x, y, t_i) * cfg.collision_penalty_factor;
+                }
+            }
+            // per-sample work beyond the budget belongs to the warp walker (lanes = samples)
+            if (more_dirty && n_exec == n_valid) heavy = true;
+            n_samples = n_exec + (infeasible && n_exec < n_valid ? 1 : 0); // the breaking iteration was entered
+            const int chunks_run = (n_exec + kChunk - 1) / kChunk;           // instrumentation: clean chunks that ran
+            n_culled = __popcll(~dirty & (chunks_run >= 64 ? ~0ull : ((1ull << chunks_run) - 1ull)));
+        }
+
+        // ---- phase C: the ribbon check-points of the executed samples (Edge.cpp:153-172) -----------------------------------
+        if (!heavy) {
+            int next_cp = 0;
+            double prev_ang = 0;
+            int prev_idx = -2;
+#pragma unroll 1
+            while (next_cp < n_exec) {
+                if (++n_cp > kThreadCheckpointBudget) { long_run = true; heavy = true; break; }
+                const int idx = next_cp;
+                double x, y, ang;
+                bool it_;
+                pose_eval(pe, tm.at(idx), &x, &y, &ang, &it_);
+                bool would_change;
+                const double toCover = seq_checkpoint(rib, nr, x, y, W, &would_change);
+                bool do_cover = cov;
+                if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159
+                    double ph;
+                    if (idx == 0) ph = edge->src[2];
+                    else if (prev_idx == idx - 1) ph = heading_of(prev_ang);
+                    else {
+                        double px_, py_, pa_;
+                        pose_eval(pe, tm.at(idx - 1), &px_, &py_, &pa_, &it_);
+                        ph = heading_of(pa_);
+                    }
+                    do_cover = (ph == heading_of(ang));
+                }
+                if (do_cover && would_change) { long_run = true; heavy = true; break; }
+                prev_ang = ang;
+                prev_idx = idx;
+                next_cp = idx + 1 + skip_count(toCover, inc, kSkipCap);
+            }
+        }
+
+        // ---- phase D: `intermediate` / lastHeading at the loop exit, truncated end state (Edge.cpp:177-179), final cover -----
+        if (!heavy) {
+            if (n_exec > 0) { // the last sample that ran the full body
+                double lx, ly, la;
+                bool it_;
+                pose_eval(pe, tm.at(n_exec - 1), &lx, &ly, &la, &it_);
+                lastHeading = heading_of(la);
+                if (!blocked_exit) { P_x = lx; P_y = ly; P_h = lastHeading; }
+            }
             double ea;
             bool in_time;
             const bool sample_ok = pose_eval(pe, endTime, &ex, &ey, &ea, &in_time);

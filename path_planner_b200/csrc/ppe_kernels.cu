@@ -15,6 +15,7 @@
 // -fmad=false: the x86-64 reference build has no FMA contraction and discrete outcomes (word
 // choice, cell index, ribbon containment, sample count) must not flip.
 #include <float.h>
+#include <stdlib.h>
 
 #include "ppe_kernels.cuh"
 #include "ppe_math.cuh"
@@ -1043,7 +1044,8 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
 // erases a ribbon, coverage already complete, a non-OK status, unusual time scales) puts the edge on the heavy list and
 // the warp walker K2b evaluates it from scratch; both paths produce the same bits.
 constexpr int kThreadCheckpointBudget = 24;
-constexpr int kThreadDirtyBudget = 6; // chunks a thread evaluates sample by sample before handing the edge over
+constexpr int kThreadDirtyBudget = 2; // chunks a thread evaluates sample by sample before handing the edge over
+constexpr int kThreadDirtyCap = 8;    // upper limit of the PPE_K2T_DIRTY tuning knob
 
 struct SeqTime { // cursor over the prepared run table
     const PreparedEdge* p;
@@ -1098,7 +1100,7 @@ __device__ __forceinline__ double seq_max_distance(const double4* __restrict__ r
 __global__ void __launch_bounds__(128)
 k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
                 const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
-                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count) {
+                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, const int dirty_budget) {
     extern __shared__ double4 smem4[];
     ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
     {
@@ -1174,7 +1176,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
         // ---- phase A: probe every chunk (the last one over its valid samples only) -------------------------------------
         const int n_chunks = (n_valid + kChunk - 1) / kChunk;
         unsigned long long dirty = 0;      // bit c: chunk c must be evaluated
-        unsigned long long dmask[kThreadDirtyBudget]; // its candidate obstacles, in order of appearance
+        unsigned long long dmask[kThreadDirtyCap]; // its candidate obstacles, in order of appearance
         int n_dirty = 0;
         bool more_dirty = false;
 #pragma unroll 1
@@ -1186,7 +1188,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             if (!probe_one(w, pe, t_first, t_mid, t_last, s_obs, endTime, rad_max, edge_mask, &om)) {
                 // more dirty chunks than the budget only matter if the loop gets that far (an edge that runs into a
                 // blocked area is dirty from there on, but stops at its first blocked sample)
-                if (n_dirty == kThreadDirtyBudget) { more_dirty = true; break; }
+                if (n_dirty == dirty_budget) { more_dirty = true; break; }
                 dirty |= 1ull << c;
                 dmask[n_dirty++] = om;
             }
@@ -1589,8 +1591,15 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
     unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
     if (heavy_list) {
         const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD);
+        static int dirty_budget = -1;
+        if (dirty_budget < 0) {
+            const char* env = getenv("PPE_K2T_DIRTY");
+            dirty_budget = env ? atoi(env) : kThreadDirtyBudget; // tuning knob; measured best at 2 on C2 / C3 / C5
+            if (dirty_budget < 0) dirty_budget = 0;
+            if (dirty_budget > kThreadDirtyCap) dirty_budget = kThreadDirtyCap;
+        }
         k2t_thread_walk<<<(unsigned)((n + 127) / 128), 128, smem_t, stream>>>(world, (long long)n, edges, prepared, results, heavy_list,
-                                                                             heavy_count);
+                                                                             heavy_count, dirty_budget);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         launches++;

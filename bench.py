@@ -406,7 +406,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {
-                "bound": "fp64", "kernel": "k2_true_cost", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "bound": "fp64", "kernel": "k2a_prepare + k2t_thread_walk + k2_true_cost (the launch group of one step)",
+                "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
                 "peak_source": "measured live: ppe_measure_fp64_peak (DFMA chain, 2 flop/FMA) -- MEASURED_PEAKS.json has no fp64 entry",
                 "flops_per_launch": flops, "traffic": measured_traffic(args.workload, n),

@@ -30,124 +30,10 @@ struct DubinsPathD {
 enum { kEdubOk = 0, kEdubCoconfigs = 1, kEdubParam = 2, kEdubBadRho = 3, kEdubNoPath = 4 };
 
 // Transcendentals go through ppe_crmath.cuh (correctly rounded w.h.p.) so that word choice and the
-// segment parameters agree with the glibc-based reference to the last bit.  The six words are
-// evaluated in enum order LSL, LSR, RSL, RSR, RLR, LRL with a strict `<` so ties go to the earliest
-// word.
-//
-// The correctly rounded functions cost ~1500 instructions each in double-double, and five of the six
-// words lose.  dubins_words_screen therefore evaluates all six with the plain 1-2 ulp library
-// functions first: when the winner leads by more than kScreenMargin and no feasibility test
-// (p^2 >= 0, |tmp0| <= 1) is within the margin of its threshold, the decision cannot depend on the
-// last bits and only the winning word is evaluated correctly rounded -- same bits as evaluating all
-// six.  Ties and near-degenerate inputs (straight-ahead edges: LSL = LSR = RSL = RSR) take the full
-// evaluation.
-struct DubinsIntermediate {
-    double alpha, beta, d, sa, sb, ca, cb, c_ab, d_sq;
-};
-
-// one word, reference operation order; F selects the transcendental flavour
-template <bool kCr>
-PPE_HD bool dubins_word(int word, const DubinsIntermediate& in, double* t_out, double* p_out, double* q_out, double* slack) {
-    const double alpha = in.alpha, beta = in.beta, d = in.d, sa = in.sa, sb = in.sb, ca = in.ca, cb = in.cb,
-                 c_ab = in.c_ab, d_sq = in.d_sq;
-#define PPE_ATAN2(y, x) (kCr ? cr_atan2((y), (x)) : atan2((y), (x)))
-#define PPE_ACOS(x) (kCr ? cr_acos(x) : acos(x))
-    double t, p, q;
-    bool ok;
-    switch (word) {
-        case 0: { // LSL
-            const double tmp0 = d + sa - sb;
-            const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sa - sb));
-            const double tmp1 = PPE_ATAN2((cb - ca), tmp0);
-            t = mod2pi(tmp1 - alpha);
-            p = sqrt(p_sq);
-            q = mod2pi(beta - tmp1);
-            ok = p_sq >= 0;
-            *slack = fabs(p_sq);
-            break;
-        }
-        case 1: { // LSR
-            const double p_sq = -2 + (d_sq) + (2 * c_ab) + (2 * d * (sa + sb));
-            p = sqrt(p_sq);
-            const double tmp0 = PPE_ATAN2((-ca - cb), (d + sa + sb)) - PPE_ATAN2(-2.0, p);
-            t = mod2pi(tmp0 - alpha);
-            q = mod2pi(tmp0 - mod2pi(beta));
-            ok = p_sq >= 0;
-            *slack = fabs(p_sq);
-            break;
-        }
-        case 2: { // RSL
-            const double p_sq = -2 + d_sq + (2 * c_ab) - (2 * d * (sa + sb));
-            p = sqrt(p_sq);
-            const double tmp0 = PPE_ATAN2((ca + cb), (d - sa - sb)) - PPE_ATAN2(2.0, p);
-            t = mod2pi(alpha - tmp0);
-            q = mod2pi(beta - tmp0);
-            ok = p_sq >= 0;
-            *slack = fabs(p_sq);
-            break;
-        }
-        case 3: { // RSR
-            const double tmp0 = d - sa + sb;
-            const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sb - sa));
-            const double tmp1 = PPE_ATAN2((ca - cb), tmp0);
-            t = mod2pi(alpha - tmp1);
-            p = sqrt(p_sq);
-            q = mod2pi(tmp1 - beta);
-            ok = p_sq >= 0;
-            *slack = fabs(p_sq);
-            break;
-        }
-        case 4: { // RLR
-            const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sa - sb)) / 8.;
-            const double phi = PPE_ATAN2(ca - cb, d - sa + sb);
-            p = mod2pi((2 * kPi) - PPE_ACOS(tmp0));
-            t = mod2pi(alpha - phi + mod2pi(p / 2.));
-            q = mod2pi(alpha - beta - t + mod2pi(p));
-            ok = fabs(tmp0) <= 1;
-            *slack = fabs(fabs(tmp0) - 1);
-            break;
-        }
-        default: { // LRL
-            const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sb - sa)) / 8.;
-            const double phi = PPE_ATAN2(ca - cb, d + sa - sb);
-            p = mod2pi(2 * kPi - PPE_ACOS(tmp0));
-            t = mod2pi(-alpha - phi + p / 2.);
-            q = mod2pi(mod2pi(beta) - alpha - t + mod2pi(p));
-            ok = fabs(tmp0) <= 1;
-            *slack = fabs(fabs(tmp0) - 1);
-            break;
-        }
-    }
-#undef PPE_ATAN2
-#undef PPE_ACOS
-    *t_out = t; *p_out = p; *q_out = q;
-    return ok;
-}
-
-constexpr double kScreenMargin = 1e-7; // >> the 1e-14-class error of the screening arithmetic
-
-// -1: undecided (take the full correctly rounded evaluation); else the word that wins by a safe margin
-PPE_HD int dubins_words_screen(const DubinsIntermediate& in) {
-    double best = INFINITY, second = INFINITY;
-    int arg = -1;
-    bool unsure = false;
-    for (int wd = 0; wd < 6; wd++) {
-        double t, p, q, slack;
-        const bool ok = dubins_word<false>(wd, in, &t, &p, &q, &slack);
-        if (!(slack > kScreenMargin)) unsure = true; // feasibility within reach of its threshold (or NaN)
-        if (!ok) continue;
-        const double cost = t + p + q;
-        // a segment length within the margin of 0 or 2 pi can wrap the other way in the exact evaluation
-        if (!(t > kScreenMargin && t < kTwoPi - kScreenMargin && q > kScreenMargin && q < kTwoPi - kScreenMargin)) unsure = true;
-        if (wd >= 4 && !(p > kScreenMargin && p < kTwoPi - kScreenMargin)) unsure = true;
-        if (!(cost == cost)) unsure = true;
-        if (cost < best) { second = best; best = cost; arg = wd; }
-        else if (cost < second) second = cost;
-    }
-    if (unsure || arg < 0 || !(second - best > kScreenMargin)) return -1;
-    return arg;
-}
-
+// segment parameters agree with the glibc-based reference to the last bit.
+// All six words are evaluated unconditionally (no data-dependent branch per word: the feasibility
+// tests become selects), in enum order LSL, LSR, RSL, RSR, RLR, LRL with a strict `<` so ties go
+// to the earliest word.
 PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const double q1[3], double rho) {
     if (rho <= 0.0) return kEdubBadRho;
     const double dx = q1[0] - q0[0];
@@ -156,14 +42,13 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     const double d = D / rho;
     double theta = 0;
     if (d > 0) theta = mod2pi(cr_atan2(dy, dx));
-    DubinsIntermediate in;
-    in.alpha = mod2pi(q0[2] - theta);
-    in.beta = mod2pi(q1[2] - theta);
-    in.d = d;
-    cr_sincos(in.alpha, &in.sa, &in.ca);
-    cr_sincos(in.beta, &in.sb, &in.cb);
-    in.c_ab = cr_cos(in.alpha - in.beta);
-    in.d_sq = d * d;
+    const double alpha = mod2pi(q0[2] - theta);
+    const double beta = mod2pi(q1[2] - theta);
+    double sa, ca, sb, cb;
+    cr_sincos(alpha, &sa, &ca);
+    cr_sincos(beta, &sb, &cb);
+    const double c_ab = cr_cos(alpha - beta);
+    const double d_sq = d * d;
 
     path->qi[0] = q0[0];
     path->qi[1] = q0[1];
@@ -173,19 +58,67 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     double best_cost = INFINITY;
     int best = -1;
     double b0 = 0, b1 = 0, b2 = 0;
-    const int screened = dubins_words_screen(in);
-    if (screened >= 0) {
-        double slack;
-        if (dubins_word<true>(screened, in, &b0, &b1, &b2, &slack)) best = screened;
+
+#define PPE_TAKE(word, ok, t, p, q)                         \
+    {                                                       \
+        const double cost_ = (t) + (p) + (q);               \
+        if ((ok) && cost_ < best_cost) {                    \
+            best_cost = cost_; best = (word);               \
+            b0 = (t); b1 = (p); b2 = (q);                   \
+        }                                                   \
     }
-    if (best < 0) { // undecided (or the screened word turned out infeasible): all six, correctly rounded
-        for (int wd = 0; wd < 6; wd++) {
-            double t, p, q, slack;
-            if (!dubins_word<true>(wd, in, &t, &p, &q, &slack)) continue;
-            const double cost = t + p + q;
-            if (cost < best_cost) { best_cost = cost; best = wd; b0 = t; b1 = p; b2 = q; }
-        }
+
+    { // LSL
+        const double tmp0 = d + sa - sb;
+        const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sa - sb));
+        const double tmp1 = cr_atan2((cb - ca), tmp0);
+        const double t = mod2pi(tmp1 - alpha);
+        const double p = sqrt(p_sq);
+        const double q = mod2pi(beta - tmp1);
+        PPE_TAKE(0, p_sq >= 0, t, p, q)
     }
+    { // LSR
+        const double p_sq = -2 + (d_sq) + (2 * c_ab) + (2 * d * (sa + sb));
+        const double p = sqrt(p_sq);
+        const double tmp0 = cr_atan2((-ca - cb), (d + sa + sb)) - cr_atan2(-2.0, p);
+        const double t = mod2pi(tmp0 - alpha);
+        const double q = mod2pi(tmp0 - mod2pi(beta));
+        PPE_TAKE(1, p_sq >= 0, t, p, q)
+    }
+    { // RSL
+        const double p_sq = -2 + d_sq + (2 * c_ab) - (2 * d * (sa + sb));
+        const double p = sqrt(p_sq);
+        const double tmp0 = cr_atan2((ca + cb), (d - sa - sb)) - cr_atan2(2.0, p);
+        const double t = mod2pi(alpha - tmp0);
+        const double q = mod2pi(beta - tmp0);
+        PPE_TAKE(2, p_sq >= 0, t, p, q)
+    }
+    { // RSR
+        const double tmp0 = d - sa + sb;
+        const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sb - sa));
+        const double tmp1 = cr_atan2((ca - cb), tmp0);
+        const double t = mod2pi(alpha - tmp1);
+        const double p = sqrt(p_sq);
+        const double q = mod2pi(tmp1 - beta);
+        PPE_TAKE(3, p_sq >= 0, t, p, q)
+    }
+    { // RLR
+        const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sa - sb)) / 8.;
+        const double phi = cr_atan2(ca - cb, d - sa + sb);
+        const double p = mod2pi((2 * kPi) - cr_acos(tmp0));
+        const double t = mod2pi(alpha - phi + mod2pi(p / 2.));
+        const double q = mod2pi(alpha - beta - t + mod2pi(p));
+        PPE_TAKE(4, fabs(tmp0) <= 1, t, p, q)
+    }
+    { // LRL
+        const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sb - sa)) / 8.;
+        const double phi = cr_atan2(ca - cb, d + sa - sb);
+        const double p = mod2pi(2 * kPi - cr_acos(tmp0));
+        const double t = mod2pi(-alpha - phi + p / 2.);
+        const double q = mod2pi(mod2pi(beta) - alpha - t + mod2pi(p));
+        PPE_TAKE(5, fabs(tmp0) <= 1, t, p, q)
+    }
+#undef PPE_TAKE
     if (best < 0) return kEdubNoPath;
     path->param[0] = b0;
     path->param[1] = b1;

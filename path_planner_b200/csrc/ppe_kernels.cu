@@ -61,6 +61,12 @@ __device__ __forceinline__ RibbonD load_ribbon(const double4* p) {
     return r;
 }
 
+// squared RibbonManager::distance (RibbonManager.h:289-291).  IEEE sqrt is monotone and correctly rounded, so
+// min / max over end-point distances are taken on the squares and rooted once: sqrt(min(a, b)) == min(sqrt a, sqrt b).
+__device__ __forceinline__ double point_distance_sq(double x1, double y1, double x2, double y2) {
+    return (x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2);
+}
+
 __device__ __forceinline__ double4 pack_ribbon(double sx, double sy, double ex, double ey) {
     return make_double4(sx, sy, ex, ey);
 }
@@ -233,9 +239,9 @@ __device__ __noinline__ int warp_checkpoint(const double4* cur, double4* alt, in
                 inside = inside || (d < W);                  // non-strict: minDistanceFrom
                 contained = d < W / 2.0;                     // strict: cover
             }
-            const double dStart = point_distance(rb.sx, rb.sy, x, y);
-            const double dEnd = point_distance(rb.ex, rb.ey, x, y);
-            mn = fmin(fmin(mn, dEnd), dStart);
+            const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
+            const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
+            mn = fmin(fmin(mn, dEnd), dStart); // squared
         }
         if (do_cover) {
             RibbonD piece = {0, 0, 0, 0};
@@ -262,7 +268,7 @@ __device__ __noinline__ int warp_checkpoint(const double4* cur, double4* alt, in
         }
     }
     __syncwarp();
-    *to_cover = (nr == 0 || __any_sync(kFull, inside)) ? 0.0 : warp_min(mn);
+    *to_cover = (nr == 0 || __any_sync(kFull, inside)) ? 0.0 : sqrt(warp_min(mn));
     if (out_base > cap) *overflow = true;
     *changed = any_change;
     return any_change ? (out_base > cap ? cap : out_base) : nr;
@@ -276,9 +282,9 @@ __device__ __noinline__ double warp_max_distance(const double4* cur, int nr, dou
     for (int r = lane; r < nr; r += 32) {
         const RibbonD rb = load_ribbon(cur + r);
         scratch[r] = sqrt(ribbon_sqlen(rb)) - 2 * W;
-        const double dStart = point_distance(rb.sx, rb.sy, x, y);
-        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
-        mn = fmin(fmin(mn, dEnd), dStart);
+        const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart); // squared
         mx = fmax(fmax(mx, dEnd), dStart);
     }
     __syncwarp();
@@ -286,8 +292,8 @@ __device__ __noinline__ double warp_max_distance(const double4* cur, int nr, dou
 #pragma unroll 1
     for (int r = 0; r < nr; r++) sumLength += scratch[r]; // list order, as the reference sums
     __syncwarp();
-    mn = warp_min(mn);
-    mx = warp_max(mx);
+    mn = sqrt(warp_min(mn));
+    mx = sqrt(warp_max(mx));
     return fmax(sumLength + mn, mx);
 }
 
@@ -1075,12 +1081,12 @@ __device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib
         }
         // cover leaves a ribbon as it is iff it is not (strictly) contained and not already short enough to erase
         change = change || contained || ribbon_covered(rb, true, W);
-        const double dStart = point_distance(rb.sx, rb.sy, x, y);
-        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
-        mn = fmin(fmin(mn, dEnd), dStart);
+        const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart); // squared
     }
     *would_change = change;
-    return inside ? 0.0 : mn;
+    return inside ? 0.0 : sqrt(mn);
 }
 
 __device__ __forceinline__ double seq_max_distance(const double4* __restrict__ rib, int nr, double x, double y, double W) {
@@ -1089,12 +1095,12 @@ __device__ __forceinline__ double seq_max_distance(const double4* __restrict__ r
     for (int r = 0; r < nr; r++) { // list order, as the reference sums (RibbonManager.cpp:234-248)
         const RibbonD rb = load_ribbon(rib + r);
         sumLength += sqrt(ribbon_sqlen(rb)) - 2 * W;
-        const double dStart = point_distance(rb.sx, rb.sy, x, y);
-        const double dEnd = point_distance(rb.ex, rb.ey, x, y);
-        mn = fmin(fmin(mn, dEnd), dStart);
+        const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart); // squared
         mx = fmax(fmax(mx, dEnd), dStart);
     }
-    return fmax(sumLength + mn, mx);
+    return fmax(sumLength + sqrt(mn), sqrt(mx));
 }
 
 __global__ void __launch_bounds__(128)

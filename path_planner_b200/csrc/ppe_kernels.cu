@@ -67,6 +67,18 @@ __device__ __forceinline__ double point_distance_sq(double x1, double y1, double
     return (x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2);
 }
 
+// Ribbon::contains (Ribbon.cpp:39-43) can only hold when the projection of the point lies in the segment's bounding
+// box (+- 1e-5) and the point is closer than the ribbon width to it, i.e. when the point lies in that box grown by
+// the width.  Outside the box grown by a safe margin the projection / distance arithmetic (three divisions and a
+// square root) is skipped: contains is false either way.  (Margin 1e-3 m; coordinates beyond 1e7 m take no shortcut.)
+__device__ __forceinline__ bool ribbon_may_contain(const RibbonD& r, double x, double y, double W) {
+    const double grow = W * (1 + 1e-9) + 1e-3;
+    const bool outside = x < fmin(r.sx, r.ex) - grow || x > fmax(r.sx, r.ex) + grow || y < fmin(r.sy, r.ey) - grow ||
+                         y > fmax(r.sy, r.ey) + grow;
+    const bool tame = fabs(x) < 1e7 && fabs(y) < 1e7 && fabs(r.sx) < 1e7 && fabs(r.sy) < 1e7 && fabs(r.ex) < 1e7 && fabs(r.ey) < 1e7;
+    return !(outside && tame);
+}
+
 __device__ __forceinline__ double4 pack_ribbon(double sx, double sy, double ex, double ey) {
     return make_double4(sx, sy, ex, ey);
 }
@@ -233,11 +245,13 @@ __device__ __noinline__ int warp_checkpoint(const double4* cur, double4* alt, in
         double px = 0, py = 0;
         if (active) {
             rb = load_ribbon(cur + r);
-            ribbon_projection(rb, x, y, &px, &py);
-            if (ribbon_contains_projection(rb, px, py)) {   // Ribbon::contains, Ribbon.cpp:39-43
-                const double d = ribbon_distance(rb, x, y);
-                inside = inside || (d < W);                  // non-strict: minDistanceFrom
-                contained = d < W / 2.0;                     // strict: cover
+            if (ribbon_may_contain(rb, x, y, W)) {
+                ribbon_projection(rb, x, y, &px, &py);
+                if (ribbon_contains_projection(rb, px, py)) {   // Ribbon::contains, Ribbon.cpp:39-43
+                    const double d = ribbon_distance(rb, x, y);
+                    inside = inside || (d < W);                  // non-strict: minDistanceFrom
+                    contained = d < W / 2.0;                     // strict: cover
+                }
             }
             const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
             const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
@@ -1071,13 +1085,15 @@ __device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib
 #pragma unroll 1
     for (int r = 0; r < nr; r++) {
         const RibbonD rb = load_ribbon(rib + r);
-        double px, py;
-        ribbon_projection(rb, x, y, &px, &py);
         bool contained = false;
-        if (ribbon_contains_projection(rb, px, py)) {
-            const double d = ribbon_distance(rb, x, y);
-            inside = inside || (d < W);
-            contained = d < W / 2.0;
+        if (ribbon_may_contain(rb, x, y, W)) {
+            double px, py;
+            ribbon_projection(rb, x, y, &px, &py);
+            if (ribbon_contains_projection(rb, px, py)) {
+                const double d = ribbon_distance(rb, x, y);
+                inside = inside || (d < W);
+                contained = d < W / 2.0;
+            }
         }
         // cover leaves a ribbon as it is iff it is not (strictly) contained and not already short enough to erase
         change = change || contained || ribbon_covered(rb, true, W);

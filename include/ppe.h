@@ -171,7 +171,12 @@ int ppe_dubins_batch(ppe_ctx* ctx, int64_t n, const double* q0, const double* q1
                      int32_t* type, double* param, double* length, int32_t* err);
 
 /* ---- K2: batched true cost = Edge::computeTrueCost ---------------------------------------- */
-/* Host buffers; H2D / D2H copies are part of the call. */
+/* Host buffers; H2D / D2H copies are part of the call.  Batches above ~390 k edges are pipelined in
+ * 262 144-edge slices (PPE_SLICE_EDGES) over two kernel lanes and two copy streams, so copies and
+ * kernels of different slices overlap; pinned host buffers make the copies asynchronous.
+ * Environment knobs read at ppe_create (tuning / testing only): PPE_THREAD_WALKER=0 evaluates every
+ * edge with the warp walker K2b instead of K2t + K2b; PPE_K2T_DIRTY=<n> non-clean chunks a K2t
+ * thread may evaluate before handing the edge to K2b (default 2). */
 int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge_result* results);
 /* Ribbons-after of edge `edge_index` of the last batch (4 doubles per ribbon, list order).
  * Returns the number of ribbons (<= cap written) or a negative status. */

@@ -1,15 +1,18 @@
 // ppe_kernels.cu -- hand-written sm_100a kernels of the batched Dubins edge-evaluation engine.
 //
-//   K1 k1_dubins_batch   one thread = one (q0, q1, rho) triple: shortest Dubins word, branch-free
-//                        over the six words, fp64.       Replaces Edge::computeApproxCost ->
-//                        DubinsWrapper::set -> dubins_shortest_path (Edge.cpp:11-20,
-//                        DubinsWrapper.cpp:9-17).
-//   K2 k2_true_cost      one warp = one edge; lanes = consecutive sample points of the path.
-//                        Replaces Edge::computeTrueCost (Edge.cpp:68-206) including the Dubins
-//                        solve for path-less edges, Map/GridWorldMap::isBlocked, Binary/Gaussian
-//                        collisionExists, the RibbonManager cover state machine, the truncated end
-//                        state, g (Vertex.cpp:102-104) and h = MaxDistance (RibbonManager.cpp:234-248).
-//   K3 best-f epilogue   fused into K2 (per-warp running best, block reduce) + k3_best_final.
+//   K1  k1_dubins_batch   thread per (q0, q1, rho): shortest Dubins word, six words evaluated without a
+//                         data-dependent branch per word, correctly rounded fp64.  Replaces Edge::computeApproxCost ->
+//                         DubinsWrapper::set -> dubins_shortest_path (Edge.cpp:11-20, DubinsWrapper.cpp:9-17).
+//   K2a k2a_prepare       thread per edge: radius / re-solve / speed change (Edge.cpp:73-85), Edge::setEnd, per-path
+//                         sampler constants, first sample time, the edge's sample-time table.
+//   K2t k2t_thread_walk   thread per edge: the loop of Edge::computeTrueCost (Edge.cpp:86-203) for SIMPLE edges -- chunks
+//                         proved clean by the probe are skipped, the ribbon list is read in place -- Map/GridWorldMap::
+//                         isBlocked, Binary/Gaussian collisionExists, ribbon check-points, truncated end state,
+//                         g (Vertex.cpp:102-104), h = MaxDistance (RibbonManager.cpp:234-248).  The rest -> heavy list.
+//   K2b k2_true_cost      warp per edge (lanes = 32 consecutive samples / lanes over ribbons): the same loop with the
+//                         mutable ribbon list (cover, coverage completion, end-time truncation, ribbons-after).
+//   K3  k3_best_scan + k3_best_final   best feasible f = g + h over the result records (pushVertexQueue's prune record).
+//   k_safe_rows / k_safe_cols          dilated free-space bitmap for the chunk probe;  k_fp64_peak  roofline denominator.
 //
 // No tensor cores: this is branchy fp64 transcendental + bit-gather work.  Compiled with
 // -fmad=false: the x86-64 reference build has no FMA contraction and discrete outcomes (word
@@ -722,13 +725,11 @@ __device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, co
 // back the pose of a sample index either from the lanes (shuffle) or by direct evaluation.
 __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* __restrict__ edge,
                              const PreparedEdge* __restrict__ prep, ppe_edge_result* __restrict__ result,
-                             const ObstacleD* s_obs, double4* bufA, double4* bufB, double* pe, TimeTable* tt, int lane,
-                             double* out_f) {
+                             const ObstacleD* s_obs, double4* bufA, double4* bufB, double* pe, TimeTable* tt, int lane) {
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width;
     const double inc = cfg.collision_checking_increment;
     const int cap = w.ribbon_cap;
-    *out_f = INFINITY;
 
     // stage the prepared record (48 doubles) and the parent's ribbons into shared memory
     __syncwarp();
@@ -1050,7 +1051,6 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
         r->ribbons_changed = (ok && modified) ? 1 : 0;
         r->reserved = n_culled; // instrumentation: chunks the probe pass proved clean
     }
-    if (!infeasible && status == PPE_EDGE_OK && h >= 0) *out_f = g + h;
 }
 
 // ---- K2t: the thread walker -------------------------------------------------------------------------------------------
@@ -1402,8 +1402,7 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
         k = __shfl_sync(kFull, k, 0);
         if (k >= todo) break;
         const unsigned long long ei = !heavy_list ? k : (unsigned long long)(k < n_front ? heavy_list[k] : heavy_list[n - 1 - (k - n_front)]);
-        double f;
-        process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], lane, &f);
+        process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], lane);
         __syncwarp();
     }
 }

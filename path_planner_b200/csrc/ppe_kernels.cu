@@ -74,12 +74,17 @@ __device__ __forceinline__ double point_distance_sq(double x1, double y1, double
 // box (+- 1e-5) and the point is closer than the ribbon width to it, i.e. when the point lies in that box grown by
 // the width.  Outside the box grown by a safe margin the projection / distance arithmetic (three divisions and a
 // square root) is skipped: contains is false either way.  (Margin 1e-3 m; coordinates beyond 1e7 m take no shortcut.)
-__device__ __forceinline__ bool ribbon_may_contain(const RibbonD& r, double x, double y, double W) {
+__device__ __forceinline__ bool ribbon_may_contain(const RibbonD& r, double x, double y, double W, bool tame) {
     const double grow = W * (1 + 1e-9) + 1e-3;
     const bool outside = x < fmin(r.sx, r.ex) - grow || x > fmax(r.sx, r.ex) + grow || y < fmin(r.sy, r.ey) - grow ||
                          y > fmax(r.sy, r.ey) + grow;
-    const bool tame = fabs(x) < 1e7 && fabs(y) < 1e7 && fabs(r.sx) < 1e7 && fabs(r.sy) < 1e7 && fabs(r.ex) < 1e7 && fabs(r.ey) < 1e7;
     return !(outside && tame);
+}
+
+// `tame`: every coordinate the shortcut compares is below 1e7 m in magnitude (decided once per edge: the path stays
+// within its length of its start, the ribbon list only ever shrinks inside the parent's extent)
+__device__ __forceinline__ bool coords_tame(const RibbonD& r) {
+    return fabs(r.sx) < 1e7 && fabs(r.sy) < 1e7 && fabs(r.ex) < 1e7 && fabs(r.ey) < 1e7;
 }
 
 __device__ __forceinline__ double4 pack_ribbon(double sx, double sy, double ex, double ey) {
@@ -234,7 +239,7 @@ __device__ __noinline__ double collision_exists(int kind, int n_obs, const Obsta
 // The new list goes to `alt`; the caller swaps the buffers when something changed.  Returns the new count and the
 // pre-cover minDistanceFrom in *to_cover (0 as soon as any ribbon contains the point, else the nearest endpoint).
 __device__ __noinline__ int warp_checkpoint(const double4* cur, double4* alt, int nr, int cap, double x, double y, double W,
-                                            bool do_cover, int lane, double* to_cover, bool* changed, bool* overflow) {
+                                            bool do_cover, bool tame, int lane, double* to_cover, bool* changed, bool* overflow) {
     double mn = DBL_MAX;
     bool inside = false;
     int out_base = 0;
@@ -248,7 +253,7 @@ __device__ __noinline__ int warp_checkpoint(const double4* cur, double4* alt, in
         double px = 0, py = 0;
         if (active) {
             rb = load_ribbon(cur + r);
-            if (ribbon_may_contain(rb, x, y, W)) {
+            if (ribbon_may_contain(rb, x, y, W, tame)) {
                 ribbon_projection(rb, x, y, &px, &py);
                 if (ribbon_contains_projection(rb, px, py)) {   // Ribbon::contains, Ribbon.cpp:39-43
                     const double d = ribbon_distance(rb, x, y);
@@ -260,7 +265,13 @@ __device__ __noinline__ int warp_checkpoint(const double4* cur, double4* alt, in
             const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
             mn = fmin(fmin(mn, dEnd), dStart); // squared
         }
-        if (do_cover) {
+        // nothing to cover in this pass: no ribbon contains the point and none is short enough to be erased
+        const bool touch = do_cover && __any_sync(kFull, active && (contained || ribbon_covered(rb, true, W)));
+        if (do_cover && !touch) {
+            // these (up to) 32 ribbons pass through unchanged; `alt` still gets them, a later pass may change the list
+            if (active && out_base + lane < cap) alt[out_base + lane] = pack_ribbon(rb.sx, rb.sy, rb.ex, rb.ey);
+            out_base += (nr - base < 32) ? (nr - base) : 32;
+        } else if (do_cover) {
             RibbonD piece = {0, 0, 0, 0};
             RibbonD rest = rb;
             if (contained) {
@@ -750,6 +761,13 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
     }
     __syncwarp();
     if (status == PPE_EDGE_OK && pe[kStatus] != 0.0) status = (int)pe[kStatus];
+    bool tame;
+    {
+        bool t_ = fabs(pe[kX0]) + fabs(pe[kLength]) < 1e7 && fabs(pe[kY0]) + fabs(pe[kLength]) < 1e7 && fabs(edge->src[0]) < 1e7 &&
+                  fabs(edge->src[1]) < 1e7;
+        for (int r = lane; r < nr; r += 32) t_ = t_ && coords_tame(load_ribbon(bufA + r));
+        tame = __all_sync(kFull, t_);
+    }
 
     const double src_t = edge->src[4];
     const bool cov = edge->coverage_allowed != 0;
@@ -897,7 +915,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 }
                 double toCover;
                 bool changed = false;
-                const int nn = warp_checkpoint(cur, alt, nr, cap, cx, cy, W, do_cover, lane, &toCover, &changed, &overflow);
+                const int nn = warp_checkpoint(cur, alt, nr, cap, cx, cy, W, do_cover, tame, lane, &toCover, &changed, &overflow);
                 if (changed) {
                     double4* tmp = cur; cur = alt; alt = tmp;
                     nr = nn;
@@ -978,7 +996,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
         if (cov || lastHeading == P_h) {
             bool changed = false;
             double unused;
-            const int nn = warp_checkpoint(cur, alt, nr, cap, P_x, P_y, W, true, lane, &unused, &changed, &overflow);
+            const int nn = warp_checkpoint(cur, alt, nr, cap, P_x, P_y, W, true, tame, lane, &unused, &changed, &overflow);
             if (changed) {
                 double4* tmp = cur; cur = alt; alt = tmp;
                 nr = nn;
@@ -1078,7 +1096,7 @@ struct SeqTime { // cursor over the prepared run table
 };
 
 // minDistanceFrom + "would cover(x, y, strict) change the list?" over the parent's ribbons, in place
-__device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib, int nr, double x, double y, double W,
+__device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib, int nr, double x, double y, double W, bool tame,
                                                  bool* would_change) {
     double mn = DBL_MAX;
     bool inside = false, change = false;
@@ -1086,7 +1104,7 @@ __device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib
     for (int r = 0; r < nr; r++) {
         const RibbonD rb = load_ribbon(rib + r);
         bool contained = false;
-        if (ribbon_may_contain(rb, x, y, W)) {
+        if (ribbon_may_contain(rb, x, y, W, tame)) {
             double px, py;
             ribbon_projection(rb, x, y, &px, &py);
             if (ribbon_contains_projection(rb, px, py)) {
@@ -1151,6 +1169,12 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
         cct = w.set_cct[set];
         rib = w.ribbons + w.set_offset[set];
         heavy = nr <= 0 || nr > w.ribbon_cap; // coverage already complete: every sample is a check-point (warp walker)
+    }
+    bool tame = fabs(pe[kX0]) + fabs(pe[kLength]) < 1e7 && fabs(pe[kY0]) + fabs(pe[kLength]) < 1e7 && fabs(edge->src[0]) < 1e7 &&
+                fabs(edge->src[1]) < 1e7;
+    if (!heavy) {
+#pragma unroll 1
+        for (int r = 0; r < nr; r++) tame = tame && coords_tame(load_ribbon(rib + r));
     }
     const double src_t = edge->src[4];
     const bool cov = edge->coverage_allowed != 0;
@@ -1269,7 +1293,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
                 bool it_;
                 pose_eval(pe, tm.at(idx), &x, &y, &ang, &it_);
                 bool would_change;
-                const double toCover = seq_checkpoint(rib, nr, x, y, W, &would_change);
+                const double toCover = seq_checkpoint(rib, nr, x, y, W, tame, &would_change);
                 bool do_cover = cov;
                 if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159
                     double ph;
@@ -1305,7 +1329,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             if (!in_time || !sample_ok) heavy = true; // the reference throws / stale pose: let the warp walker report it
             if (!heavy && (cov || lastHeading == P_h)) {
                 bool would_change;
-                seq_checkpoint(rib, nr, P_x, P_y, W, &would_change);
+                seq_checkpoint(rib, nr, P_x, P_y, W, tame, &would_change);
                 if (would_change) heavy = true;
             }
         }

@@ -58,6 +58,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     double best_cost = INFINITY;
     int best = -1;
     double b0 = 0, b1 = 0, b2 = 0;
+    double at_lsl = 0, at_rsr = 0; // shared with the CCC words below
 
 #define PPE_TAKE(word, ok, t, p, q)                         \
     {                                                       \
@@ -72,6 +73,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
         const double tmp0 = d + sa - sb;
         const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sa - sb));
         const double tmp1 = cr_atan2((cb - ca), tmp0);
+        at_lsl = tmp1;
         const double t = mod2pi(tmp1 - alpha);
         const double p = sqrt(p_sq);
         const double q = mod2pi(beta - tmp1);
@@ -97,6 +99,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
         const double tmp0 = d - sa + sb;
         const double p_sq = 2 + d_sq - (2 * c_ab) + (2 * d * (sb - sa));
         const double tmp1 = cr_atan2((ca - cb), tmp0);
+        at_rsr = tmp1;
         const double t = mod2pi(alpha - tmp1);
         const double p = sqrt(p_sq);
         const double q = mod2pi(tmp1 - beta);
@@ -104,7 +107,7 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     }
     { // RLR
         const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sa - sb)) / 8.;
-        const double phi = cr_atan2(ca - cb, d - sa + sb);
+        const double phi = at_rsr; // atan2(ca - cb, d - sa + sb): the very call RSR made
         const double p = mod2pi((2 * kPi) - cr_acos(tmp0));
         const double t = mod2pi(alpha - phi + mod2pi(p / 2.));
         const double q = mod2pi(alpha - beta - t + mod2pi(p));
@@ -112,7 +115,10 @@ PPE_HD int dubins_shortest_path(DubinsPathD* path, const double q0[3], const dou
     }
     { // LRL
         const double tmp0 = (6. - d_sq + 2 * c_ab + 2 * d * (sb - sa)) / 8.;
-        const double phi = cr_atan2(ca - cb, d + sa - sb);
+        // atan2(ca - cb, d + sa - sb) = atan2(-(cb - ca), same x) = -atan2(cb - ca, x): atan2 is odd in y and the
+        // correctly rounded value of -v is -(correctly rounded v), so LSL's call is reused
+        // (when cb == ca both differences are +0 and the identity does not apply to the zero's sign)
+        const double phi = (cb - ca != 0.0) ? -at_lsl : cr_atan2(ca - cb, d + sa - sb);
         const double p = mod2pi(2 * kPi - cr_acos(tmp0));
         const double t = mod2pi(-alpha - phi + p / 2.);
         const double q = mod2pi(mod2pi(beta) - alpha - t + mod2pi(p));

@@ -131,6 +131,22 @@ int ref_set_map_bitmap(ref_ctx* ctx, const uint8_t* bits, int rows, int cols, in
     return 0;
 }
 
+// The reference's own parser on a file as it lies on disk (tests of the engine's `.map` ingest).
+int ref_set_map_file(ref_ctx* ctx, const char* path) {
+    try {
+        ctx->config.setMap(std::make_shared<GridWorldMap>(path));
+    } catch (std::exception& ex) {
+        ctx->lastError = ex.what();
+        return -3;
+    }
+    return 0;
+}
+
+// Map::isBlocked of the installed map (virtual dispatch, as Edge.cpp:144 calls it)
+int ref_is_blocked(ref_ctx* ctx, double x, double y) { return ctx->config.map()->isBlocked(x, y) ? 1 : 0; }
+
+double ref_map_resolution(ref_ctx* ctx) { return ctx->config.map()->resolution(); }
+
 int ref_set_obstacles_none(ref_ctx* ctx) {
     ctx->binary.reset(); ctx->gaussian.reset();
     ctx->config.setObstaclesManager(std::make_shared<DynamicObstaclesManager>());

@@ -5,8 +5,8 @@ as hand-written sm_100a CUDA kernels behind the C ABI of include/ppe.h.  Importi
 does not load the CUDA library; constructing an `EdgeEngine` does, and fails loudly when the
 library or the GPU is missing (there is no CPU fallback).
 """
-from . import abi, synth  # noqa: F401  (sharding imports torch: import it explicitly)
+from . import abi, mapio, synth  # noqa: F401  (sharding imports torch: import it explicitly)
 from ._capi import PpeError  # noqa: F401
 from .engine import EdgeEngine, load_library, LIB_PATH  # noqa: F401
 
-__all__ = ["abi", "synth", "EdgeEngine", "PpeError", "load_library", "LIB_PATH"]
+__all__ = ["abi", "mapio", "synth", "EdgeEngine", "PpeError", "load_library", "LIB_PATH"]

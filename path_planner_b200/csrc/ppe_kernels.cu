@@ -1592,12 +1592,10 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
                              ppe_edge_result* results, unsigned long long* work_counter, const unsigned int* heavy_list,
                              const unsigned int* heavy_count, int max_blocks, int sm_count, cudaStream_t stream) {
     const size_t smem = k2_smem_bytes(kW, world.ribbon_cap, world.n_obs);
-    static size_t configured = 0;
     cudaError_t e;
-    if (smem > configured) {
+    if (smem > 48 * 1024) { // per device and per function: set it whenever it is needed rather than remembering
         e = cudaFuncSetAttribute(k2_true_cost<kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     int per_sm = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_true_cost<kW>, kW * 32, smem);

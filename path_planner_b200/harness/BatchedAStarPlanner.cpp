@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstring>
 #include <list>
+#include <memory>
 #include <stdexcept>
 #include <string>
 
@@ -85,20 +86,29 @@ void BatchedAStarPlanner::uploadWorld(const RibbonManager& ribbonManager, const 
     c.heuristic = m_Heuristic;
     check(ppe_set_config(m_Ctx, &c), "ppe_set_config");
 
-    // static map: rasterise Map::isBlocked at cell centres (GridWorldMap cells are res x res squares)
+    // static map: rasterise Map::isBlocked at cell centres (GridWorldMap cells are res x res squares).  The Executive
+    // hands the same immutable Map object to every planning cycle (executive.cpp:182-190), so the bitmap already on the
+    // device is kept as long as that very object is alive and this context received it last.
     const Map::SharedPtr& map = config.map();
-    const double res = map->resolution();
-    const double* ext = map->extremes();
-    if (!(res > 0) || !(ext[1] < 1e300)) {
-        check(ppe_set_map_none(m_Ctx), "ppe_set_map_none");
-    } else {
-        const int cols = (int)std::llround((ext[1] - ext[0]) / res), rows = (int)std::llround((ext[3] - ext[2]) / res);
-        const int stride = (cols + 7) / 8;
-        std::vector<uint8_t> bits((size_t)rows * stride, 0);
-        for (int r = 0; r < rows; r++)
-            for (int cc = 0; cc < cols; cc++)
-                if (map->isBlocked((cc + 0.5) * res, (r + 0.5) * res)) bits[(size_t)r * stride + (cc >> 3)] |= (uint8_t)(1u << (cc & 7));
-        check(ppe_set_map_bitmap(m_Ctx, bits.data(), rows, cols, stride, res), "ppe_set_map_bitmap");
+    static std::weak_ptr<Map> s_uploadedMap;
+    static ppe_ctx* s_uploadedCtx = nullptr;
+    const bool sameMap = s_uploadedCtx == m_Ctx && !s_uploadedMap.expired() && s_uploadedMap.lock() == map;
+    if (!sameMap) {
+        const double res = map->resolution();
+        const double* ext = map->extremes();
+        if (!(res > 0) || !(ext[1] < 1e300)) {
+            check(ppe_set_map_none(m_Ctx), "ppe_set_map_none");
+        } else {
+            const int cols = (int)std::llround((ext[1] - ext[0]) / res), rows = (int)std::llround((ext[3] - ext[2]) / res);
+            const int stride = (cols + 7) / 8;
+            std::vector<uint8_t> bits((size_t)rows * stride, 0);
+            for (int r = 0; r < rows; r++)
+                for (int cc = 0; cc < cols; cc++)
+                    if (map->isBlocked((cc + 0.5) * res, (r + 0.5) * res)) bits[(size_t)r * stride + (cc >> 3)] |= (uint8_t)(1u << (cc & 7));
+            check(ppe_set_map_bitmap(m_Ctx, bits.data(), rows, cols, stride, res), "ppe_set_map_bitmap");
+        }
+        s_uploadedMap = map;
+        s_uploadedCtx = m_Ctx;
     }
 
     // dynamic obstacles in container iteration order (the summation order of collisionExists)

@@ -59,7 +59,8 @@ def algorithmic_bytes(n_edges, sum_samples):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms period; the
+    timed region of a default run is ~0.1 s, shorter than nvidia-smi's start-up), nvidia-smi -lms as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -67,8 +68,37 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.samples = []
+        self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, reasons))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
@@ -77,6 +107,18 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": ["no samples"]}
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            reasons = sorted({n for n, bit in names for _, r in self.samples if r & bit})
+            sm = [v for v, _ in self.samples]
+            busy = [v for v in sm if v >= 0.5 * max(sm)] or sm
+            return {"sm_mhz": statistics.median(busy), "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm), "source": "nvml, 5 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -101,7 +143,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         busy = [v for v in sm if v >= 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def load_cpu_lib():
@@ -145,20 +187,30 @@ def plan_at_budget(budget_s, device):
     if not common.have_harness():
         return {"unavailable": "oracle/_ref/libppe_harness.so not built (needs the reference sources at build time)"}
     lib = common.load_harness()
-    out = {"budget_s": budget_s, "unit": "f = g + h of the returned plan, seconds (lower is better)", "scenarios": []}
+    reps = 3
+    out = {"budget_s": budget_s, "repetitions": reps,
+           "unit": "f = g + h of the returned plan, seconds (lower is better); the planner seeds its sampler from the wall "
+                   "clock (AStarPlanner.cpp:33), so every scenario is planned `repetitions` times by each planner: median f, "
+                   "best f, mean expansions",
+           "scenarios": []}
     for wname, start in PLAN_SCENARIOS:
         world = synth.WORLDS[wname]()
         sid = world.upload_ref(lib)
         st0 = world.start if start is None else np.array(start, dtype=np.float64)
         rec = {"world": wname, "start": [float(v) for v in st0]}
         for which in ("ref", "harness"):
-            t0 = time.perf_counter()
-            plan, st = common.run_plan(lib, which, sid, st0, budget_s, 0.0, 0.0, 100, device=device)
-            dt = time.perf_counter() - t0
+            fs, exp, smp, wall = [], [], [], []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                plan, st = common.run_plan(lib, which, sid, st0, budget_s, 0.0, 0.0, 100, device=device)
+                wall.append(time.perf_counter() - t0)
+                if len(plan):
+                    fs.append(st["f"])
+                exp.append(st["expanded"])
+                smp.append(st["samples"])
             rec["reference_cpu" if which == "ref" else "engine"] = {
-                "f": st["f"] if len(plan) else None, "plan_edges": len(plan), "expanded": int(st["expanded"]),
-                "generated": int(st["generated"]), "samples": int(st["samples"]), "iterations": int(st["iterations"]),
-                "wall_s": round(dt, 3)}
+                "f_median": statistics.median(fs) if fs else None, "f_best": min(fs) if fs else None, "plans_found": len(fs),
+                "expanded_mean": sum(exp) / reps, "samples_mean": sum(smp) / reps, "wall_s_mean": round(sum(wall) / reps, 3)}
         out["scenarios"].append(rec)
     return out
 

@@ -1081,7 +1081,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
 // to "would it change anything?") and the check-point budget is not exceeded.  Anything else (a cover that splits or
 // erases a ribbon, coverage already complete, a non-OK status, unusual time scales) puts the edge on the heavy list and
 // the warp walker K2b evaluates it from scratch; both paths produce the same bits.
-constexpr int kThreadCheckpointBudget = 24;
+constexpr int kThreadCheckpointBudget = 6; // measured best in [4, 8] on C2 / C3 / C5 (PPE_K2T_CPS)
 constexpr int kThreadDirtyBudget = 2; // chunks a thread evaluates sample by sample before handing the edge over
 constexpr int kThreadDirtyCap = 8;    // upper limit of the PPE_K2T_DIRTY tuning knob
 
@@ -1140,7 +1140,8 @@ __device__ __forceinline__ double seq_max_distance(const double4* __restrict__ r
 __global__ void __launch_bounds__(128)
 k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
                 const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
-                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, const int dirty_budget) {
+                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, const int dirty_budget,
+                const int cp_budget) {
     extern __shared__ double4 smem4[];
     ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
     {
@@ -1287,7 +1288,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             int prev_idx = -2;
 #pragma unroll 1
             while (next_cp < n_exec) {
-                if (++n_cp > kThreadCheckpointBudget) { long_run = true; heavy = true; break; }
+                if (++n_cp > cp_budget) { long_run = true; heavy = true; break; }
                 const int idx = next_cp;
                 double x, y, ang;
                 bool it_;
@@ -1634,15 +1635,17 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
     unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
     if (heavy_list) {
         const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD);
-        static int dirty_budget = -1;
+        static int dirty_budget = -1, cp_budget = kThreadCheckpointBudget;
         if (dirty_budget < 0) {
+            const char* env_cp = getenv("PPE_K2T_CPS"); // tuning knob: check-points a K2t thread may walk
+            if (env_cp && atoi(env_cp) > 0) cp_budget = atoi(env_cp);
             const char* env = getenv("PPE_K2T_DIRTY");
             dirty_budget = env ? atoi(env) : kThreadDirtyBudget; // tuning knob; measured best at 2 on C2 / C3 / C5
             if (dirty_budget < 0) dirty_budget = 0;
             if (dirty_budget > kThreadDirtyCap) dirty_budget = kThreadDirtyCap;
         }
         k2t_thread_walk<<<(unsigned)((n + 127) / 128), 128, smem_t, stream>>>(world, (long long)n, edges, prepared, results, heavy_list,
-                                                                             heavy_count, dirty_budget);
+                                                                             heavy_count, dirty_budget, cp_budget);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         launches++;

@@ -5,7 +5,7 @@ the reference's AStarPlanner and of the product's BatchedAStarPlanner on the sam
 state and virtual clock (PlannerConfig::setNowFunction, PlannerConfig.h:110)."""
 import numpy as np
 
-from path_planner_b200 import synth
+from path_planner_b200 import abi, synth
 from tests import common
 
 COUNTERS = ("samples", "generated", "expanded", "iterations", "depth", "now_calls")
@@ -21,6 +21,9 @@ CASES = [
     ("c3-gaussian", "c3", (420.0, 395.0, 0.0, 2.5, 1.0), 0.95, 4e-3, 100),       # BASELINE configs[2]
     ("c3-binary", "c3b", (420.0, 395.0, 0.0, 2.5, 1.0), 0.95, 4e-3, 100),
     ("c4-10k-samples", "c4", None, 0.95, 0.12, 10000),            # BASELINE configs[3]
+    # Executive's default heuristic (executive.cpp:391, TspPointRobotNoSplitKRibbons) on <= 5 ribbons: the engine returns
+    # h = -1 and the adapter calls the reference's Vertex::computeApproxToGo on the returned ribbon set
+    ("c1-tsp-heuristic", "c1-tsp", None, 0.95, 2e-3, 100),
 ]
 CASE_IDS = [c[0] for c in CASES]
 
@@ -28,7 +31,12 @@ CASE_IDS = [c[0] for c in CASES]
 def compare(lib, case, exact, knn_chunk=128, clock0=1000.0):
     """Runs both planners; asserts plan identity.  Returns (harness stats, reference plan)."""
     _, wname, start, budget, tick, initial = case
-    world = synth.WORLDS[wname]()
+    if wname == "c1-tsp":
+        world = synth.world_c1()
+        world.cfg.heuristic = abi.H_TSP_POINT_ROBOT_NO_SPLIT_K
+        world.ribbons = np.array([[0.0, 10.0, 0.0, 30.0], [6.0, 30.0, 6.0, 10.0]])
+    else:
+        world = synth.WORLDS[wname]()
     start = world.start if start is None else np.array(start, dtype=np.float64)
     sid = world.upload_ref(lib)
     want_plan, want = common.run_plan(lib, "ref", sid, start, budget, clock0, tick, initial)

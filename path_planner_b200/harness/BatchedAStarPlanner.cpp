@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <list>
 #include <memory>
@@ -196,35 +197,38 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
     }
     const size_t nEndpointEdges = m_Edges.size();
 
-    // (b) k nearest samples by Dubins distance, :83-133.  Same heap operations on m_Samples as the
-    // reference; the Dubins solves of the next `m_KnnChunk` samples in Euclidean order go to K1
-    // in one launch, found by popping a scratch copy of the heap.
+    // (b) k nearest samples by Dubins distance, :83-133.  Same heap operations on m_Samples as the reference, in the
+    // same order.  The Dubins solves of the samples the loop is about to pop ride in one K1 launch per chunk: the next
+    // `m_KnnChunk` samples in pop order are read off the heap WITHOUT touching it (best-first walk over the heap's
+    // tree with a small auxiliary queue), solved on the device, and then the reference's loop body is replayed with
+    // real pops.  A popped sample that is not where the walk predicted (only possible among samples at exactly equal
+    // distance) is looked up in the chunk, and solved on its own if it is not there.
     auto comp = [&](const State& s1, const State& s2) { return s1.distanceTo(src) > s2.distanceTo(src); };
     auto dubinsComp = [](const Candidate& a, const Candidate& b) { return a.approxCost < b.approxCost; };
     std::make_heap(m_Samples.begin(), m_Samples.end(), comp);
-    m_Scratch = m_Samples;
     std::vector<Candidate> bestSamplesHeaps[nTurningRadii];
     bool doneChecks[nTurningRadii] = {false, false};
     const size_t nSamples = m_Samples.size();
     const size_t kBranch = (size_t)k();
-    size_t pops = 0; // how many samples the reference's loop has consumed
-    size_t scratchPopped = 0;
-    std::vector<State> chunk;
-    while (pops < nSamples && (!doneChecks[0] || !doneChecks[1])) {
-        // next chunk of samples in Euclidean order
-        chunk.clear();
-        const size_t want = std::min<size_t>((size_t)m_KnnChunk, nSamples - scratchPopped);
-        for (size_t c = 0; c < want; c++) {
-            chunk.push_back(m_Scratch.front());
-            std::pop_heap(m_Scratch.begin(), m_Scratch.end() - scratchPopped, comp);
-            scratchPopped++;
-        }
-        // K1: src -> sample at every radius in use
+    size_t pops = 0; // how many samples the reference's loop has consumed = how far the heap has shrunk
+    std::vector<State>& chunk = m_Scratch;
+    typedef std::pair<double, size_t> Node; // (distance to src, index in the heap array)
+    auto nodeGreater = [](const Node& a, const Node& b) { return a.first > b.first || (a.first == b.first && a.second > b.second); };
+    std::vector<Node> walk;
+    std::vector<char> used;
+    struct Solve { double q0[3], param[3], length; int type; bool valid; };
+    static const bool mispredict = getenv("PPE_HARNESS_TEST_MISPREDICT") != nullptr; // tests/test_harness_host_logic.py
+    auto sameState = [](const State& a, const State& b) {
+        return a.x() == b.x() && a.y() == b.y() && a.heading() == b.heading() && a.speed() == b.speed() && a.time() == b.time();
+    };
+    // solves src -> every sample of `chunk` at every radius still in play; slot[2 c + j] indexes the K1 outputs
+    std::vector<long> slot;
+    auto solveChunk = [&]() {
         const size_t m = chunk.size();
         m_Q0.resize(6 * m); m_Q1.resize(6 * m); m_Rho.resize(2 * m);
         m_Param.resize(6 * m); m_Length.resize(2 * m); m_Type.resize(2 * m); m_Err.resize(2 * m);
+        slot.assign(2 * m, -1);
         size_t nq = 0;
-        std::vector<long> slot(2 * m, -1);
         for (size_t c = 0; c < m; c++)
             for (int j = 0; j < nTurningRadii; j++) {
                 if (turningRadii[j] <= 0 || doneChecks[j]) continue;
@@ -239,10 +243,67 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
             m_DubinsSolves += (long)nq;
             m_Batches++;
         }
-        // replay of the reference's loop body over this chunk
+    };
+    while (pops < nSamples && (!doneChecks[0] || !doneChecks[1])) {
+        // the next chunk of samples in pop order, read off the heap [0, heapLen) without modifying it
+        const size_t heapLen = nSamples - pops;
+        const size_t want = std::min<size_t>((size_t)m_KnnChunk, heapLen);
+        chunk.clear();
+        walk.clear();
+        walk.push_back(Node(m_Samples[0].distanceTo(src), 0));
+        while (chunk.size() < want && !walk.empty()) {
+            std::pop_heap(walk.begin(), walk.end(), nodeGreater);
+            const size_t idx = walk.back().second;
+            walk.pop_back();
+            chunk.push_back(m_Samples[idx]);
+            for (size_t child = 2 * idx + 1; child <= 2 * idx + 2 && child < heapLen; child++) {
+                walk.push_back(Node(m_Samples[child].distanceTo(src), child));
+                std::push_heap(walk.begin(), walk.end(), nodeGreater);
+            }
+        }
+        if (mispredict && chunk.size() > 2) { // test hook: scramble the prediction so that the look-up and single-solve paths run
+            std::reverse(chunk.begin(), chunk.end());
+            chunk.resize(chunk.size() - chunk.size() / 3);
+        }
+        solveChunk();
+        const size_t m = chunk.size();
+        used.assign(m, 0);
+        // replay of the reference's loop body: real pops
         for (size_t c = 0; c < m && (!doneChecks[0] || !doneChecks[1]); c++) {
-            State sample = chunk[c];
+            State sample = m_Samples.front();
+            std::pop_heap(m_Samples.begin(), m_Samples.end() - pops, comp);
             pops++;
+            // where are this sample's solves?
+            size_t at = m;
+            if (!used[c] && sameState(chunk[c], sample)) at = c;
+            else for (size_t o = 0; o < m; o++) if (!used[o] && sameState(chunk[o], sample)) { at = o; break; }
+            Solve solves[nTurningRadii];
+            if (at < m) {
+                used[at] = 1;
+                for (int j = 0; j < nTurningRadii; j++) {
+                    const long q = slot[2 * at + j];
+                    solves[j].valid = q >= 0;
+                    if (q < 0) continue;
+                    for (int d = 0; d < 3; d++) { solves[j].q0[d] = m_Q0[3 * q + d]; solves[j].param[d] = m_Param[3 * q + d]; }
+                    solves[j].length = m_Length[q];
+                    solves[j].type = m_Type[q];
+                }
+            } else {
+                // not predicted (samples at exactly equal distance popped in another order): solve this one on its own
+                for (int j = 0; j < nTurningRadii; j++) {
+                    solves[j].valid = false;
+                    if (turningRadii[j] <= 0 || doneChecks[j]) continue;
+                    const double q0[3] = {src.x(), src.y(), src.yaw()}, q1[3] = {sample.x(), sample.y(), sample.yaw()};
+                    const double rho = turningRadii[j];
+                    int32_t type = 0, err = 0;
+                    check(ppe_dubins_batch(m_Ctx, 1, q0, q1, &rho, &type, solves[j].param, &solves[j].length, &err), "ppe_dubins_batch");
+                    m_DubinsSolves++;
+                    m_Batches++;
+                    for (int d = 0; d < 3; d++) solves[j].q0[d] = q0[d];
+                    solves[j].type = type;
+                    solves[j].valid = true;
+                }
+            }
             for (int j = 0; j < nTurningRadii; j++) {
                 if (doneChecks[j]) continue;
                 const double turningRadius = turningRadii[j];
@@ -251,15 +312,16 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
                 if (bestSamples.size() < kBranch || bestSamples.front().length > sample.distanceTo(src)) {
                     if (src.distanceTo(sample) > inc) {
                         sample.speed() = m_Config.maxSpeed();
-                        const long q = slot[2 * c + j];
+                        const Solve& sv = solves[j];
+                        if (!sv.valid) throw std::logic_error("BatchedAStarPlanner: missing Dubins solve for a popped sample");
                         Candidate cand;
                         cand.sample = sample;
                         cand.coverageAllowed = turningRadius == m_Config.coverageTurningRadius();
-                        cand.path[0] = m_Q0[3 * q]; cand.path[1] = m_Q0[3 * q + 1]; cand.path[2] = m_Q0[3 * q + 2];
-                        cand.path[3] = m_Param[3 * q]; cand.path[4] = m_Param[3 * q + 1]; cand.path[5] = m_Param[3 * q + 2];
+                        cand.path[0] = sv.q0[0]; cand.path[1] = sv.q0[1]; cand.path[2] = sv.q0[2];
+                        cand.path[3] = sv.param[0]; cand.path[4] = sv.param[1]; cand.path[5] = sv.param[2];
                         cand.path[6] = turningRadius;
-                        cand.type = m_Type[q];
-                        cand.length = m_Length[q];
+                        cand.type = sv.type;
+                        cand.length = sv.length;
                         // Edge::computeApproxCost(): length / end speed (= max speed) * timePenaltyFactor, Edge.cpp:11-20,64-66
                         cand.approxCost = cand.length / sample.speed() * Edge::timePenaltyFactor();
                         bestSamples.push_back(cand);
@@ -275,8 +337,6 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
             }
         }
     }
-    // leave m_Samples exactly as the reference's pops would
-    for (size_t i = 0; i < pops; i++) std::pop_heap(m_Samples.begin(), m_Samples.end() - i, comp);
 
     // (c) winners x speeds, :134-149 -- wrapper reused, speed set per edge
     struct Winner { const Candidate* cand; double speed; };

@@ -34,3 +34,22 @@ def test_knn_chunk_only_changes_the_launch_count(lib):
     b, plan_b = plan_cases.compare(lib, case, exact=True, knn_chunk=512)
     assert np.array_equal(plan_a, plan_b)
     assert a["dubins_solves"] < b["dubins_solves"] and a["batches"] > b["batches"]
+
+
+def test_mispredicted_chunks_do_not_change_the_plan():
+    """The K1 chunk is a PREDICTION of the samples the replayed loop will pop.  With the prediction scrambled on purpose
+    (reversed, a third dropped) every pop goes through the look-up or the single-solve fallback -- the plan must still be
+    the reference's bit for bit.  Runs in a fresh process: the hook is read once per process."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys\n"
+        "os.environ['PPE_HARNESS_TEST_MISPREDICT'] = '1'\n"
+        "sys.path.insert(0, %r)\n"
+        "from tests import common, plan_cases\n"
+        "lib = common.load_harness(%r)\n"
+        "for i in (0, 2, 5):\n"
+        "    got, plan = plan_cases.compare(lib, plan_cases.CASES[i], exact=True, knn_chunk=16)\n"
+        "print('ok')\n" % (common.ROOT, CPU_SO))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

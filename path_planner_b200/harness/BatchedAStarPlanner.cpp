@@ -7,6 +7,7 @@
 // operations, the candidate tests and the pushVertexQueue order are replayed exactly as the
 // reference performs them, so the open list evolves identically.
 #include "BatchedAStarPlanner.h"
+#include "KeyedHeap.h"
 
 #include <algorithm>
 #include <cmath>
@@ -142,6 +143,7 @@ Planner::Stats BatchedAStarPlanner::plan(const RibbonManager& ribbonManager, con
                                          const DubinsPlan& previousPlan, double timeRemaining) {
     uploadWorld(ribbonManager, start, config);
     m_TrueCostEdges = m_DubinsSolves = m_Batches = 0;
+    m_Perm.clear(); // AStarPlanner::plan starts from an empty sample set (AStarPlanner.cpp:24)
     return AStarPlanner::plan(ribbonManager, start, std::move(config), previousPlan, timeRemaining);
 }
 
@@ -203,9 +205,15 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
     // tree with a small auxiliary queue), solved on the device, and then the reference's loop body is replayed with
     // real pops.  A popped sample that is not where the walk predicted (only possible among samples at exactly equal
     // distance) is looked up in the chunk, and solved on its own if it is not there.
-    auto comp = [&](const State& s1, const State& s2) { return s1.distanceTo(src) > s2.distanceTo(src); };
     auto dubinsComp = [](const Candidate& a, const Candidate& b) { return a.approxCost < b.approxCost; };
-    std::make_heap(m_Samples.begin(), m_Samples.end(), comp);
+    // std::make_heap(m_Samples.begin(), m_Samples.end(), comp) with comp = "farther from src is lower priority", on
+    // the (distance, index) representation: every distance is computed once instead of twice per comparison
+    const size_t nAll = m_Samples.size();
+    if (m_Perm.size() > nAll) m_Perm.clear();
+    for (size_t i = m_Perm.size(); i < nAll; i++) m_Perm.push_back((uint32_t)i); // addSamples appended at the end
+    m_Keys.resize(nAll);
+    for (size_t i = 0; i < nAll; i++) m_Keys[i] = m_Samples[m_Perm[i]].distanceTo(src);
+    ppe_heap::make_heap(m_Keys.data(), m_Perm.data(), (std::ptrdiff_t)nAll);
     std::vector<Candidate> bestSamplesHeaps[nTurningRadii];
     bool doneChecks[nTurningRadii] = {false, false};
     const size_t nSamples = m_Samples.size();
@@ -250,14 +258,14 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
         const size_t want = std::min<size_t>((size_t)m_KnnChunk, heapLen);
         chunk.clear();
         walk.clear();
-        walk.push_back(Node(m_Samples[0].distanceTo(src), 0));
+        walk.push_back(Node(m_Keys[0], 0));
         while (chunk.size() < want && !walk.empty()) {
             std::pop_heap(walk.begin(), walk.end(), nodeGreater);
             const size_t idx = walk.back().second;
             walk.pop_back();
-            chunk.push_back(m_Samples[idx]);
+            chunk.push_back(m_Samples[m_Perm[idx]]);
             for (size_t child = 2 * idx + 1; child <= 2 * idx + 2 && child < heapLen; child++) {
-                walk.push_back(Node(m_Samples[child].distanceTo(src), child));
+                walk.push_back(Node(m_Keys[child], child));
                 std::push_heap(walk.begin(), walk.end(), nodeGreater);
             }
         }
@@ -270,8 +278,8 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
         used.assign(m, 0);
         // replay of the reference's loop body: real pops
         for (size_t c = 0; c < m && (!doneChecks[0] || !doneChecks[1]); c++) {
-            State sample = m_Samples.front();
-            std::pop_heap(m_Samples.begin(), m_Samples.end() - pops, comp);
+            State sample = m_Samples[m_Perm[0]]; // m_Samples.front() of the reference's arrangement
+            ppe_heap::pop_heap(m_Keys.data(), m_Perm.data(), (std::ptrdiff_t)(nSamples - pops));
             pops++;
             // where are this sample's solves?
             size_t at = m;

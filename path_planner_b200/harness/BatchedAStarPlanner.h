@@ -12,6 +12,7 @@
 #ifndef PPE_BATCHED_ASTAR_PLANNER_H
 #define PPE_BATCHED_ASTAR_PLANNER_H
 
+#include <cstdint>
 #include <vector>
 
 #include "planner/AStarPlanner.h"
@@ -52,6 +53,12 @@ private:
     int m_KnnChunk;
     int m_Heuristic = PPE_H_MAX_DISTANCE;
     long m_TrueCostEdges = 0, m_DubinsSolves = 0, m_Batches = 0;
+
+    // The reference keeps m_Samples itself heap-ordered (SamplingBasedPlanner.cpp:85-93).  Here the States stay where
+    // addSamples put them; the arrangement the reference's vector would have is m_Samples[m_Perm[i]], and the heap
+    // operations run on (m_Keys, m_Perm) -- see KeyedHeap.h.
+    std::vector<uint32_t> m_Perm;
+    std::vector<double> m_Keys;
 
     // scratch reused across expansions
     std::vector<State> m_Scratch;

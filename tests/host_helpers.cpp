@@ -77,3 +77,31 @@ void hh_libm_acos(int64_t n, const double* x, double* out) {
 }
 
 } // extern "C"
+
+// ---- KeyedHeap.h against the real std::make_heap / std::pop_heap (ties included) ---------------------------------
+#include <algorithm>
+#include <vector>
+
+#include "../path_planner_b200/harness/KeyedHeap.h"
+
+extern "C" {
+// keys: n doubles (duplicates welcome); pops: how many pop_heap calls follow the make_heap.  Returns 0 when the keyed
+// routines leave exactly the arrangement the std:: ones leave on (key, id) pairs compared by key only.
+int hh_keyed_heap_check(const double* keys, int n, int pops) {
+    struct Item { double key; uint32_t id; };
+    std::vector<Item> ref((size_t)n);
+    std::vector<double> k(keys, keys + n);
+    std::vector<uint32_t> id((size_t)n);
+    for (int i = 0; i < n; i++) { ref[i].key = keys[i]; ref[i].id = (uint32_t)i; id[i] = (uint32_t)i; }
+    auto comp = [](const Item& a, const Item& b) { return a.key > b.key; }; // SamplingBasedPlanner.cpp:36-40
+    std::make_heap(ref.begin(), ref.end(), comp);
+    ppe_heap::make_heap(k.data(), id.data(), n);
+    for (int i = 0; i < n; i++) if (ref[i].id != id[i] || ref[i].key != k[i]) return 1 + i;
+    for (int p = 0; p < pops && p < n; p++) {
+        std::pop_heap(ref.begin(), ref.end() - p, comp);
+        ppe_heap::pop_heap(k.data(), id.data(), n - p);
+        for (int i = 0; i < n; i++) if (ref[i].id != id[i] || ref[i].key != k[i]) return 100000 + p;
+    }
+    return 0;
+}
+}

@@ -53,3 +53,27 @@ def test_mispredicted_chunks_do_not_change_the_plan():
         "print('ok')\n" % (common.ROOT, CPU_SO))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_keyed_heap_matches_libstdcxx(host_helpers):
+    """path_planner_b200/harness/KeyedHeap.h restates libstdc++'s heap algorithms on (key, index) arrays; the arrangement
+    after make_heap and after every pop_heap must be the one std::make_heap / std::pop_heap produce -- with heavy ties."""
+    import ctypes as C
+    hh = host_helpers
+    hh.hh_keyed_heap_check.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
+    rng = np.random.default_rng(12)
+    for n in (1, 2, 3, 4, 5, 7, 8, 16, 17, 100, 101, 1000, 4097):
+        for mode in ("distinct", "ties", "all-equal", "sorted", "reversed"):
+            if mode == "distinct":
+                k = rng.uniform(0, 100, n)
+            elif mode == "ties":
+                k = rng.integers(0, max(2, n // 8), n).astype(np.float64)
+            elif mode == "all-equal":
+                k = np.full(n, 3.5)
+            elif mode == "sorted":
+                k = np.sort(rng.uniform(0, 100, n))
+            else:
+                k = np.sort(rng.uniform(0, 100, n))[::-1].copy()
+            k = np.ascontiguousarray(k, dtype=np.float64)
+            rc = hh.hh_keyed_heap_check(k.ctypes.data_as(C.POINTER(C.c_double)), n, min(n, 300))
+            assert rc == 0, (n, mode, rc)

@@ -144,6 +144,7 @@ Planner::Stats BatchedAStarPlanner::plan(const RibbonManager& ribbonManager, con
     uploadWorld(ribbonManager, start, config);
     m_TrueCostEdges = m_DubinsSolves = m_Batches = 0;
     m_Perm.clear(); // AStarPlanner::plan starts from an empty sample set (AStarPlanner.cpp:24)
+    m_SampleXY.clear();
     return AStarPlanner::plan(ribbonManager, start, std::move(config), previousPlan, timeRemaining);
 }
 
@@ -209,10 +210,25 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
     // std::make_heap(m_Samples.begin(), m_Samples.end(), comp) with comp = "farther from src is lower priority", on
     // the (distance, index) representation: every distance is computed once instead of twice per comparison
     const size_t nAll = m_Samples.size();
-    if (m_Perm.size() > nAll) m_Perm.clear();
-    for (size_t i = m_Perm.size(); i < nAll; i++) m_Perm.push_back((uint32_t)i); // addSamples appended at the end
+    if (m_Perm.size() > nAll) { m_Perm.clear(); m_SampleXY.clear(); }
+    for (size_t i = m_Perm.size(); i < nAll; i++) { // addSamples appended at the end
+        m_Perm.push_back((uint32_t)i);
+        m_SampleXY.push_back(m_Samples[i].x());
+        m_SampleXY.push_back(m_Samples[i].y());
+    }
+    // State::distanceTo (State.cpp:91-93), same expression, streamed over the stored samples; then gathered into
+    // the heap's arrangement
+    m_Dist.resize(nAll);
+    {
+        const double sx = src.x(), sy = src.y();
+        const double* xy = m_SampleXY.data();
+        for (size_t i = 0; i < nAll; i++) {
+            const double x = xy[2 * i], y = xy[2 * i + 1];
+            m_Dist[i] = sqrt((x - sx) * (x - sx) + (y - sy) * (y - sy));
+        }
+    }
     m_Keys.resize(nAll);
-    for (size_t i = 0; i < nAll; i++) m_Keys[i] = m_Samples[m_Perm[i]].distanceTo(src);
+    for (size_t i = 0; i < nAll; i++) m_Keys[i] = m_Dist[m_Perm[i]];
     ppe_heap::make_heap(m_Keys.data(), m_Perm.data(), (std::ptrdiff_t)nAll);
     std::vector<Candidate> bestSamplesHeaps[nTurningRadii];
     bool doneChecks[nTurningRadii] = {false, false};

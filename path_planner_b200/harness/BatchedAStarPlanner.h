@@ -59,6 +59,8 @@ private:
     // operations run on (m_Keys, m_Perm) -- see KeyedHeap.h.
     std::vector<uint32_t> m_Perm;
     std::vector<double> m_Keys;
+    std::vector<double> m_SampleXY; // x, y of m_Samples in storage order (the distance pass streams 16 B per sample)
+    std::vector<double> m_Dist;     // distance of every stored sample to the vertex being expanded
 
     // scratch reused across expansions
     std::vector<State> m_Scratch;

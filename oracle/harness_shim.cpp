@@ -26,4 +26,18 @@ int harness_plan(ref_ctx* ctx, int device, int ribbon_set, const double* start5,
     return n;
 }
 
+// the same single expansion through the product's adapter (its expand() needs the world on the engine: plan() would
+// upload it, so this entry point does)
+int harness_expand_once(ref_ctx* ctx, int device, int ribbon_set, int nSamples, int seed, double* f_out, int cap) {
+    static ppe_ctx* engine = nullptr;
+    if (!engine && ppe_create(device, &engine) != PPE_OK) { ctx->lastError = "ppe_create failed"; return -2; }
+    BatchedAStarPlanner planner(engine, 128);
+    try {
+        PlannerConfig config = ctx->config;
+        config.setStartStateTime(1);
+        planner.prepareWorld(ctx->sets[ribbon_set], State(0, 0, 0, 2.5, 1), config);
+    } catch (std::exception& ex) { ctx->lastError = ex.what(); return -1; }
+    return ref_run_expand_once(planner, ctx, ribbon_set, nSamples, seed, f_out, cap);
+}
+
 } // extern "C"

@@ -382,4 +382,9 @@ int ref_plan(ref_ctx* ctx, int ribbon_set, const double* start5, double timeRema
                         plan_out, plan_cap, stats10);
 }
 
+int ref_expand_once(ref_ctx* ctx, int ribbon_set, int nSamples, int seed, double* f_out, int cap) {
+    AStarPlanner planner;
+    return ref_run_expand_once(planner, ctx, ribbon_set, nSamples, seed, f_out, cap);
+}
+
 } // extern "C"

@@ -10,6 +10,9 @@
 
 #include "planner/AStarPlanner.h"
 #include "planner/utilities/RibbonManager.h"
+#include "planner/utilities/StateGenerator.h"
+#include "planner/search/Vertex.h"
+#include <stdexcept>
 #include "common/dynamic_obstacles/BinaryDynamicObstaclesManager.h"
 #include "common/dynamic_obstacles/GaussianDynamicObstaclesManager.h"
 #include "ppe.h"
@@ -80,6 +83,36 @@ int ref_run_plan(PlannerT& planner, ref_ctx* ctx, int ribbon_set, const double* 
     stats10[6] = n ? stats.PlanTimePenalty : -1; stats10[7] = n ? stats.PlanHValue : -1;
     stats10[8] = n ? (double)stats.PlanDepth : -1; stats10[9] = (double)ctx->clockCalls;
     return n;
+}
+
+// ExpandTest1Ribbons (test_planner.cpp:1061-1082): one expansion of a root vertex over `nSamples` samples drawn by
+// StateGenerator(-50, 50, -50, 50, 2.5, 2.5, seed); the start state is the generator's first draw with time 1.
+// Pops the open list dry: returns the number of vertices it held, f_out receives their f-values in pop order.
+template <typename PlannerT>
+int ref_run_expand_once(PlannerT& planner, ref_ctx* ctx, int ribbon_set, int nSamples, int seed, double* f_out, int cap) {
+    try {
+        StateGenerator generator(-50, 50, -50, 50, 2.5, 2.5, seed);
+        State start = generator.generate();
+        start.time() = 1;
+        PlannerConfig config = ctx->config;
+        config.setStartStateTime(1);
+        auto root = Vertex::makeRoot(start, ctx->sets[ribbon_set]);
+        root->computeApproxToGo(config);
+        planner.setConfig(config);
+        planner.addSamples(generator, nSamples);
+        planner.expand(root, config.obstaclesManager());
+        int n = 0;
+        for (;;) {
+            Vertex::SharedPtr v;
+            try { v = planner.popVertexQueue(); } catch (std::out_of_range&) { break; }
+            if (n < cap) f_out[n] = v->f();
+            n++;
+        }
+        return n;
+    } catch (std::exception& ex) {
+        ctx->lastError = ex.what();
+        return -1;
+    }
 }
 
 #endif

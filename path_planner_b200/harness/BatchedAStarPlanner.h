@@ -31,6 +31,14 @@ public:
 
     void expand(const std::shared_ptr<Vertex>& sourceVertex, const DynamicObstaclesManager& obstacles) override;
 
+    // What plan() does before it hands over to AStarPlanner::plan: config, map, obstacles to the engine.  Public for
+    // callers that drive expand() themselves (the reference's ExpandTest1Ribbons does).
+    void prepareWorld(const RibbonManager& ribbonManager, const State& start, const PlannerConfig& config) {
+        uploadWorld(ribbonManager, start, config);
+        m_Perm.clear();
+        m_SampleXY.clear();
+    }
+
     // instrumentation
     long trueCostEdges() const { return m_TrueCostEdges; }
     long dubinsSolves() const { return m_DubinsSolves; }

@@ -238,3 +238,43 @@ def test_binary_dynamic_obstacles_test_1():
     ce = lambda x, y, t: lib.oracle_collision_exists(o.ctx, x, y, t, 0)
     assert [ce(42, 42, 1), ce(42, 49, 1), ce(42, 50, 1), ce(44, 42, 1), ce(45, 42, 1)] == [1, 1, 0, 1, 0]
     assert [ce(42, 52, 11), ce(42, 59, 11), ce(42, 60, 11), ce(44, 52, 11), ce(45, 52, 11)] == [1, 1, 0, 1, 0]
+
+
+def test_angle_consistency_2():
+    """AngleConsitencyTest2, test_planner.cpp:1160-1182: along a Dubins path of radius 8 sampled every
+    increment / maxSpeed seconds at max speed, consecutive headings differ by at most increment / radius + 1e-5, the
+    sample at the wrapper's end time has the destination's heading, and so does the last sample (same tolerance)."""
+    o = common.load_oracle("glibc")
+    lib = o.lib
+    D, I = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.oracle_wrapper_sample.argtypes = [D, D, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, D, D, D, D, I]
+    cfg = _cfg()
+    o.set_config(cfg)
+    tol = cfg.collision_checking_increment / cfg.turning_radius + 1e-5
+    rng = np.random.default_rng(7)
+    yaw = lambda h: (math.pi / 2 - h) if math.pi / 2 - h >= 0 else math.pi / 2 - h + 2 * math.pi
+    hdiff = lambda a, b: abs((a - b + math.pi) % (2 * math.pi) - math.pi)   # State::headingDifference, wrapped
+    for _ in range(10):
+        s = [rng.uniform(-50, 50), rng.uniform(-50, 50), rng.uniform(0, 2 * math.pi)]
+        e = [rng.uniform(-50, 50), rng.uniform(-50, 50), rng.uniform(0, 2 * math.pi)]
+        q0, q1 = [s[0], s[1], yaw(s[2])], [e[0], e[1], yaw(e[2])]
+        typ, par, length, err = o.dubins_batch([q0], [q1], [cfg.turning_radius])
+        assert err[0] == 0
+        dt = cfg.collision_checking_increment / cfg.max_speed
+        t_end = 1.0 + length[0] / cfg.max_speed
+        times = np.append(np.arange(1.0, t_end, dt), t_end)
+        n = len(times)
+        x, y, h = np.zeros(n), np.zeros(n), np.zeros(n)
+        ok = np.zeros(n, dtype=np.int32)
+        qi = np.array(q0)
+        pr = np.ascontiguousarray(par[0])
+        lib.oracle_wrapper_sample(abi.dptr(qi), abi.dptr(pr), cfg.turning_radius, int(typ[0]), 1.0, cfg.max_speed, n,
+                                  abi.dptr(times), abi.dptr(x), abi.dptr(y), abi.dptr(h), ok.ctypes.data_as(I))
+        assert (ok == 1).all()                                    # 1 = sampled, 0 = the reference throws
+        assert hdiff(h[-1], e[2]) <= tol                          # sample at the end time
+        prev = s[2]
+        for k in range(n - 1):
+            assert hdiff(prev, h[k]) <= tol, (k, prev, h[k])
+            prev = h[k]
+        assert hdiff(prev, e[2]) <= tol
+        assert math.hypot(x[-1] - e[0], y[-1] - e[1]) < 2e-5     # the end sample may take the 1e-5 m retry (DubinsWrapper.cpp:39-42)

@@ -32,3 +32,21 @@ def test_knn_chunk_does_not_change_the_plan(lib):
     b, plan_b = plan_cases.compare(lib, case, exact=False, knn_chunk=512)
     assert np.array_equal(plan_a, plan_b)
     assert a["dubins_solves"] < b["dubins_solves"]
+
+
+def test_expand_test_1_ribbons_on_the_engine(lib):
+    """ExpandTest1Ribbons (test_planner.cpp:1061-1082) with the CUDA engine behind the adapter: exactly 40 vertices,
+    non-decreasing f, the reference's f-values within 1e-9."""
+    import ctypes as C
+    from path_planner_b200 import synth
+    D = C.POINTER(C.c_double)
+    lib.lib.ref_expand_once.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, D, C.c_int]
+    lib.lib.harness_expand_once.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, D, C.c_int]
+    world = synth.world_c1()
+    sid = world.upload_ref(lib)
+    f_ref, f_har = np.zeros(64), np.zeros(64)
+    n_ref = lib.lib.ref_expand_once(lib.ctx, sid, 1000, 9, f_ref.ctypes.data_as(D), 64)
+    n_har = lib.lib.harness_expand_once(lib.ctx, 0, sid, 1000, 9, f_har.ctypes.data_as(D), 64)
+    assert n_ref == 40 and n_har == 40
+    assert np.all(np.diff(f_har[:40]) >= 0)
+    assert np.allclose(f_ref[:40], f_har[:40], rtol=common.RTOL, atol=common.ATOL)

@@ -77,3 +77,22 @@ def test_keyed_heap_matches_libstdcxx(host_helpers):
             k = np.ascontiguousarray(k, dtype=np.float64)
             rc = hh.hh_keyed_heap_check(k.ctypes.data_as(C.POINTER(C.c_double)), n, min(n, 300))
             assert rc == 0, (n, mode, rc)
+
+
+def test_expand_test_1_ribbons(lib):
+    """ExpandTest1Ribbons, test_planner.cpp:1061-1082: one expansion over 1000 samples leaves exactly 40 vertices on
+    the open list (2 speeds x 2 radii to the ribbon end point + 2 radii x k = 9 winners x 2 speeds), popped in
+    non-decreasing f.  The adapter's expansion must push the same 40 f-values in the same order as the reference's."""
+    import ctypes as C
+    from path_planner_b200 import synth
+    D = C.POINTER(C.c_double)
+    lib.lib.ref_expand_once.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, D, C.c_int]
+    lib.lib.harness_expand_once.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, D, C.c_int]
+    world = synth.world_c1()          # RibbonManager().add(0, 10, 0, 30), Map base, no obstacles
+    sid = world.upload_ref(lib)
+    f_ref, f_har = np.zeros(64), np.zeros(64)
+    n_ref = lib.lib.ref_expand_once(lib.ctx, sid, 1000, 9, f_ref.ctypes.data_as(D), 64)
+    n_har = lib.lib.harness_expand_once(lib.ctx, 0, sid, 1000, 9, f_har.ctypes.data_as(D), 64)
+    assert n_ref == 40 and n_har == 40
+    assert np.all(np.diff(f_ref[:40]) >= 0)
+    assert np.array_equal(f_ref[:40], f_har[:40])

@@ -370,7 +370,7 @@ def main():
         eng.true_cost_batch_device(n, d_edges.data_ptr(), d_results.data_ptr(), sh)
         if distributed:
             # the path's only exchange: one (best f, edge index) record per GPU back to the planner
-            eng.best_copy_device(best_local.data_ptr(), sh)
+            eng.best_copy_device(best_local.data_ptr(), 0, sh)
             dist.all_gather_into_tensor(best_all, best_local)
 
     for _ in range(args.warmup):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PPE_ABI_VERSION 1
+#define PPE_ABI_VERSION 2
 
 typedef struct ppe_ctx ppe_ctx;
 
@@ -194,10 +194,16 @@ int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges,
                                ppe_edge_result* d_results, void* stream);
 /* (f, edge_index) of the last *_device batch; synchronises `stream`. */
 int ppe_best_device(ppe_ctx* ctx, double* f, int64_t* edge_index, void* stream);
-/* Same record as 16 bytes {double f; int64 edge_index} copied device-to-device into d_dst on
- * `stream` without synchronising: the send buffer of the per-batch NCCL gather (one record per
- * GPU) when edge batches are sharded over ranks. */
-int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, void* stream);
+/* Same record as 16 bytes {double f; int64 edge_index + index_base} written into d_dst on `stream`
+ * without synchronising: the send buffer of the per-batch NCCL gather (one record per GPU) when one
+ * edge batch is sharded over ranks; index_base = the rank's first edge in the whole batch, so the
+ * gathered records carry GLOBAL edge indices and ties break towards the smaller global index. */
+int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, int64_t index_base, void* stream);
+
+/* Counter bumped by every ppe_set_map_none / ppe_set_map_bitmap on this context.  A caller that keeps
+ * "which Map object did I upload last" next to its context (path_planner_b200/harness WorldCache)
+ * compares it to notice uploads made by anybody else. */
+uint64_t ppe_map_generation(const ppe_ctx* ctx);
 
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* number of engine kernels launched on this ctx since creation */

@@ -6,18 +6,31 @@
 
 #include "BatchedAStarPlanner.h"
 
+#include <map>
+#include <mutex>
+
+// one engine context (+ its world cache) per (test context, device): nothing process-global is shared between
+// planning threads
+struct EngineSlot { ppe_ctx* engine = nullptr; PpeWorldCache cache; };
+static EngineSlot& engineFor(ref_ctx* ctx, int device) {
+    static std::mutex mu;
+    static std::map<std::pair<ref_ctx*, int>, EngineSlot> slots;
+    std::lock_guard<std::mutex> lock(mu);
+    EngineSlot& s = slots[std::make_pair(ctx, device)];
+    if (!s.engine && ppe_create(device, &s.engine) != PPE_OK) s.engine = nullptr;
+    return s;
+}
+
 extern "C" {
 
 // stats13 = the 10 values of ref_plan + true-cost edges, Dubins solves, engine batches
 int harness_plan(ref_ctx* ctx, int device, int ribbon_set, const double* start5, double timeRemaining, double clock0,
                  double tick, int initialSamples, int useBrownPaths, int knnChunk, double* plan_out, int plan_cap,
                  double* stats13) {
-    static ppe_ctx* engine = nullptr; // one engine context per process (one planning thread)
-    if (!engine) {
-        int rc = ppe_create(device, &engine);
-        if (rc != PPE_OK) { ctx->lastError = "ppe_create failed: no CUDA device (the engine has no CPU path)"; return -2; }
-    }
-    BatchedAStarPlanner planner(engine, knnChunk > 0 ? knnChunk : 128);
+    EngineSlot& slot = engineFor(ctx, device);
+    if (!slot.engine) { ctx->lastError = "ppe_create failed: no CUDA device (the engine has no CPU path)"; return -2; }
+    ppe_ctx* engine = slot.engine;
+    BatchedAStarPlanner planner(engine, knnChunk > 0 ? knnChunk : 128, &slot.cache);
     int n = ref_run_plan(planner, ctx, ribbon_set, start5, timeRemaining, clock0, tick, initialSamples, useBrownPaths,
                          plan_out, plan_cap, stats13);
     stats13[10] = (double)planner.trueCostEdges();
@@ -29,9 +42,10 @@ int harness_plan(ref_ctx* ctx, int device, int ribbon_set, const double* start5,
 // the same single expansion through the product's adapter (its expand() needs the world on the engine: plan() would
 // upload it, so this entry point does)
 int harness_expand_once(ref_ctx* ctx, int device, int ribbon_set, int nSamples, int seed, double* f_out, int cap) {
-    static ppe_ctx* engine = nullptr;
-    if (!engine && ppe_create(device, &engine) != PPE_OK) { ctx->lastError = "ppe_create failed"; return -2; }
-    BatchedAStarPlanner planner(engine, 128);
+    EngineSlot& slot = engineFor(ctx, device);
+    if (!slot.engine) { ctx->lastError = "ppe_create failed"; return -2; }
+    ppe_ctx* engine = slot.engine;
+    BatchedAStarPlanner planner(engine, 128, &slot.cache);
     try {
         PlannerConfig config = ctx->config;
         config.setStartStateTime(1);

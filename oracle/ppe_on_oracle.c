@@ -35,12 +35,15 @@ int oracle_get_ribbons_after(oracle_ctx* c, int64_t i, double* xyxy, int cap);
 #define O(ctx) ((oracle_ctx*)(ctx))
 
 int ppe_abi_version(void) { return PPE_ABI_VERSION; }
+static uint64_t g_map_generation = 0;
+uint64_t ppe_map_generation(const ppe_ctx* ctx) { (void)ctx; return g_map_generation; }
 int ppe_create(int device, ppe_ctx** out) { (void)device; return oracle_create((oracle_ctx**)out); }
 void ppe_destroy(ppe_ctx* ctx) { oracle_destroy(O(ctx)); }
 const char* ppe_last_error(const ppe_ctx* ctx) { return oracle_last_error((const oracle_ctx*)ctx); }
 int ppe_set_config(ppe_ctx* ctx, const ppe_config* cfg) { return oracle_set_config(O(ctx), cfg); }
-int ppe_set_map_none(ppe_ctx* ctx) { return oracle_set_map_none(O(ctx)); }
+int ppe_set_map_none(ppe_ctx* ctx) { g_map_generation++; return oracle_set_map_none(O(ctx)); }
 int ppe_set_map_bitmap(ppe_ctx* ctx, const uint8_t* bits, int rows, int cols, int stride, double res) {
+    g_map_generation++;
     return oracle_set_map_bitmap(O(ctx), bits, rows, cols, stride, res);
 }
 int ppe_set_obstacles_none(ppe_ctx* ctx) { return oracle_set_obstacles_none(O(ctx)); }

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-PPE_ABI_VERSION = 1
+PPE_ABI_VERSION = 2
 
 # ppe_status
 PPE_OK = 0

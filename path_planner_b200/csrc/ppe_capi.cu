@@ -51,6 +51,7 @@ struct ppe_ctx {
     int safe_radius = -1;           // radius d_safe was built for; -1 = stale
     int map_kind = kMapNone, rows = 0, cols = 0, stride_words = 0;
     double resolution = 1;
+    uint64_t map_generation = 0;    // bumped by every ppe_set_map_*: lets a caller-side cache notice foreign uploads
     int obs_cull_ok = 1;
 
     // dynamic obstacles
@@ -62,6 +63,7 @@ struct ppe_ctx {
     std::vector<int> h_off, h_cnt;
     std::vector<double> h_cct;
     bool sets_dirty = true;
+    size_t uploaded_ribbons = 0, uploaded_sets = 0; // the pool is append-only: only the tail is copied
     int max_set = 0;
     double4* d_ribbons = nullptr;
     int* d_off = nullptr;
@@ -88,6 +90,7 @@ struct ppe_ctx {
     unsigned int* d_heavy = nullptr;
     size_t cap_heavy = 0;
     bool thread_walker = true;            // PPE_THREAD_WALKER=0: the warp walker evaluates every edge
+    K2Tuning tuning;                      // PPE_K2T_DIRTY / PPE_K2T_CPS, read at ppe_create
     BestD* d_block_best = nullptr;
     BestD* d_best = nullptr;
     int max_blocks = 0;
@@ -138,37 +141,53 @@ int ribbon_cap_for(int max_set) {
     return cap;
 }
 
+// grows a device array to hold `need` elements, keeping its first `keep` (device-to-device copy)
+template <typename T>
+int grow_keep(ppe_ctx* ctx, T** p, size_t* cap, size_t need, size_t keep, size_t first_cap) {
+    if (need <= *cap) return PPE_OK;
+    size_t c = *cap ? *cap : first_cap;
+    while (c < need) c *= 2;
+    T* fresh = nullptr;
+    PPE_CUDA(ctx, cudaMalloc((void**)&fresh, c * sizeof(T)));
+    if (*p && keep) PPE_CUDA(ctx, cudaMemcpyAsync(fresh, *p, keep * sizeof(T), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (*p) {
+        PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PPE_CUDA(ctx, cudaFree(*p));
+    }
+    *p = fresh;
+    *cap = c;
+    return PPE_OK;
+}
+
+// The interned pool is append-only between ppe_clear_ribbon_sets calls: only the sets added since the last
+// upload travel (one expansion interns one set, so a plan of E expansions copies O(E) ribbons, not O(E^2)).
 int upload_sets(ppe_ctx* ctx) {
     if (!ctx->sets_dirty) return PPE_OK;
     const size_t nr = ctx->h_ribbons.size() / 4, ns = ctx->h_cnt.size();
-    if (nr + 1 > ctx->cap_ribbons) {
-        if (ctx->d_ribbons) PPE_CUDA(ctx, cudaFree(ctx->d_ribbons));
-        ctx->d_ribbons = nullptr;
-        size_t c = ctx->cap_ribbons ? ctx->cap_ribbons : 1024;
-        while (c < nr + 1) c *= 2;
-        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_ribbons, c * sizeof(double4)));
-        ctx->cap_ribbons = c;
+    if (ctx->uploaded_ribbons > nr || ctx->uploaded_sets > ns) ctx->uploaded_ribbons = ctx->uploaded_sets = 0;
+    const size_t r0 = ctx->uploaded_ribbons, s0 = ctx->uploaded_sets;
+    int rc = grow_keep(ctx, &ctx->d_ribbons, &ctx->cap_ribbons, nr + 1, r0, 1024);
+    if (rc != PPE_OK) return rc;
+    {
+        size_t c1 = ctx->cap_sets, c2 = ctx->cap_sets, c3 = ctx->cap_sets;
+        rc = grow_keep(ctx, &ctx->d_off, &c1, ns + 1, s0, 64);
+        if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_cnt, &c2, ns + 1, s0, 64);
+        if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_cct, &c3, ns + 1, s0, 64);
+        if (rc != PPE_OK) return rc;
+        ctx->cap_sets = c1;
     }
-    if (ns + 1 > ctx->cap_sets) {
-        if (ctx->d_off) PPE_CUDA(ctx, cudaFree(ctx->d_off));
-        if (ctx->d_cnt) PPE_CUDA(ctx, cudaFree(ctx->d_cnt));
-        if (ctx->d_cct) PPE_CUDA(ctx, cudaFree(ctx->d_cct));
-        ctx->d_off = ctx->d_cnt = nullptr;
-        ctx->d_cct = nullptr;
-        size_t c = ctx->cap_sets ? ctx->cap_sets : 64;
-        while (c < ns + 1) c *= 2;
-        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_off, c * sizeof(int)));
-        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_cnt, c * sizeof(int)));
-        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_cct, c * sizeof(double)));
-        ctx->cap_sets = c;
+    if (nr > r0)
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_ribbons + r0, ctx->h_ribbons.data() + 4 * r0, (nr - r0) * 4 * sizeof(double),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    if (ns > s0) {
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_off + s0, ctx->h_off.data() + s0, (ns - s0) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cnt + s0, ctx->h_cnt.data() + s0, (ns - s0) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cct + s0, ctx->h_cct.data() + s0, (ns - s0) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (nr) PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_ribbons, ctx->h_ribbons.data(), nr * 4 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    if (ns) {
-        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_off, ctx->h_off.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cnt, ctx->h_cnt.data(), ns * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cct, ctx->h_cct.data(), ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    // batches run on other streams (caller's / the lanes'): the tail must have landed before they start
     PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->uploaded_ribbons = nr;
+    ctx->uploaded_sets = ns;
     ctx->sets_dirty = false;
     return PPE_OK;
 }
@@ -279,6 +298,11 @@ int ppe_create(int device, ppe_ctx** out) {
     {
         const char* env = getenv("PPE_THREAD_WALKER");
         if (env && env[0] == '0') ctx->thread_walker = false;
+        const char* env_cp = getenv("PPE_K2T_CPS");   // tuning knob: check-points a K2t thread may walk
+        if (env_cp && atoi(env_cp) > 0) ctx->tuning.cp_budget = atoi(env_cp);
+        const char* env_d = getenv("PPE_K2T_DIRTY");  // tuning knob: non-clean chunks a K2t thread may evaluate
+        if (env_d) ctx->tuning.dirty_budget = atoi(env_d);
+        ctx->tuning = clamp_tuning(ctx->tuning);
     }
     bool ok = cudaMalloc((void**)&ctx->d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_out_count, sizeof(unsigned long long)) == cudaSuccess &&
@@ -333,6 +357,7 @@ int ppe_set_config(ppe_ctx* ctx, const ppe_config* cfg) {
 int ppe_set_map_none(ppe_ctx* ctx) {
     if (!ctx) return PPE_ERR_INVALID;
     ctx->map_kind = kMapNone;
+    ctx->map_generation++;
     return PPE_OK;
 }
 
@@ -361,6 +386,7 @@ int ppe_set_map_bitmap(ppe_ctx* ctx, const uint8_t* bits, int rows, int cols, in
     PPE_CUDA(ctx, cudaMemcpy(ctx->d_map, packed.data(), packed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->map_kind = kMapBitmap;
     ctx->rows = rows; ctx->cols = cols; ctx->stride_words = words; ctx->resolution = resolution;
+    ctx->map_generation++;
     return PPE_OK;
 }
 
@@ -467,6 +493,7 @@ int ppe_clear_ribbon_sets(ppe_ctx* ctx) {
     if (!ctx) return PPE_ERR_INVALID;
     ctx->h_ribbons.clear(); ctx->h_off.clear(); ctx->h_cnt.clear(); ctx->h_cct.clear();
     ctx->max_set = 0;
+    ctx->uploaded_ribbons = ctx->uploaded_sets = 0;
     ctx->sets_dirty = true;
     ctx->have_batch = false;
     return PPE_OK;
@@ -528,7 +555,7 @@ static int run_batch_device(ppe_ctx* ctx, const WorldD& w, int64_t n, const ppe_
     int blocks = 1, launches = 0;
     PPE_CUDA(ctx, launch_true_cost_kernels(w, n, d_edges, ctx->d_prepared, d_results, ctx->d_work,
                                            ctx->thread_walker ? ctx->d_heavy : nullptr, ctx->d_block_best, ctx->max_blocks,
-                                           ctx->sm_count, stream, true, &blocks, &launches));
+                                           ctx->sm_count, stream, true, ctx->tuning, &blocks, &launches));
     PPE_CUDA(ctx, launch_best_final(ctx->d_block_best, blocks, ctx->d_best, 0, false, stream));
     ctx->launches += launches + 1;
     return PPE_OK;
@@ -549,6 +576,8 @@ int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges,
 int ppe_best_device(ppe_ctx* ctx, double* f, int64_t* edge_index, void* stream) {
     if (!ctx || !f || !edge_index) return PPE_ERR_INVALID;
     PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->cfg.heuristic != PPE_H_MAX_DISTANCE && !tsp_on_device(ctx->cfg.heuristic))
+        return fail(ctx, PPE_ERR_STATE, "ppe_best*: h is not evaluated on the device for this heuristic (f = g + h unknown)");
     BestD b;
     PPE_CUDA(ctx, cudaMemcpyAsync(&b, ctx->d_best, sizeof b, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     PPE_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
@@ -557,10 +586,13 @@ int ppe_best_device(ppe_ctx* ctx, double* f, int64_t* edge_index, void* stream) 
     return PPE_OK;
 }
 
-int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, void* stream) {
+int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, int64_t index_base, void* stream) {
     if (!ctx || !d_dst16) return PPE_ERR_INVALID;
     PPE_CUDA(ctx, cudaSetDevice(ctx->device));
-    PPE_CUDA(ctx, cudaMemcpyAsync(d_dst16, ctx->d_best, sizeof(BestD), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (ctx->cfg.heuristic != PPE_H_MAX_DISTANCE && !tsp_on_device(ctx->cfg.heuristic))
+        return fail(ctx, PPE_ERR_STATE, "ppe_best*: h is not evaluated on the device for this heuristic (f = g + h unknown)");
+    PPE_CUDA(ctx, launch_best_export(ctx->d_best, reinterpret_cast<BestD*>(d_dst16), index_base, (cudaStream_t)stream));
+    ctx->launches += 1;
     return PPE_OK;
 }
 
@@ -618,7 +650,7 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
             int blocks = 1, launches = 0;
             PPE_CUDA(ctx, launch_true_cost_kernels(w, cnt, ctx->d_edges + lo, ln.d_prepared, ctx->d_results + lo, ln.d_work,
                                                    ctx->thread_walker ? ln.d_heavy : nullptr, ln.d_block_best, ctx->max_blocks,
-                                                   ctx->sm_count, ln.stream, false, &blocks, &launches));
+                                                   ctx->sm_count, ln.stream, false, ctx->tuning, &blocks, &launches));
             PPE_CUDA(ctx, cudaEventRecord(ctx->ev_k2[k], ln.stream));
             PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_k2[k], 0));
             PPE_CUDA(ctx, launch_best_final(ln.d_block_best, blocks, ctx->d_best, lo, k > 0, ctx->stream));
@@ -674,6 +706,7 @@ int ppe_best(ppe_ctx* ctx, double* f, int64_t* edge_index) {
 }
 
 int64_t ppe_launch_count(const ppe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t ppe_map_generation(const ppe_ctx* ctx) { return ctx ? ctx->map_generation : 0; }
 
 int ppe_measure_fp64_peak(ppe_ctx* ctx, double* tflops, void* stream) {
     if (!ctx || !tflops) return PPE_ERR_INVALID;

@@ -1081,9 +1081,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
 // to "would it change anything?") and the check-point budget is not exceeded.  Anything else (a cover that splits or
 // erases a ribbon, coverage already complete, a non-OK status, unusual time scales) puts the edge on the heavy list and
 // the warp walker K2b evaluates it from scratch; both paths produce the same bits.
-constexpr int kThreadCheckpointBudget = 6; // measured best in [4, 8] on C2 / C3 / C5 (PPE_K2T_CPS)
-constexpr int kThreadDirtyBudget = 2; // chunks a thread evaluates sample by sample before handing the edge over
-constexpr int kThreadDirtyCap = 8;    // upper limit of the PPE_K2T_DIRTY tuning knob
+constexpr int kThreadDirtyCap = 8;    // upper limit of K2Tuning::dirty_budget (size of the per-thread mask array)
 
 struct SeqTime { // cursor over the prepared run table
     const PreparedEdge* p;
@@ -1619,7 +1617,7 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
 cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
                                      ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
                                      BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool,
-                                     int* blocks_out, int* launches_out) {
+                                     K2Tuning tuning, int* blocks_out, int* launches_out) {
     PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
     cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
@@ -1635,15 +1633,11 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
     unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
     if (heavy_list) {
         const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD);
-        static int dirty_budget = -1, cp_budget = kThreadCheckpointBudget;
-        if (dirty_budget < 0) {
-            const char* env_cp = getenv("PPE_K2T_CPS"); // tuning knob: check-points a K2t thread may walk
-            if (env_cp && atoi(env_cp) > 0) cp_budget = atoi(env_cp);
-            const char* env = getenv("PPE_K2T_DIRTY");
-            dirty_budget = env ? atoi(env) : kThreadDirtyBudget; // tuning knob; measured best at 2 on C2 / C3 / C5
-            if (dirty_budget < 0) dirty_budget = 0;
-            if (dirty_budget > kThreadDirtyCap) dirty_budget = kThreadDirtyCap;
+        if (smem_t > 48 * 1024) {
+            e = cudaFuncSetAttribute(k2t_thread_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+            if (e != cudaSuccess) return e;
         }
+        const int dirty_budget = tuning.dirty_budget, cp_budget = tuning.cp_budget;
         k2t_thread_walk<<<(unsigned)((n + 127) / 128), 128, smem_t, stream>>>(world, (long long)n, edges, prepared, results, heavy_list,
                                                                              heavy_count, dirty_budget, cp_budget);
         e = cudaGetLastError();
@@ -1674,6 +1668,24 @@ cudaError_t launch_best_final(const BestD* block_best, int blocks, BestD* best, 
                               cudaStream_t stream) {
     k3_best_final<<<1, 256, 0, stream>>>(block_best, blocks, best, (long long)index_base, accumulate ? 1 : 0);
     return cudaGetLastError();
+}
+
+__global__ void k3_best_export(const BestD* src, BestD* dst, long long index_base) {
+    BestD b = *src;
+    if (b.idx >= 0) b.idx += index_base;
+    *dst = b;
+}
+
+cudaError_t launch_best_export(const BestD* src, BestD* dst, int64_t index_base, cudaStream_t stream) {
+    k3_best_export<<<1, 1, 0, stream>>>(src, dst, (long long)index_base);
+    return cudaGetLastError();
+}
+
+K2Tuning clamp_tuning(K2Tuning t) {
+    if (t.dirty_budget < 0) t.dirty_budget = 0;
+    if (t.dirty_budget > kThreadDirtyCap) t.dirty_budget = kThreadDirtyCap;
+    if (t.cp_budget < 1) t.cp_budget = 1;
+    return t;
 }
 
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t stream) {

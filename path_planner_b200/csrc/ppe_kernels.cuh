@@ -63,15 +63,26 @@ struct BestD {
     long long idx;
 };
 
+// K2t hand-over budgets (measured best on C2 / C3 / C5; PPE_K2T_DIRTY / PPE_K2T_CPS override them per context)
+struct K2Tuning {
+    int dirty_budget = 2; // non-clean chunks a K2t thread evaluates sample by sample before handing the edge to K2b
+    int cp_budget = 6;    // ribbon check-points a K2t thread walks
+};
+K2Tuning clamp_tuning(K2Tuning t);
+// heuristics other than MaxDistance that the kernels evaluate themselves (h >= 0 in the result records)
+inline bool tsp_on_device(int heuristic) { (void)heuristic; return false; }
+
 // launchers (ppe_kernels.cu)
 cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type,
                                 double* param, double* length, int32_t* err, cudaStream_t stream);
 cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_edge* edges, void* prepared_scratch,
                                      ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
                                      BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool,
-                                     int* blocks_out, int* launches_out);
+                                     K2Tuning tuning, int* blocks_out, int* launches_out);
 cudaError_t launch_best_final(const BestD* block_best, int blocks, BestD* best, int64_t index_base, bool accumulate,
                               cudaStream_t stream);
+// *dst = {src->f, src->idx + index_base}: the NCCL send record of a rank that holds edges [index_base, ...)
+cudaError_t launch_best_export(const BestD* src, BestD* dst, int64_t index_base, cudaStream_t stream);
 size_t prepared_edge_bytes();
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t stream);
 // safe[r][c] = all cells within Chebyshev distance `radius` of (r, c) are in bounds and free

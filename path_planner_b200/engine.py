@@ -47,10 +47,12 @@ def load_library():
     lib.ppe_true_cost_batch_device.restype = C.c_int
     lib.ppe_best_device.argtypes = [C.c_void_p, D, C.POINTER(C.c_int64), C.c_void_p]
     lib.ppe_best_device.restype = C.c_int
-    lib.ppe_best_copy_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ppe_best_copy_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ppe_best_copy_device.restype = C.c_int
     lib.ppe_launch_count.argtypes = [C.c_void_p]
     lib.ppe_launch_count.restype = C.c_int64
+    lib.ppe_map_generation.argtypes = [C.c_void_p]
+    lib.ppe_map_generation.restype = C.c_uint64
     lib.ppe_measure_fp64_peak.argtypes = [C.c_void_p, D, C.c_void_p]
     lib.ppe_measure_fp64_peak.restype = C.c_int
     if lib.ppe_abi_version() != abi.PPE_ABI_VERSION:
@@ -102,9 +104,12 @@ class EdgeEngine(CApiWorld):
         self._check(self._lib.ppe_best_device(self._ctx, C.byref(f), C.byref(idx), C.c_void_p(stream)), "best_device")
         return f.value, idx.value
 
-    def best_copy_device(self, d_dst16, stream=0):
-        """{f64 f, i64 edge_index} of the last device batch -> 16 bytes at d_dst16 (no sync)."""
-        self._check(self._lib.ppe_best_copy_device(self._ctx, C.c_void_p(d_dst16), C.c_void_p(stream)), "best_copy_device")
+    def best_copy_device(self, d_dst16, index_base=0, stream=0):
+        """{f64 f, i64 edge_index + index_base} of the last device batch -> 16 bytes at d_dst16 (no sync)."""
+        self._check(self._lib.ppe_best_copy_device(self._ctx, C.c_void_p(d_dst16), int(index_base), C.c_void_p(stream)), "best_copy_device")
+
+    def map_generation(self):
+        return int(self._lib.ppe_map_generation(self._ctx))
 
     # ---- instrumentation ---------------------------------------------------------------------
     def launch_count(self):

@@ -17,6 +17,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <typeinfo>
 
 #include "common/dynamic_obstacles/BinaryDynamicObstaclesManager.h"
 #include "common/dynamic_obstacles/GaussianDynamicObstaclesManager.h"
@@ -60,7 +61,8 @@ int heuristicId(RibbonManager::Heuristic h) {
 }
 } // namespace
 
-BatchedAStarPlanner::BatchedAStarPlanner(ppe_ctx* ctx, int knnChunk) : m_Ctx(ctx), m_KnnChunk(knnChunk) {}
+BatchedAStarPlanner::BatchedAStarPlanner(ppe_ctx* ctx, int knnChunk, PpeWorldCache* cache)
+    : m_Ctx(ctx), m_KnnChunk(knnChunk), m_Cache(cache) {}
 
 void BatchedAStarPlanner::check(int rc, const char* what) {
     if (rc < 0) throw std::runtime_error(std::string(what) + ": " + ppe_last_error(m_Ctx));
@@ -90,17 +92,22 @@ void BatchedAStarPlanner::uploadWorld(const RibbonManager& ribbonManager, const 
 
     // static map: rasterise Map::isBlocked at cell centres (GridWorldMap cells are res x res squares).  The Executive
     // hands the same immutable Map object to every planning cycle (executive.cpp:182-190), so the bitmap already on the
-    // device is kept as long as that very object is alive and this context received it last.
+    // device is kept while the caller's PpeWorldCache (it lives next to the ppe_ctx) says this very object went up last
+    // AND the engine's map generation shows nobody else has uploaded a map to this context since.
     const Map::SharedPtr& map = config.map();
-    static std::weak_ptr<Map> s_uploadedMap;
-    static ppe_ctx* s_uploadedCtx = nullptr;
-    const bool sameMap = s_uploadedCtx == m_Ctx && !s_uploadedMap.expired() && s_uploadedMap.lock() == map;
+    const bool sameMap = m_Cache && m_Cache->valid && m_Cache->generation == ppe_map_generation(m_Ctx) &&
+                         !m_Cache->map.expired() && m_Cache->map.lock() == map;
     if (!sameMap) {
         const double res = map->resolution();
         const double* ext = map->extremes();
-        if (!(res > 0) || !(ext[1] < 1e300)) {
-            check(ppe_set_map_none(m_Ctx), "ppe_set_map_none");
+        if (typeid(*map) == typeid(Map)) {
+            check(ppe_set_map_none(m_Ctx), "ppe_set_map_none"); // the base class: never blocked (Map.cpp:4-6)
         } else {
+            // any other Map must describe itself as a grid (positive resolution, finite extremes anchored at the origin,
+            // as GridWorldMap does); GeoTiffMap overrides neither -> refuse instead of silently dropping its isBlocked
+            if (!(res > 0) || !(ext[1] < 1e300) || !(ext[3] < 1e300) || ext[0] != 0 || ext[2] != 0)
+                throw std::runtime_error("BatchedAStarPlanner: this Map subclass does not expose a grid (resolution() > 0, finite "
+                                         "extremes() with origin 0,0); convert it to an occupancy bitmap first");
             const int cols = (int)std::llround((ext[1] - ext[0]) / res), rows = (int)std::llround((ext[3] - ext[2]) / res);
             const int stride = (cols + 7) / 8;
             std::vector<uint8_t> bits((size_t)rows * stride, 0);
@@ -109,8 +116,11 @@ void BatchedAStarPlanner::uploadWorld(const RibbonManager& ribbonManager, const 
                     if (map->isBlocked((cc + 0.5) * res, (r + 0.5) * res)) bits[(size_t)r * stride + (cc >> 3)] |= (uint8_t)(1u << (cc & 7));
             check(ppe_set_map_bitmap(m_Ctx, bits.data(), rows, cols, stride, res), "ppe_set_map_bitmap");
         }
-        s_uploadedMap = map;
-        s_uploadedCtx = m_Ctx;
+        if (m_Cache) {
+            m_Cache->map = map;
+            m_Cache->generation = ppe_map_generation(m_Ctx);
+            m_Cache->valid = true;
+        }
     }
 
     // dynamic obstacles in container iteration order (the summation order of collisionExists)

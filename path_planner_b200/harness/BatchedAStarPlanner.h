@@ -13,17 +13,27 @@
 #define PPE_BATCHED_ASTAR_PLANNER_H
 
 #include <cstdint>
+#include <memory>
 #include <vector>
 
 #include "planner/AStarPlanner.h"
 #include "ppe.h"
+
+// "Which Map object did this engine context receive last": owned by whoever owns the ppe_ctx (one per planning
+// thread), handed to every planner instance created for it (the Executive makes a new planner per cycle,
+// executive.cpp:85-90).  Never shared between contexts or threads.
+struct PpeWorldCache {
+    std::weak_ptr<Map> map;
+    uint64_t generation = 0; // ppe_map_generation(ctx) right after the upload
+    bool valid = false;
+};
 
 class BatchedAStarPlanner : public AStarPlanner {
 public:
     // `ctx` is borrowed (one ppe_ctx per planning thread); `knnChunk` = how many nearest samples
     // (Euclidean order) get their Dubins paths solved per K1 launch while replaying the
     // reference's k-nearest selection.
-    explicit BatchedAStarPlanner(ppe_ctx* ctx, int knnChunk = 128);
+    explicit BatchedAStarPlanner(ppe_ctx* ctx, int knnChunk = 128, PpeWorldCache* cache = nullptr);
     ~BatchedAStarPlanner() override = default;
 
     Stats plan(const RibbonManager& ribbonManager, const State& start, PlannerConfig config,
@@ -59,6 +69,7 @@ private:
 
     ppe_ctx* m_Ctx;
     int m_KnnChunk;
+    PpeWorldCache* m_Cache; // borrowed, may be null (then the map is uploaded for every plan)
     int m_Heuristic = PPE_H_MAX_DISTANCE;
     long m_TrueCostEdges = 0, m_DubinsSolves = 0, m_Batches = 0;
 

@@ -216,6 +216,46 @@ def world_c5(size=4096):
     return _add_obstacles(w, "gaussian", 50, 0.05 * size, 0.95 * size, 5)
 
 
+def with_resolution(world, resolution):
+    """The same world with its occupancy grid resampled to `resolution` metres per cell over the same extent
+    (nearest cell).  Exercises x / res by division (non power-of-two resolutions, GridWorldMap.cpp:84-93) and the
+    resolution-dependent dilation radius of the engine's chunk culling."""
+    old = world.blocked_cells()
+    ext_y, ext_x = old.shape[0] * world.resolution, old.shape[1] * world.resolution
+    rows, cols = int(round(ext_y / resolution)), int(round(ext_x / resolution))
+    ry = np.clip(((np.arange(rows) + 0.5) * resolution / world.resolution).astype(np.int64), 0, old.shape[0] - 1)
+    rx = np.clip(((np.arange(cols) + 0.5) * resolution / world.resolution).astype(np.int64), 0, old.shape[1] - 1)
+    world.set_grid(old[np.ix_(ry, rx)], resolution)
+    world.name += "@%gm" % resolution
+    return world
+
+
+def with_time_offset(world, t0):
+    """Epoch-scale clock: the ROS node feeds state times ~1.7e9 s (seconds since 1970).  Start time, obstacle
+    observation times and (through make_edges) every edge's source time move by t0."""
+    world.cfg.start_state_time += t0
+    world.start = world.start.copy()
+    world.start[4] += t0
+    if world.obstacles is not None:
+        world.obstacles["time"] = world.obstacles["time"] + t0
+    world.name += "+%g s" % t0
+    return world
+
+
+def with_covariances(world, seed=9):
+    """Per-obstacle random symmetric positive-definite covariances instead of the manager's default
+    [[30, 10], [10, 30]] (GaussianDynamicObstaclesManager.h:24-25)."""
+    assert world.obstacle_kind == "gaussian"
+    rng = np.random.default_rng(seed)
+    n = len(world.obstacles["x"])
+    a = rng.uniform(5, 60, n)
+    d = rng.uniform(5, 60, n)
+    b = rng.uniform(-0.8, 0.8, n) * np.sqrt(a * d)
+    world.obstacles["cov"] = np.column_stack([a, b, b, d])
+    world.name += "+cov"
+    return world
+
+
 WORLDS = {
     "c1": world_c1,
     "c2": world_c2,

@@ -44,7 +44,7 @@ def oracle_glibc():
     return common.load_oracle("glibc")
 
 
-# measured on the CPU (tests/test_oracle_variants.py): 4e-5 of edges; allow 5x head-room
+# measured on the CPU (tests/test_oracle_variants.py): 4e-5 of edges; allow 5x head-room (and never less than one edge)
 GLIBC_EDGE_BUDGET = 2e-4
 
 
@@ -80,6 +80,30 @@ def _check_batch(engine, oracle, world, edges, ribbon_lists=200):
     return got, want
 
 
+def _vs_glibc_reference(engine, oracle_glibc, world, edges, got, label):
+    """GPU vs oracle-A (glibc libm == the compiled reference bit for bit).  The engine's Dubins transcendentals are
+    correctly rounded, glibc's are faithful (< 1 ulp): on a few edges per 100 k the last bit differs and with it the
+    side of the 1e-5 m end-sample retry (DubinsWrapper.cpp:39-42).  Costs, flags, status, sample counts and end
+    times must match on EVERY edge; every other field -- all discrete ones included -- on all but a measured handful,
+    and the measured counts are printed per config."""
+    n = len(edges)
+    world.upload(oracle_glibc)
+    ref = oracle_glibc.true_cost_batch(edges)
+    bad = common.diff_results(got, ref)
+    for name_ in ("true_cost", "collision_penalty", "g", "infeasible", "status", "n_samples", "w_end_time"):
+        assert name_ not in bad, common.describe(bad, got, ref)
+    counts = {k: int(len(v)) for k, v in bad.items()}
+    print("[glibc-parity] %s n=%d differing edges per field: %s" % (label, n, counts or "none"))
+    budget = max(1, int(GLIBC_EDGE_BUDGET * n))
+    for name_ in common.DISCRETE:  # word, check-point count, ribbon count, changed flag: a handful at most
+        assert counts.get(name_, 0) <= budget, (name_, counts, common.describe(bad, got, ref))
+    idx = set()
+    for v in bad.values():
+        idx |= set(v.tolist())
+    assert len(idx) <= max(1, int(GLIBC_EDGE_BUDGET * n * 5)), common.describe(bad, got, ref)
+    return counts
+
+
 @pytest.mark.parametrize("name,near,n", [("c1", 0.5, 3000), ("c2", 0.0, 4000), ("c2", 0.6, 4000),
                                           ("c3", 0.3, 1000), ("c3b", 0.3, 1500), ("c4", 0.5, 2000), ("c5", 0.2, 600)])
 def test_true_cost_matches_oracle(engine, oracle, oracle_glibc, name, near, n):
@@ -87,17 +111,72 @@ def test_true_cost_matches_oracle(engine, oracle, oracle_glibc, name, near, n):
     edges = synth.make_edges(world, n, seed=11, near_ribbons=near)
     got, want = _check_batch(engine, oracle, world, edges)
     assert (want["status"] == 0).all()
-    # against the glibc oracle (== reference): flags, word, counts and costs on every edge;
-    # only the end pose / h may differ, on a bounded number of edges, by the 1e-5 m retry
-    world.upload(oracle_glibc)
-    ref = oracle_glibc.true_cost_batch(edges)
-    bad = common.diff_results(got, ref)
-    for name_ in ("true_cost", "collision_penalty", "g", "infeasible", "status", "n_samples", "w_end_time"):
-        assert name_ not in bad, common.describe(bad, got, ref)
-    idx = set()
-    for v in bad.values():
-        idx |= set(v.tolist())
-    assert len(idx) <= max(1, int(GLIBC_EDGE_BUDGET * n * 5)), common.describe(bad, got, ref)
+    _vs_glibc_reference(engine, oracle_glibc, world, edges, got, "%s near=%.1f" % (name, near))
+
+
+# ---- configurations the first round never ran through the CUDA path ("What's weak" #2) ----------------
+@pytest.mark.parametrize("name,near,n", [("c2", 0.5, 3000), ("c3", 0.3, 800), ("c3b", 0.3, 1000)])
+def test_epoch_scale_state_times(engine, oracle, oracle_glibc, name, near, n):
+    """State times ~1.7e9 s, what the ROS node feeds: one binade, ulp(t) = 2.4e-7 s, so `t += dt` (Edge.cpp:173)
+    rounds every step and the sample count / int(ribbonsDoneTime) depend on it."""
+    world = synth.with_time_offset(synth.WORLDS[name](), 1.7e9)
+    edges = synth.make_edges(world, n, seed=12, near_ribbons=near)
+    assert edges["src"][:, 4].min() > 1.6e9
+    got, want = _check_batch(engine, oracle, world, edges)
+    assert (want["status"] == 0).all() and want["ribbons_changed"].sum() > 0
+    _vs_glibc_reference(engine, oracle_glibc, world, edges, got, world.name)
+
+
+@pytest.mark.parametrize("name,res,near,n", [("c2", 0.5, 0.3, 3000), ("c2", 2.5, 0.3, 3000), ("c2", 0.3, 0.3, 2000),
+                                              ("c4", 0.5, 0.3, 1500), ("c4", 2.5, 0.3, 1500), ("c5", 2.5, 0.2, 500)])
+def test_map_resolutions(engine, oracle, oracle_glibc, name, res, near, n):
+    """GridWorldMap::isBlocked divides by the resolution (GridWorldMap.cpp:84-93): 0.5 m is the exact-reciprocal path,
+    2.5 m and 0.3 m the division path; the dilation radius of the chunk-culling safe map depends on it too."""
+    world = synth.with_resolution(synth.WORLDS[name](), res)
+    edges = synth.make_edges(world, n, seed=13, near_ribbons=near)
+    got, want = _check_batch(engine, oracle, world, edges)
+    assert (want["status"] == 0).all()
+    assert (want["infeasible"] == 1).any() and (want["infeasible"] == 0).any()
+    _vs_glibc_reference(engine, oracle_glibc, world, edges, got, world.name)
+
+
+def test_non_default_covariances(engine, oracle, oracle_glibc):
+    """Per-obstacle SPD covariances instead of the manager default (GaussianDynamicObstaclesManager.h:24-25,39-44)."""
+    for base in ("c3", "c5"):
+        world = synth.with_covariances(synth.WORLDS[base]())
+        edges = synth.make_edges(world, 800 if base == "c3" else 500, seed=14, near_ribbons=0.2)
+        got, want = _check_batch(engine, oracle, world, edges)
+        assert (want["collision_penalty"] > 0).any()
+        _vs_glibc_reference(engine, oracle_glibc, world, edges, got, world.name)
+
+
+def test_previous_plan_style_wrappers(engine, oracle, oracle_glibc):
+    """has_path edges as AStarPlanner.cpp:46-59 builds them from a previous plan: wrapper started earlier than the
+    source vertex, end time truncated, and a foreign radius that forces the re-solve of Edge.cpp:78-80
+    (mirrors tests/test_oracle_vs_ref.py::test_oracle_has_path_edges_and_dubins_match_the_reference)."""
+    world = synth.world_c2()
+    n = 3000
+    edges = synth.make_edges(world, n, seed=23, near_ribbons=0.5)
+    cfg = world.cfg
+    q0 = np.column_stack([edges["src"][:, 0], edges["src"][:, 1], _yaw(edges["src"][:, 2])])
+    q1 = np.column_stack([edges["dst"][:, 0], edges["dst"][:, 1], _yaw(edges["dst"][:, 2])])
+    rho = np.where(edges["coverage_allowed"] == 1, cfg.coverage_turning_radius, cfg.turning_radius)
+    world.upload(engine)
+    typ, par, length, err = engine.dubins_batch(q0, q1, rho)
+    edges["has_path"] = 1
+    edges["path_qi"] = q0
+    edges["path_param"] = par
+    edges["path_rho"] = rho
+    edges["path_type"] = typ
+    edges["w_speed"] = edges["dst"][:, 3]
+    edges["w_start_time"] = edges["src"][:, 4]
+    edges["w_end_time"] = edges["src"][:, 4] + length / edges["dst"][:, 3]
+    k = np.arange(n) % 3 == 0
+    edges["w_start_time"][k] -= 0.5
+    edges["w_end_time"][k] = edges["w_start_time"][k] + 0.7 * length[k] / edges["dst"][k, 3]
+    edges["path_rho"][::50] = 11.0
+    got, want = _check_batch(engine, oracle, world, edges)
+    _vs_glibc_reference(engine, oracle_glibc, world, edges, got, "c2 previous-plan wrappers")
 
 
 def test_has_path_edges_match_oracle(engine, oracle):

@@ -43,6 +43,41 @@ def test_oracle_is_bit_identical_to_the_compiled_reference(name, near, n):
     assert (want["infeasible"] == 1).any() or name == "c1"
 
 
+NEW_WORLDS = {
+    "c2-epoch": (lambda: synth.with_time_offset(synth.world_c2(), 1.7e9), 0.5, 1200),
+    "c3-epoch": (lambda: synth.with_time_offset(synth.WORLDS["c3"](), 1.7e9), 0.3, 250),
+    "c3b-epoch": (lambda: synth.with_time_offset(synth.WORLDS["c3b"](), 1.7e9), 0.3, 300),
+    "c2@0.5m": (lambda: synth.with_resolution(synth.world_c2(), 0.5), 0.3, 1200),
+    "c2@2.5m": (lambda: synth.with_resolution(synth.world_c2(), 2.5), 0.3, 1200),
+    "c2@0.3m": (lambda: synth.with_resolution(synth.world_c2(), 0.3), 0.3, 1200),
+    "c4@2.5m": (lambda: synth.with_resolution(synth.world_c4(), 2.5), 0.3, 600),
+    "c3+cov": (lambda: synth.with_covariances(synth.WORLDS["c3"]()), 0.2, 250),
+}
+
+
+@needs_ref
+@pytest.mark.parametrize("key", sorted(NEW_WORLDS))
+def test_oracle_is_bit_identical_on_epoch_times_resolutions_and_covariances(key):
+    """The configurations tests/test_gpu_parity.py adds in round 2 (epoch-scale state times as the ROS node feeds them,
+    map resolutions != 1 m incl. non powers of two, per-obstacle covariances): the oracle is pinned against the
+    compiled reference on them before the GPU is compared with the oracle."""
+    mk, near, n = NEW_WORLDS[key]
+    ref = common.load_ref()
+    ora = common.load_oracle("glibc")
+    world = mk()
+    sid = world.upload_ref(ref)
+    order = common.ref_obstacle_order(ref) if world.obstacle_kind != "none" else None
+    assert world.upload(ora, order) == sid
+    edges = synth.make_edges(world, n, seed=12, near_ribbons=near)
+    edges["ribbon_set"] = sid
+    want = ref.true_cost_batch(edges)
+    got = ora.true_cost_batch(edges)
+    bad = common.diff_results(got, want, exact=True, check_counts=False)
+    assert not bad, common.describe(bad, got, want)
+    assert _ribbon_lists_equal(ora, ref, np.flatnonzero(want["ribbons_changed"])[:200]) is None
+    assert want["ribbons_changed"].sum() > 0 and (want["infeasible"] == 1).any()
+
+
 @needs_ref
 def test_oracle_has_path_edges_and_dubins_match_the_reference():
     """Winner edges of expand() (pre-solved wrapper, speed change) and previous-plan style wrappers

@@ -89,7 +89,7 @@ typedef struct {
     double w_start_time; /* DubinsWrapper m_StartTime      (has_path)                         */
     double w_end_time;   /* DubinsWrapper::getEndTime()    (has_path; may be truncated)       */
     int32_t path_type;   /* PPE_LSL.. (has_path)                                              */
-    int32_t has_path;    /* 0: solve src->dst at the edge's radius first (Edge.cpp:78-80)     */
+    int32_t has_path;    /* 0: solve src->dst at the edge's radius first (Edge.cpp:78-80); < 0: skip */
     int32_t coverage_allowed; /* end()->coverageAllowed()                                     */
     int32_t ribbon_set;  /* id from ppe_put_ribbon_set: start()->ribbonManager()              */
 } ppe_edge;
@@ -99,7 +99,8 @@ enum {
     PPE_EDGE_OK = 0,
     PPE_EDGE_ERR_END_SAMPLE = 1,     /* DubinsWrapper::sample(end state) would throw (DubinsWrapper.cpp:30-35) */
     PPE_EDGE_ERR_NO_PATH = 2,        /* dubins_shortest_path failed (unset wrapper, Edge.cpp:85)                */
-    PPE_EDGE_ERR_RIBBON_CAPACITY = 3 /* ribbon set outgrew the per-edge device capacity                         */
+    PPE_EDGE_ERR_RIBBON_CAPACITY = 3,/* ribbon set outgrew the per-edge device capacity                         */
+    PPE_EDGE_SKIPPED = 4             /* has_path < 0: an empty slot of a frontier batch, not evaluated           */
 };
 
 /* What Edge::computeTrueCost writes into Edge/Vertex members (Edge.cpp:177-203). */
@@ -186,6 +187,68 @@ int ppe_get_ribbons_after(ppe_ctx* ctx, int64_t edge_index, double* xyxy, int ca
 /* *f = +inf and *edge_index = -1 when no feasible edge exists. */
 int ppe_best(ppe_ctx* ctx, double* f, int64_t* edge_index);
 
+/* ---- frontier expansion: SamplingBasedPlanner::expand for MANY vertices in one launch group ----
+ * (SamplingBasedPlanner.cpp:52-151).  The sample set is resident on the device; per vertex the
+ * engine orders the samples by Euclidean distance (:85-94), replays the per-radius k-best heaps over
+ * Dubins lengths solved on the fly (:95-133, std::push_heap / std::pop_heap arrangement included),
+ * emits the <= 4 nearest-endpoint edges (:65-81) and the winners x speeds (:134-149) in the
+ * reference's push order and evaluates their true cost (K2) -- no host round trip in between. */
+
+/* m_Samples.clear() (AStarPlanner.cpp:24) */
+int ppe_clear_samples(ppe_ctx* ctx);
+/* SamplingBasedPlanner::addSamples (SamplingBasedPlanner.cpp:157-164): n generated states in generation
+ * order; the device evaluates Map::isBlocked for each, appends the free ones (order kept) to the resident
+ * sample set and writes keep[i] = 1 / 0 so the caller's m_Samples mirrors it.  Returns the number kept. */
+int64_t ppe_add_samples(ppe_ctx* ctx, int64_t n, const double* x, const double* y, const double* heading, uint8_t* keep);
+int64_t ppe_sample_count(const ppe_ctx* ctx);
+
+/* A vertex of the open list about to be expanded. */
+typedef struct {
+    double state[5];      /* Vertex::state(): x, y, heading, speed, time                          */
+    double g;             /* Vertex::currentCost()                                                */
+    double endpoint[3];   /* Vertex::getNearestPointAsState(): x, y, heading (has_endpoint != 0)  */
+    int32_t ribbon_set;   /* id from ppe_put_ribbon_set: Vertex::ribbonManager()                  */
+    int32_t has_endpoint; /* !done() && distanceTo(endpoint) > increment (:65-68)                 */
+} ppe_vertex;
+
+/* One child edge of an expanded vertex: what computeTrueCost + the k-nearest selection produced.  The
+ * wrapper is (qi = vertex pose as yaw, path_param, rho by coverage_allowed, path_type, speed = end[3],
+ * start time = vertex time, end time = w_end_time). */
+typedef struct {
+    double true_cost, collision_penalty, approx_cost;
+    double end[5];                  /* end()->state() after truncation                          */
+    double g, h;                    /* h = -1 when the heuristic is not evaluated on the device */
+    double coverage_completed_time;
+    double path_param[3];
+    double w_end_time;
+    int64_t ribbons_offset;         /* into the batch's ribbons-after pool; -1 if unchanged     */
+    int32_t sample_index;           /* resident sample the edge leads to; -1 = endpoint edge    */
+    int32_t path_type;
+    int32_t infeasible;
+    int32_t status;                 /* PPE_EDGE_*                                               */
+    int32_t coverage_allowed;
+    int32_t n_ribbons_after;
+    int32_t ribbons_changed;
+    int32_t reserved;
+} ppe_child;
+
+enum {
+    PPE_EXPAND_TIE = 1,      /* two samples at exactly equal distance inside the consumed prefix: their pop order
+                                depends on the std::heap arrangement, the caller must replay this vertex exactly */
+    PPE_EXPAND_OVERFLOW = 2  /* internal candidate capacity exceeded (caller falls back as for a tie) */
+};
+
+/* children per vertex slot: 4 endpoint edges + 2 radii x branching_factor x 2 speeds */
+int ppe_expand_stride(const ppe_ctx* ctx);
+/* Expands n vertices.  Outputs (host): n_children[n]; children[n * stride] (vertex v's children at
+ * v * stride, in push order); flags[n] (PPE_EXPAND_*); n_popped[n] = samples the k-nearest loop consumed.
+ * The ribbons-after of changed children are fetched with ppe_ribbon_pool(). */
+int ppe_expand_batch(ppe_ctx* ctx, int n, const ppe_vertex* vertices, int32_t* n_children, ppe_child* children,
+                     int32_t* flags, int32_t* n_popped);
+/* Host copy (pinned, owned by the context, valid until the next batch) of the ribbons-after pool of the last
+ * ppe_expand_batch: 4 doubles per ribbon; a child's list is [ribbons_offset, ribbons_offset + n_ribbons_after). */
+const double* ppe_ribbon_pool(ppe_ctx* ctx, int64_t* n_ribbons);
+
 /* ---- device-resident variants (inputs already in HBM; `stream` is a cudaStream_t) --------- */
 int ppe_dubins_batch_device(ppe_ctx* ctx, int64_t n, const double* d_q0, const double* d_q1,
                             const double* d_rho, int32_t* d_type, double* d_param, double* d_length,
@@ -208,6 +271,8 @@ uint64_t ppe_map_generation(const ppe_ctx* ctx);
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* number of engine kernels launched on this ctx since creation */
 int64_t ppe_launch_count(const ppe_ctx* ctx);
+/* Dubins solves of ppe_expand_batch that entered a k-best heap, since creation */
+int64_t ppe_expand_solve_count(const ppe_ctx* ctx);
 /* measured FP64 FMA throughput of the device in TFLOP/s (2 flop per DFMA), `ms` of work */
 int ppe_measure_fp64_peak(ppe_ctx* ctx, double* tflops, void* stream);
 

@@ -32,6 +32,15 @@ int oracle_dubins_batch(oracle_ctx* c, int64_t n, const double* q0, const double
 int oracle_true_cost_batch(oracle_ctx* c, int64_t n, const ppe_edge* edges, ppe_edge_result* results);
 int oracle_get_ribbons_after(oracle_ctx* c, int64_t i, double* xyxy, int cap);
 
+int oracle_clear_samples(oracle_ctx* c);
+int64_t oracle_sample_count(oracle_ctx* c);
+int64_t oracle_expand_solve_count(oracle_ctx* c);
+int64_t oracle_add_samples(oracle_ctx* c, int64_t n, const double* x, const double* y, const double* heading, uint8_t* keep);
+int oracle_expand_stride(oracle_ctx* c);
+int oracle_expand_batch(oracle_ctx* c, int n, const ppe_vertex* verts, int32_t* n_children, ppe_child* children, int32_t* flags,
+                        int32_t* n_popped);
+const double* oracle_ribbon_pool(oracle_ctx* c, int64_t* n_ribbons);
+
 #define O(ctx) ((oracle_ctx*)(ctx))
 
 int ppe_abi_version(void) { return PPE_ABI_VERSION; }
@@ -67,3 +76,16 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
     return oracle_true_cost_batch(O(ctx), n, edges, results);
 }
 int ppe_get_ribbons_after(ppe_ctx* ctx, int64_t i, double* xyxy, int cap) { return oracle_get_ribbons_after(O(ctx), i, xyxy, cap); }
+
+/* frontier expansion (oracle/ppe_oracle_expand.c) */
+int ppe_clear_samples(ppe_ctx* ctx) { return oracle_clear_samples(O(ctx)); }
+int64_t ppe_sample_count(const ppe_ctx* ctx) { return oracle_sample_count((oracle_ctx*)ctx); }
+int64_t ppe_expand_solve_count(const ppe_ctx* ctx) { return oracle_expand_solve_count((oracle_ctx*)ctx); }
+int64_t ppe_add_samples(ppe_ctx* ctx, int64_t n, const double* x, const double* y, const double* heading, uint8_t* keep) {
+    return oracle_add_samples(O(ctx), n, x, y, heading, keep);
+}
+int ppe_expand_stride(const ppe_ctx* ctx) { return oracle_expand_stride((oracle_ctx*)ctx); }
+int ppe_expand_batch(ppe_ctx* ctx, int n, const ppe_vertex* v, int32_t* n_children, ppe_child* children, int32_t* flags, int32_t* n_popped) {
+    return oracle_expand_batch(O(ctx), n, v, n_children, children, flags, n_popped);
+}
+const double* ppe_ribbon_pool(ppe_ctx* ctx, int64_t* n) { return oracle_ribbon_pool(O(ctx), n); }

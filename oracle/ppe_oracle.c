@@ -475,6 +475,7 @@ void oracle_destroy(oracle_ctx* c) {
 const char* oracle_last_error(const oracle_ctx* c) { return c->err; }
 
 int oracle_set_config(oracle_ctx* c, const ppe_config* cfg) { c->cfg = *cfg; c->have_cfg = 1; return PPE_OK; }
+const ppe_config* oracle_config(const oracle_ctx* c) { return &c->cfg; }
 
 int oracle_set_map_none(oracle_ctx* c) { c->map_kind = 0; return PPE_OK; }
 

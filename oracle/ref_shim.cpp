@@ -382,6 +382,14 @@ int ref_plan(ref_ctx* ctx, int ribbon_set, const double* start5, double timeRema
                         plan_out, plan_cap, stats10);
 }
 
+int ref_plan2(ref_ctx* ctx, int ribbon_set, const double* start5, double timeRemaining, double clock0, double tick,
+              int initialSamples, int useBrownPaths, const double* prev_plan, int n_prev, double* plan_out, int plan_cap,
+              double* stats10) {
+    AStarPlanner planner;
+    return ref_run_plan(planner, ctx, ribbon_set, start5, timeRemaining, clock0, tick, initialSamples, useBrownPaths,
+                        plan_out, plan_cap, stats10, prev_plan, n_prev);
+}
+
 int ref_expand_once(ref_ctx* ctx, int ribbon_set, int nSamples, int seed, double* f_out, int cap) {
     AStarPlanner planner;
     return ref_run_expand_once(planner, ctx, ribbon_set, nSamples, seed, f_out, cap);

@@ -40,10 +40,12 @@ struct ref_ctx {
 // (12 doubles per Dubins path: qi[3], param[3], rho, type, speed, start, end, 0) and
 // stats10 = Samples, Generated, Expanded, Iterations, PlanFValue, PlanCollisionPenalty,
 // PlanTimePenalty, PlanHValue, PlanDepth, now() calls.  Returns the number of paths or -1.
+// `prev_plan` / `n_prev`: a previous plan in the same 12-double record layout (nullptr / 0 = none): what the
+// Executive passes on every cycle after the first (executive.cpp:146,189), re-validated at AStarPlanner.cpp:46-59.
 template <typename PlannerT>
 int ref_run_plan(PlannerT& planner, ref_ctx* ctx, int ribbon_set, const double* start5, double timeRemaining,
                  double clock0, double tick, int initialSamples, int useBrownPaths, double* plan_out, int plan_cap,
-                 double* stats10) {
+                 double* stats10, const double* prev_plan = nullptr, int n_prev = 0) {
     PlannerConfig config = ctx->config;
     config.setInitialSamples(initialSamples);
     config.setUseBrownPaths(useBrownPaths != 0);
@@ -59,8 +61,20 @@ int ref_run_plan(PlannerT& planner, ref_ctx* ctx, int ribbon_set, const double* 
     }
     State start(start5[0], start5[1], start5[2], start5[3], start5[4]);
     Planner::Stats stats;
+    DubinsPlan previous;
+    for (int i = 0; i < n_prev; i++) {
+        const double* o = prev_plan + 12 * i;
+        DubinsPath p;
+        p.qi[0] = o[0]; p.qi[1] = o[1]; p.qi[2] = o[2];
+        p.param[0] = o[3]; p.param[1] = o[4]; p.param[2] = o[5];
+        p.rho = o[6]; p.type = (DubinsPathType)(int)o[7];
+        DubinsWrapper w;
+        w.fill(p, o[8], o[9]);
+        if (o[10] < w.getEndTime()) w.updateEndTime(o[10]);
+        previous.append(w);
+    }
     try {
-        stats = planner.plan(ctx->sets[ribbon_set], start, config, DubinsPlan(), timeRemaining);
+        stats = planner.plan(ctx->sets[ribbon_set], start, config, previous, timeRemaining);
     } catch (std::exception& ex) {
         ctx->lastError = ex.what();
         return -1;

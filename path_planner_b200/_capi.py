@@ -132,3 +132,36 @@ class CApiWorld:
         if n > cap:
             return self.ribbons_after(edge_index, cap=n)
         return buf[:n].copy()
+
+    # -- frontier expansion (SamplingBasedPlanner::addSamples / ::expand for many vertices) ---------------
+    def clear_samples(self):
+        self._check(self._fn("clear_samples")(self._ctx), "clear_samples")
+
+    def add_samples(self, x, y, heading):
+        """Appends the states the map does not block to the resident sample set; returns the keep mask."""
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, heading)]
+        keep = np.zeros(len(a[0]), dtype=np.uint8)
+        kept = self._fn("add_samples")(self._ctx, len(a[0]), abi.dptr(a[0]), abi.dptr(a[1]), abi.dptr(a[2]), abi.vptr(keep))
+        self._check(int(min(kept, 0)), "add_samples")
+        assert kept == int(keep.sum())
+        return keep.astype(bool)
+
+    def sample_count(self):
+        return int(self._fn("sample_count")(self._ctx))
+
+    def expand_batch(self, vertices):
+        """`abi.VERTEX_DTYPE` records -> (n_children[n], children[n, stride] of `abi.CHILD_DTYPE`, flags[n], n_popped[n],
+        ribbon pool [m, 4])."""
+        vertices = np.ascontiguousarray(vertices, dtype=abi.VERTEX_DTYPE)
+        n = vertices.shape[0]
+        stride = int(self._fn("expand_stride")(self._ctx))
+        nch = np.zeros(n, dtype=np.int32)
+        flags = np.zeros(n, dtype=np.int32)
+        pops = np.zeros(n, dtype=np.int32)
+        children = np.zeros((n, stride), dtype=abi.CHILD_DTYPE)
+        self._check(self._fn("expand_batch")(self._ctx, n, abi.vptr(vertices), abi.iptr(nch), abi.vptr(children), abi.iptr(flags),
+                                             abi.iptr(pops)), "expand_batch")
+        m = C.c_int64()
+        p = self._fn("ribbon_pool")(self._ctx, C.byref(m))
+        pool = np.ctypeslib.as_array(p, shape=(m.value * 4,)).reshape(-1, 4).copy() if m.value > 0 else np.zeros((0, 4))
+        return nch, children, flags, pops, pool

@@ -132,8 +132,42 @@ RESULT_DTYPE = np.dtype(
     align=True,
 )
 
+# ppe_vertex (80 bytes) / ppe_child (160 bytes): frontier expansion
+VERTEX_DTYPE = np.dtype(
+    [("state", "<f8", (5,)), ("g", "<f8"), ("endpoint", "<f8", (3,)), ("ribbon_set", "<i4"), ("has_endpoint", "<i4")],
+    align=True,
+)
+CHILD_DTYPE = np.dtype(
+    [
+        ("true_cost", "<f8"),
+        ("collision_penalty", "<f8"),
+        ("approx_cost", "<f8"),
+        ("end", "<f8", (5,)),
+        ("g", "<f8"),
+        ("h", "<f8"),
+        ("coverage_completed_time", "<f8"),
+        ("path_param", "<f8", (3,)),
+        ("w_end_time", "<f8"),
+        ("ribbons_offset", "<i8"),
+        ("sample_index", "<i4"),
+        ("path_type", "<i4"),
+        ("infeasible", "<i4"),
+        ("status", "<i4"),
+        ("coverage_allowed", "<i4"),
+        ("n_ribbons_after", "<i4"),
+        ("ribbons_changed", "<i4"),
+        ("reserved", "<i4"),
+    ],
+    align=True,
+)
+EXPAND_TIE = 1
+EXPAND_OVERFLOW = 2
+EDGE_SKIPPED = 4
+
 assert EDGE_DTYPE.itemsize == 176, EDGE_DTYPE.itemsize
 assert RESULT_DTYPE.itemsize == 208, RESULT_DTYPE.itemsize
+assert VERTEX_DTYPE.itemsize == 80, VERTEX_DTYPE.itemsize
+assert CHILD_DTYPE.itemsize == 160, CHILD_DTYPE.itemsize
 
 
 def dptr(a):
@@ -183,3 +217,11 @@ def declare_world_api(lib, prefix, ctx_t=C.c_void_p):
     f("dubins_batch", [ctx_t, C.c_int64, D, D, D, I, D, D, I])
     f("true_cost_batch", [ctx_t, C.c_int64, C.c_void_p, C.c_void_p])
     f("get_ribbons_after", [ctx_t, C.c_int64, D, C.c_int])
+    if hasattr(lib, prefix + "expand_batch"):  # the engine and the C oracle; the compiled reference expands through its planner
+        f("clear_samples", [ctx_t])
+        f("add_samples", [ctx_t, C.c_int64, D, D, D, C.c_void_p], C.c_int64)
+        f("sample_count", [ctx_t], C.c_int64)
+        f("expand_stride", [ctx_t])
+        f("expand_batch", [ctx_t, C.c_int, C.c_void_p, I, C.c_void_p, I, I])
+        f("ribbon_pool", [ctx_t, C.POINTER(C.c_int64)], D)
+        f("expand_solve_count", [ctx_t], C.c_int64)

@@ -103,6 +103,28 @@ struct ppe_ctx {
     unsigned long long last_out_count = 0;
     bool have_batch = false;
 
+    // ---- frontier expansion: resident samples + per-batch buffers (ppe_expand.cu) ----
+    double *d_sx = nullptr, *d_sy = nullptr, *d_sh = nullptr; // m_Samples, SoA
+    size_t cap_samples = 0;
+    int64_t n_samples = 0;
+    double* d_stage = nullptr;            // x, y, heading of the states being added
+    uint8_t* d_keep = nullptr;
+    unsigned int* d_blockcnt = nullptr;   // per-block keep counts / offsets + [last] total
+    size_t cap_stage = 0;
+    ppe_vertex* d_verts = nullptr;
+    ppe_edge* d_xedges = nullptr;
+    ppe_edge_result* d_xresults = nullptr;
+    ppe_child* d_children = nullptr;
+    int32_t* d_xints = nullptr;           // [edge_sample: n * stride][n_children n][flags n][n_popped n][n_solved n]
+    size_t cap_verts = 0;
+    void* h_pinned = nullptr;             // pinned staging of one expand batch (inputs and outputs)
+    size_t cap_pinned = 0;
+    double* h_pool = nullptr;             // pinned host copy of the ribbons-after pool of the last expand batch
+    size_t cap_pool = 0;
+    int64_t n_pool = 0;
+    int64_t expand_solves = 0;            // instrumentation: Dubins solves that ended up in a k-best heap
+    bool last_was_expand = false;
+
     int64_t launches = 0;
 };
 
@@ -328,6 +350,11 @@ void ppe_destroy(ppe_ctx* ctx) {
     cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_prepared); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
     cudaFree(ctx->d_work); cudaFree(ctx->d_heavy); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
+    cudaFree(ctx->d_sx); cudaFree(ctx->d_sy); cudaFree(ctx->d_sh); cudaFree(ctx->d_stage); cudaFree(ctx->d_keep);
+    cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_verts); cudaFree(ctx->d_xedges); cudaFree(ctx->d_xresults);
+    cudaFree(ctx->d_children); cudaFree(ctx->d_xints);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_pool) cudaFreeHost(ctx->h_pool);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream_in) cudaStreamDestroy(ctx->stream_in);
     if (ctx->stream_out) cudaStreamDestroy(ctx->stream_out);
@@ -672,6 +699,7 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
     }
     ctx->last_count = n;
     ctx->have_batch = true;
+    ctx->last_was_expand = false;
     ctx->out_downloaded = false;
     return PPE_OK;
 }
@@ -704,6 +732,212 @@ int ppe_best(ppe_ctx* ctx, double* f, int64_t* edge_index) {
     if (!ctx || !ctx->have_batch) return fail(ctx, PPE_ERR_STATE, "ppe_best: no batch has been evaluated");
     return ppe_best_device(ctx, f, edge_index, ctx->stream);
 }
+
+// ---- frontier expansion ------------------------------------------------------------------------------
+int ppe_clear_samples(ppe_ctx* ctx) {
+    if (!ctx) return PPE_ERR_INVALID;
+    ctx->n_samples = 0;
+    return PPE_OK;
+}
+
+int64_t ppe_sample_count(const ppe_ctx* ctx) { return ctx ? ctx->n_samples : 0; }
+
+static int grow_pinned(ppe_ctx* ctx, void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return PPE_OK;
+    size_t c = *cap ? *cap : (1 << 16);
+    while (c < need) c *= 2;
+    if (*p) PPE_CUDA(ctx, cudaFreeHost(*p));
+    *p = nullptr;
+    *cap = 0;
+    PPE_CUDA(ctx, cudaMallocHost(p, c));
+    *cap = c;
+    return PPE_OK;
+}
+
+int64_t ppe_add_samples(ppe_ctx* ctx, int64_t n, const double* x, const double* y, const double* heading, uint8_t* keep) {
+    if (!ctx || n < 0 || (n > 0 && (!x || !y || !heading || !keep))) return fail(ctx, PPE_ERR_INVALID, "ppe_add_samples: bad arguments");
+    if (n == 0) return 0;
+    if (n > ((int64_t)1 << 24)) return fail(ctx, PPE_ERR_CAPACITY, "ppe_add_samples: at most 2^24 states per call");
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    WorldD w;
+    int rc = make_world(ctx, &w);
+    if (rc != PPE_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    const int blocks = (int)((n + 255) / 256);
+    if ((size_t)n > ctx->cap_stage) {
+        size_t c = ctx->cap_stage ? ctx->cap_stage : 4096;
+        while (c < (size_t)n) c *= 2;
+        cudaFree(ctx->d_stage); cudaFree(ctx->d_keep); cudaFree(ctx->d_blockcnt);
+        ctx->d_stage = nullptr; ctx->d_keep = nullptr; ctx->d_blockcnt = nullptr; ctx->cap_stage = 0;
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_stage, 3 * c * sizeof(double)));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_keep, c));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_blockcnt, ((c + 255) / 256 + 1) * sizeof(unsigned int)));
+        ctx->cap_stage = c;
+    }
+    // room for all n: the resident arrays keep what they hold (device-to-device) when they grow
+    {
+        const size_t need = (size_t)ctx->n_samples + (size_t)n;
+        size_t c1 = ctx->cap_samples, c2 = ctx->cap_samples, c3 = ctx->cap_samples;
+        rc = grow_keep(ctx, &ctx->d_sx, &c1, need, (size_t)ctx->n_samples, 1 << 14);
+        if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_sy, &c2, need, (size_t)ctx->n_samples, 1 << 14);
+        if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_sh, &c3, need, (size_t)ctx->n_samples, 1 << 14);
+        if (rc != PPE_OK) return rc;
+        ctx->cap_samples = c1;
+    }
+    double* dx = ctx->d_stage;
+    double* dy = dx + ctx->cap_stage;
+    double* dh = dy + ctx->cap_stage;
+    PPE_CUDA(ctx, cudaMemcpyAsync(dx, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    PPE_CUDA(ctx, cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    PPE_CUDA(ctx, cudaMemcpyAsync(dh, heading, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, st));
+    unsigned int* d_total = ctx->d_blockcnt + blocks;
+    PPE_CUDA(ctx, launch_sample_filter(w, n, dx, dy, dh, ctx->d_keep, ctx->d_blockcnt, d_total, nullptr, nullptr, nullptr, 0, st, 0));
+    PPE_CUDA(ctx, launch_sample_filter(w, n, dx, dy, dh, ctx->d_keep, ctx->d_blockcnt, d_total, ctx->d_sx, ctx->d_sy, ctx->d_sh,
+                                       ctx->n_samples, st, 1));
+    unsigned int total = 0;
+    PPE_CUDA(ctx, cudaMemcpyAsync(keep, ctx->d_keep, (size_t)n, cudaMemcpyDeviceToHost, st));
+    PPE_CUDA(ctx, cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
+    PPE_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->launches += 3;
+    ctx->n_samples += (int64_t)total;
+    return (int64_t)total;
+}
+
+int ppe_expand_stride(const ppe_ctx* ctx) {
+    if (!ctx || !ctx->have_cfg) return 0;
+    return 4 + 4 * ctx->cfg.branching_factor;
+}
+
+int ppe_expand_batch(ppe_ctx* ctx, int n, const ppe_vertex* vertices, int32_t* n_children, ppe_child* children,
+                     int32_t* flags, int32_t* n_popped) {
+    if (!ctx || n < 0 || (n > 0 && (!vertices || !n_children || !children || !flags || !n_popped)))
+        return fail(ctx, PPE_ERR_INVALID, "ppe_expand_batch: bad arguments");
+    if (n == 0) return PPE_OK;
+    PPE_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->have_cfg) return fail(ctx, PPE_ERR_STATE, "ppe_set_config must be called before a batch");
+    const int k = ctx->cfg.branching_factor;
+    if (k < 1 || k > expand_max_branch()) return fail(ctx, PPE_ERR_CAPACITY, "ppe_expand_batch: branching factor outside [1, 16]");
+    WorldD w;
+    int rc = make_world(ctx, &w);
+    if (rc != PPE_OK) return rc;
+    const int stride = ppe_expand_stride(ctx);
+    const size_t slots = (size_t)n * stride;
+    if ((size_t)n > ctx->cap_verts) {
+        size_t c = ctx->cap_verts ? ctx->cap_verts : 64;
+        while (c < (size_t)n) c *= 2;
+        cudaFree(ctx->d_verts); cudaFree(ctx->d_xedges); cudaFree(ctx->d_xresults); cudaFree(ctx->d_children); cudaFree(ctx->d_xints);
+        ctx->d_verts = nullptr; ctx->d_xedges = nullptr; ctx->d_xresults = nullptr; ctx->d_children = nullptr; ctx->d_xints = nullptr;
+        ctx->cap_verts = 0;
+        const size_t cs = c * (size_t)(4 + 4 * expand_max_branch());
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_verts, c * sizeof(ppe_vertex)));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_xedges, cs * sizeof(ppe_edge)));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_xresults, cs * sizeof(ppe_edge_result)));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_children, cs * sizeof(ppe_child)));
+        PPE_CUDA(ctx, cudaMalloc((void**)&ctx->d_xints, (cs + 4 * c) * sizeof(int32_t)));
+        ctx->cap_verts = c;
+    }
+    rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, slots * prepared_edge_bytes());
+    if (rc != PPE_OK) return rc;
+    if (ctx->thread_walker) {
+        rc = grow(ctx, &ctx->d_heavy, &ctx->cap_heavy, slots);
+        if (rc != PPE_OK) return rc;
+    }
+    // pinned staging: [vertices][children][4 int arrays]
+    const size_t bytes_v = (size_t)n * sizeof(ppe_vertex), bytes_c = slots * sizeof(ppe_child), bytes_i = 4 * (size_t)n * sizeof(int32_t);
+    rc = grow_pinned(ctx, &ctx->h_pinned, &ctx->cap_pinned, bytes_v + bytes_c + bytes_i + 64);
+    if (rc != PPE_OK) return rc;
+    char* hp = (char*)ctx->h_pinned;
+    ppe_vertex* h_v = (ppe_vertex*)hp;
+    ppe_child* h_c = (ppe_child*)(hp + bytes_v);
+    int32_t* h_i = (int32_t*)(hp + bytes_v + bytes_c);
+    memcpy(h_v, vertices, bytes_v);
+
+    int32_t* d_edge_sample = ctx->d_xints;
+    int32_t* d_nchild = ctx->d_xints + slots;
+    int32_t* d_flags = d_nchild + n;
+    int32_t* d_pops = d_flags + n;
+    int32_t* d_solved = d_pops + n;
+
+    ExpandParamsD p;
+    memset(&p, 0, sizeof p);
+    p.sx = ctx->d_sx; p.sy = ctx->d_sy; p.sh = ctx->d_sh;
+    p.n_samples = (int)ctx->n_samples;
+    p.k = k;
+    p.stride = stride;
+    p.inc = ctx->cfg.collision_checking_increment;
+    p.max_speed = ctx->cfg.max_speed;
+    p.time_factor = ctx->cfg.time_penalty_factor;
+    p.speed[0] = ctx->cfg.max_speed;
+    p.speed[1] = ctx->cfg.max_speed == ctx->cfg.slow_speed ? -1 : ctx->cfg.slow_speed;
+    p.rho[0] = ctx->cfg.turning_radius;
+    p.rho[1] = ctx->cfg.coverage_turning_radius == ctx->cfg.turning_radius ? -1 : ctx->cfg.coverage_turning_radius;
+    p.coverage_rho = ctx->cfg.coverage_turning_radius;
+    {
+        // first search disc: about 24 k candidates' worth of the sampling square (2 v T)^2 -- AStarPlanner.cpp:26-32;
+        // the kernel widens / shrinks it on its own when the guess is off
+        const double side = 2.0 * ctx->cfg.max_speed * ctx->cfg.time_horizon;
+        const double density = (double)(ctx->n_samples > 0 ? ctx->n_samples : 1) / (side * side);
+        const char* env = getenv("PPE_EXPAND_R2"); // testing only: force the retry paths
+        p.r2_init = env ? atof(env) : (24.0 * k) / (3.141592653589793 * density);
+    }
+    cudaStream_t st = ctx->stream;
+    PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_verts, h_v, bytes_v, cudaMemcpyHostToDevice, st));
+    PPE_CUDA(ctx, launch_expand_select(p, n, ctx->d_verts, ctx->d_xedges, d_edge_sample, d_nchild, d_flags, d_pops, d_solved, st));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        int blocks = 1, launches = 0;
+        PPE_CUDA(ctx, launch_true_cost_kernels(w, (int64_t)slots, ctx->d_xedges, ctx->d_prepared, ctx->d_xresults, ctx->d_work,
+                                               ctx->thread_walker ? ctx->d_heavy : nullptr, ctx->d_block_best, ctx->max_blocks,
+                                               ctx->sm_count, st, true, ctx->tuning, &blocks, &launches));
+        PPE_CUDA(ctx, launch_best_final(ctx->d_block_best, blocks, ctx->d_best, 0, false, st));
+        ctx->launches += launches + 1;
+        PPE_CUDA(ctx, cudaMemcpyAsync(&ctx->last_out_count, ctx->d_out_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (attempt == 0) {
+            PPE_CUDA(ctx, launch_expand_pack((int64_t)slots, ctx->d_xedges, ctx->d_xresults, d_edge_sample, ctx->d_children, st));
+            PPE_CUDA(ctx, cudaMemcpyAsync(h_c, ctx->d_children, bytes_c, cudaMemcpyDeviceToHost, st));
+            PPE_CUDA(ctx, cudaMemcpyAsync(h_i, d_nchild, bytes_i, cudaMemcpyDeviceToHost, st));
+        }
+        PPE_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->last_out_count <= ctx->out_cap) {
+            if (attempt == 1) { // the pool had to grow: pack again from the second evaluation
+                PPE_CUDA(ctx, launch_expand_pack((int64_t)slots, ctx->d_xedges, ctx->d_xresults, d_edge_sample, ctx->d_children, st));
+                PPE_CUDA(ctx, cudaMemcpyAsync(h_c, ctx->d_children, bytes_c, cudaMemcpyDeviceToHost, st));
+                PPE_CUDA(ctx, cudaStreamSynchronize(st));
+            }
+            break;
+        }
+        rc = ensure_pool(ctx, (size_t)(ctx->last_out_count + ctx->last_out_count / 4 + 1024));
+        if (rc != PPE_OK) return rc;
+        rc = make_world(ctx, &w);
+        if (rc != PPE_OK) return rc;
+    }
+    ctx->launches += 2;
+    // the ribbons-after pool: one copy for the whole batch
+    ctx->n_pool = (int64_t)ctx->last_out_count;
+    if (ctx->n_pool > 0) {
+        void* pp = ctx->h_pool;
+        rc = grow_pinned(ctx, &pp, &ctx->cap_pool, (size_t)ctx->n_pool * sizeof(double4));
+        ctx->h_pool = (double*)pp;
+        if (rc != PPE_OK) return rc;
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->h_pool, ctx->d_out_ribbons, (size_t)ctx->n_pool * sizeof(double4), cudaMemcpyDeviceToHost, st));
+        PPE_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    memcpy(children, h_c, bytes_c);
+    memcpy(n_children, h_i, (size_t)n * sizeof(int32_t));
+    memcpy(flags, h_i + n, (size_t)n * sizeof(int32_t));
+    memcpy(n_popped, h_i + 2 * (size_t)n, (size_t)n * sizeof(int32_t));
+    for (int v = 0; v < n; v++) ctx->expand_solves += h_i[3 * (size_t)n + v];
+    ctx->have_batch = false; // ppe_get_ribbons_after refers to ppe_true_cost_batch only
+    ctx->last_was_expand = true;
+    return PPE_OK;
+}
+
+const double* ppe_ribbon_pool(ppe_ctx* ctx, int64_t* n_ribbons) {
+    if (!ctx || !ctx->last_was_expand) { if (n_ribbons) *n_ribbons = 0; return nullptr; }
+    if (n_ribbons) *n_ribbons = ctx->n_pool;
+    return ctx->h_pool;
+}
+
+int64_t ppe_expand_solve_count(const ppe_ctx* ctx) { return ctx ? ctx->expand_solves : 0; }
 
 int64_t ppe_launch_count(const ppe_ctx* ctx) { return ctx ? ctx->launches : 0; }
 uint64_t ppe_map_generation(const ppe_ctx* ctx) { return ctx ? ctx->map_generation : 0; }

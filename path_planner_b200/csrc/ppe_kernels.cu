@@ -22,6 +22,7 @@
 
 #include "ppe_kernels.cuh"
 #include "ppe_math.cuh"
+#include "ppe_device.cuh"
 
 namespace ppe {
 
@@ -89,39 +90,6 @@ __device__ __forceinline__ bool coords_tame(const RibbonD& r) {
 
 __device__ __forceinline__ double4 pack_ribbon(double sx, double sy, double ex, double ey) {
     return make_double4(sx, sy, ex, ey);
-}
-
-// Map::isBlocked (Map.cpp:4-6) / GridWorldMap::isBlocked (GridWorldMap.cpp:84-93).  The bitmap
-// (<= 2 MiB at 4096^2) stays L2/L1 resident; consecutive lanes are consecutive 0.05 m samples, so
-// a warp's 32 lookups fall into one or two 32-byte sectors.  x / res is a multiplication by the
-// exact reciprocal when the resolution is a power of two (bit-identical quotient), else a division.
-__device__ __forceinline__ bool map_cell(const WorldD& w, double x, double y, unsigned long long* r, unsigned long long* c) {
-    double qx, qy;
-    if (w.res_pow2) { qx = x * w.inv_resolution; qy = y * w.inv_resolution; }
-    else { qx = x / w.resolution; qy = y / w.resolution; }
-    if (x < 0 || qx >= (double)w.cols) return false;
-    if (y < 0 || qy >= (double)w.rows) return false;
-    *r = (unsigned long long)qy;
-    *c = (unsigned long long)qx;
-    return true;
-}
-
-__device__ __forceinline__ bool map_blocked(const WorldD& w, double x, double y) {
-    if (w.map_kind == kMapNone) return false;
-    unsigned long long r, c;
-    if (!map_cell(w, x, y, &r, &c)) return true; // out of bounds = blocked
-    const uint32_t word = __ldg(&w.map_bits[r * (unsigned long long)w.stride_words + (c >> 5)]);
-    return (word >> (c & 31)) & 1u;
-}
-
-// Chunk culling: true when every cell within the dilation radius of (x, y)'s cell is in bounds and free.
-__device__ __forceinline__ bool map_safe(const WorldD& w, double x, double y) {
-    if (w.map_kind == kMapNone) return true;
-    if (w.safe_bits == nullptr) return false;
-    unsigned long long r, c;
-    if (!map_cell(w, x, y, &r, &c)) return false;
-    const uint32_t word = __ldg(&w.safe_bits[r * (unsigned long long)w.stride_words + (c >> 5)]);
-    return (word >> (c & 31)) & 1u;
 }
 
 // BinaryDynamicObstaclesManager::collisionExists (Binary...cpp:4-22) and
@@ -362,7 +330,8 @@ __device__ void prepare_edge(const ppe_config& cfg, double dt, double horizon_en
                              PreparedEdge* __restrict__ out) {
     const double src_x = edge->src[0], src_y = edge->src[1], src_h = edge->src[2], src_speed = edge->src[3],
                  src_t = edge->src[4];
-    const bool has_path = edge->has_path != 0;
+    const bool has_path = edge->has_path > 0;
+    const bool skip = edge->has_path < 0; // empty slot of a frontier batch
     const bool cov = edge->coverage_allowed != 0;
 
     DubinsPathD path;
@@ -375,10 +344,13 @@ __device__ void prepare_edge(const ppe_config& cfg, double dt, double horizon_en
     bool w_init = false;
     double ex, ey, eh, es; // end()->state() pose
     double approx = -1;
-    int status = PPE_EDGE_OK;
+    int status = skip ? PPE_EDGE_SKIPPED : PPE_EDGE_OK;
     bool sample_fault = false; // both dubins_path_sample attempts failed (stale-pose case)
 
-    if (has_path) {
+    if (skip) {
+        ex = ey = eh = es = 0;
+        approx = 0;
+    } else if (has_path) {
         path.qi[0] = edge->path_qi[0]; path.qi[1] = edge->path_qi[1]; path.qi[2] = edge->path_qi[2];
         path.param[0] = edge->path_param[0]; path.param[1] = edge->path_param[1]; path.param[2] = edge->path_param[2];
         path.rho = edge->path_rho; path.type = edge->path_type;
@@ -1157,6 +1129,13 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width, inc = cfg.collision_checking_increment, dt = w.dt;
 
+    if (pe[kStatus] == (double)PPE_EDGE_SKIPPED) { // empty slot of a frontier batch: nothing to evaluate
+        ppe_edge_result* r = results + ei;
+        memset(r, 0, sizeof *r);
+        r->ribbons_offset = -1;
+        r->status = PPE_EDGE_SKIPPED;
+        return;
+    }
     // ---- is this edge simple at all? -------------------------------------------------------------------------------
     const int set = edge->ribbon_set;
     bool heavy = !(set >= 0 && set < w.n_sets) || pe[kStatus] != 0.0 || pe[kSampleFault] != 0.0 || prep->n_runs <= 0;

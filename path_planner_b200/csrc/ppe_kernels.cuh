@@ -72,6 +72,32 @@ K2Tuning clamp_tuning(K2Tuning t);
 // heuristics other than MaxDistance that the kernels evaluate themselves (h >= 0 in the result records)
 inline bool tsp_on_device(int heuristic) { (void)heuristic; return false; }
 
+// ---- frontier expansion (ppe_expand.cu) ------------------------------------------------------------------------------
+struct ExpandParamsD {
+    const double* sx;      // resident samples, SoA
+    const double* sy;
+    const double* sh;
+    int n_samples;
+    int k;                 // PlannerConfig::branchingFactor()
+    int stride;            // child slots per vertex: 4 + 4 k
+    double inc;            // collisionCheckingIncrement
+    double max_speed;
+    double time_factor;    // Edge::timePenaltyFactor()
+    double speed[2];       // {max, slow or -1}                       (SamplingBasedPlanner.cpp:58-59)
+    double rho[2];         // {turning, coverage or -1}               (:61-63)
+    double coverage_rho;
+    double r2_init;        // first search radius (squared) of the candidate collection
+};
+int expand_max_branch();
+cudaError_t launch_sample_filter(const WorldD& w, int64_t n, const double* x, const double* y, const double* h, uint8_t* keep,
+                                 unsigned int* block_count, unsigned int* total, double* sx, double* sy, double* sh, int64_t base,
+                                 cudaStream_t stream, int phase);
+cudaError_t launch_expand_select(const ExpandParamsD& p, int n_vertices, const ppe_vertex* verts, ppe_edge* edges,
+                                 int32_t* edge_sample, int32_t* n_children, int32_t* flags, int32_t* n_popped, int32_t* n_solved,
+                                 cudaStream_t stream);
+cudaError_t launch_expand_pack(int64_t n, const ppe_edge* edges, const ppe_edge_result* results, const int32_t* edge_sample,
+                               ppe_child* out, cudaStream_t stream);
+
 // launchers (ppe_kernels.cu)
 cudaError_t launch_dubins_batch(int64_t n, const double* q0, const double* q1, const double* rho, int32_t* type,
                                 double* param, double* length, int32_t* err, cudaStream_t stream);

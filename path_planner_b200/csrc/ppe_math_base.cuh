@@ -7,7 +7,7 @@
 
 #if defined(__CUDACC__)
 #define PPE_HD __host__ __device__ __forceinline__
-#define PPE_HD_NOINLINE __host__ __device__ __noinline__
+#define PPE_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define PPE_HD inline
 #define PPE_HD_NOINLINE inline

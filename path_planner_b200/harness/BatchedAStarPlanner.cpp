@@ -1,11 +1,13 @@
-// BatchedAStarPlanner.cpp -- see the header.  Host-side restructuring of
-// SamplingBasedPlanner::expand (SamplingBasedPlanner.cpp:52-151): the three per-edge call sites
-//   :76   computeTrueCost for the nearest-ribbon-endpoint edges
-//   :119  computeApproxCost (Dubins solve) for the k-nearest candidates
-//   :145  computeTrueCost for every winner x speed
-// become one K1 launch per chunk of candidates and ONE K2 launch per expansion, while the heap
-// operations, the candidate tests and the pushVertexQueue order are replayed exactly as the
-// reference performs them, so the open list evolves identically.
+// BatchedAStarPlanner.cpp -- see the header.  Host side of the restructured planner:
+//   * expandFrontier / speculate: SamplingBasedPlanner::expand (SamplingBasedPlanner.cpp:52-151) for the popped vertex
+//     AND the best vertices of the open list in one ppe_expand_batch call; children cached per vertex and handed to
+//     pushVertexQueue in the reference's order when the reference's aStar loop pops that vertex.
+//   * expandExact: the same expansion with the k-nearest heaps replayed on the host (K1 per chunk of candidates, one K2
+//     launch per vertex) -- the path taken when two samples lie at exactly equal distance, where the pop order depends
+//     on the arrangement std::make_heap / std::pop_heap leave in m_Samples.
+//   * plan: AStarPlanner::plan (AStarPlanner.cpp:12-132) with the same control flow and now() sequence; previous-plan
+//     re-validation (:46-59), Brown-path expansion (:150-162) and addSamples (SamplingBasedPlanner.cpp:157-164) call the
+//     engine instead of Edge::computeTrueCost / Map::isBlocked.
 #include "BatchedAStarPlanner.h"
 #include "KeyedHeap.h"
 
@@ -48,6 +50,7 @@ PPE_ACCESS(VertexH, Vertex, double, m_ApproxToGo)
 PPE_ACCESS(RibbonList, RibbonManager, std::list<Ribbon>, m_Ribbons)
 PPE_ACCESS(RibbonHeuristic, RibbonManager, RibbonManager::Heuristic, m_Heuristic)
 PPE_ACCESS(RibbonCct, RibbonManager, double, m_CoverageCompletedTime)
+PPE_ACCESS(OpenList, SamplingBasedPlanner, std::vector<std::shared_ptr<Vertex>>, m_VertexQueue)
 #undef PPE_ACCESS
 
 int heuristicId(RibbonManager::Heuristic h) {
@@ -87,6 +90,7 @@ void BatchedAStarPlanner::uploadWorld(const RibbonManager& ribbonManager, const 
     RibbonManager::Heuristic h = ribbonManager.*get(RibbonHeuristic());
     if (ribbonManager.get().size() > 5) h = RibbonManager::MaxDistance;
     m_Heuristic = heuristicId(h);
+    m_HOnDevice = m_Heuristic == PPE_H_MAX_DISTANCE;
     c.heuristic = m_Heuristic;
     check(ppe_set_config(m_Ctx, &c), "ppe_set_config");
 
@@ -149,17 +153,451 @@ void BatchedAStarPlanner::uploadWorld(const RibbonManager& ribbonManager, const 
     check(ppe_clear_ribbon_sets(m_Ctx), "ppe_clear_ribbon_sets");
 }
 
+void BatchedAStarPlanner::prepareWorld(const RibbonManager& ribbonManager, const State& start, const PlannerConfig& config) {
+    uploadWorld(ribbonManager, start, config);
+    m_Perm.clear();
+    m_SampleXY.clear();
+    m_Log.clear();
+    m_LogApplied = 0;
+    m_Expansions.clear();
+    check(ppe_clear_samples(m_Ctx), "ppe_clear_samples");
+}
+
+// SamplingBasedPlanner::addSamples (SamplingBasedPlanner.cpp:157-164): the generator is the reference's own (the
+// sample sequence must be the reference's); Map::isBlocked runs on the device for the whole batch and the free
+// states are appended to the resident sample set in the same order as to m_Samples.
+void BatchedAStarPlanner::addSamplesResident(StateGenerator& generator, int n) {
+    m_AttemptedSamples += n;
+    if (n <= 0) return;
+    std::vector<State>& gen = m_Scratch;
+    gen.clear();
+    m_GenX.resize(n); m_GenY.resize(n); m_GenH.resize(n); m_Keep.resize(n);
+    for (int i = 0; i < n; i++) {
+        gen.push_back(generator.generate());
+        m_GenX[i] = gen.back().x(); m_GenY[i] = gen.back().y(); m_GenH[i] = gen.back().heading();
+    }
+    // the resident set must mirror m_Samples before anything is appended to either
+    if ((size_t)ppe_sample_count(m_Ctx) != m_Samples.size()) {
+        check(ppe_clear_samples(m_Ctx), "ppe_clear_samples");
+        m_Samples.clear();
+    }
+    const int64_t kept = ppe_add_samples(m_Ctx, n, m_GenX.data(), m_GenY.data(), m_GenH.data(), m_Keep.data());
+    check((int)std::min<int64_t>(kept, 0), "ppe_add_samples");
+    for (int i = 0; i < n; i++)
+        if (m_Keep[i]) m_Samples.push_back(gen[i]);
+    m_Batches++;
+}
+
+int32_t BatchedAStarPlanner::internRibbons(const RibbonManager& ribbons) {
+    m_RibbonBuf.clear();
+    for (const auto& r : ribbons.get()) {
+        m_RibbonBuf.push_back(r.start().first); m_RibbonBuf.push_back(r.start().second);
+        m_RibbonBuf.push_back(r.end().first); m_RibbonBuf.push_back(r.end().second);
+    }
+    int32_t setId = -1;
+    check(ppe_put_ribbon_set(m_Ctx, (int)(m_RibbonBuf.size() / 4), m_RibbonBuf.data(), ribbons.coverageCompletedTime(), &setId),
+          "ppe_put_ribbon_set");
+    return setId;
+}
+
+// Edge members written by computeTrueCost (Edge.cpp:177-199), Vertex members (Vertex.cpp:102-104, :49-64) and the
+// child's ribbon manager, from one engine result.
+void BatchedAStarPlanner::fillChild(const std::shared_ptr<Vertex>& v, const double qi[3], const double param[3], double rho, int type,
+                                    double wSpeed, double wStart, double wEnd, bool infeasible, double approx, double trueCost,
+                                    double penalty, double g, double h, double cct, bool ribbonsChanged, const double* ribbons,
+                                    int nRibbons) {
+    Edge& edge = *v->parentEdge();
+    DubinsPath p;
+    p.qi[0] = qi[0]; p.qi[1] = qi[1]; p.qi[2] = qi[2];
+    p.param[0] = param[0]; p.param[1] = param[1]; p.param[2] = param[2];
+    p.rho = rho; p.type = (DubinsPathType)type;
+    DubinsWrapper w;
+    w.fill(p, wSpeed, wStart);
+    if (wEnd < w.getEndTime()) w.updateEndTime(wEnd);
+    edge.*get(EdgeWrapper()) = w;
+    edge.*get(EdgeInfeasible()) = infeasible;
+    edge.*get(EdgeApprox()) = approx;
+    edge.*get(EdgeTrue()) = trueCost;
+    edge.*get(EdgePenalty()) = penalty;
+    (*v).*get(VertexG()) = g;
+    RibbonManager& rm = v->ribbonManager();
+    if (ribbonsChanged) {
+        std::list<Ribbon>& list = rm.*get(RibbonList());
+        list.clear();
+        for (int k2 = 0; k2 < nRibbons; k2++) list.emplace_back(ribbons[4 * k2], ribbons[4 * k2 + 1], ribbons[4 * k2 + 2], ribbons[4 * k2 + 3]);
+    }
+    rm.*get(RibbonCct()) = cct;
+    if (m_HOnDevice) (*v).*get(VertexH()) = h;
+    else v->computeApproxToGo(m_Config); // heuristics the engine does not evaluate stay on the host (RibbonManager.cpp:53-140)
+    if (m_Config.visualizations()) dumpTrajectory(v);
+}
+
+// The "Trajectory:" block Edge::computeTrueCost writes for every evaluated edge when visualizations are on
+// (Edge.cpp:122-143): one State line per int(1 / increment) + 1 sample points, f / g / h as the reference prints them
+// (g so far = parent g + time so far; the running collision penalty is only known for the whole edge and is left out).
+void BatchedAStarPlanner::dumpTrajectory(const std::shared_ptr<Vertex>& v) {
+    std::ostream& os = m_Config.visualizationStream();
+    os << "Trajectory:" << std::endl;
+    Edge& edge = *v->parentEdge();
+    const DubinsWrapper& w = edge.*get(EdgeWrapper());
+    const auto parent = v->parent();
+    const double startG = parent->currentCost(), startH = parent->approxToGo();
+    const double dt = m_Config.collisionCheckingIncrement() / m_Config.maxSpeed();
+    State s = parent->state();
+    s.time() += fmod(s.time() - m_Config.startStateTime(), dt);
+    int visCount = 0;
+    const double endTime = v->state().time();
+    while (s.time() < endTime) {
+        try { w.sample(s); } catch (std::runtime_error&) { break; }
+        if (visCount-- <= 0) {
+            visCount = int(1.0 / m_Config.collisionCheckingIncrement());
+            const double gSoFar = startG + (s.time() - parent->state().time());
+            os << "State: (" << s.toStringRad() << "), f: " << gSoFar + startH << ", g: " << gSoFar << ", h: " << startH << " trajectory" << std::endl;
+        }
+        s.time() += dt;
+    }
+}
+
+// AStarPlanner.cpp:46-59: the previous plan, wrapper by wrapper, each one an edge from the end of the one before
+// (its ribbons-after and g feed the next), evaluated by the engine as has_path edges.
+Vertex::SharedPtr BatchedAStarPlanner::revalidatePreviousPlan(const Vertex::SharedPtr& startV, const DubinsPlan& previousPlan, bool visualize) {
+    Vertex::SharedPtr lastPlanEnd = startV;
+    if (previousPlan.empty()) return lastPlanEnd;
+    for (const auto& p : previousPlan.get()) {
+        if (p.getEndTime() <= startV->state().time()) continue;
+        if (p.getNetTime() == 0) continue;
+        const bool cov = p.getRho() == m_Config.coverageTurningRadius();
+        const State& src = lastPlanEnd->state();
+        ppe_edge e;
+        std::memset(&e, 0, sizeof e);
+        e.src[0] = src.x(); e.src[1] = src.y(); e.src[2] = src.heading(); e.src[3] = src.speed(); e.src[4] = src.time();
+        e.src_g = lastPlanEnd->currentCost();
+        e.ribbon_set = internRibbons(lastPlanEnd->ribbonManager());
+        const DubinsPath& path = p.unwrap();
+        e.has_path = 1;
+        e.path_qi[0] = path.qi[0]; e.path_qi[1] = path.qi[1]; e.path_qi[2] = path.qi[2];
+        e.path_param[0] = path.param[0]; e.path_param[1] = path.param[1]; e.path_param[2] = path.param[2];
+        e.path_rho = path.rho;
+        e.path_type = (int32_t)path.type;
+        e.w_speed = p.getSpeed();
+        e.w_start_time = p.getStartTime();
+        e.w_end_time = p.getEndTime();
+        e.dst[3] = p.getSpeed();
+        e.coverage_allowed = cov;
+        ppe_edge_result r;
+        check(ppe_true_cost_batch(m_Ctx, 1, &e, &r), "ppe_true_cost_batch");
+        m_TrueCostEdges++;
+        m_Batches++;
+        if (r.status != PPE_EDGE_OK)
+            throw std::runtime_error("previous-plan edge failed where the reference throws (status " + std::to_string(r.status) + ")");
+        lastPlanEnd = Vertex::connect(lastPlanEnd, p, cov); // Edge::setEnd(wrapper), Edge.cpp:208-215
+        lastPlanEnd->state() = State(r.end[0], r.end[1], r.end[2], r.end[3], r.end[4]);
+        if (r.ribbons_changed) {
+            m_RibbonBuf.resize((size_t)std::max(1, r.n_ribbons_after) * 4);
+            check(ppe_get_ribbons_after(m_Ctx, 0, m_RibbonBuf.data(), r.n_ribbons_after), "ppe_get_ribbons_after");
+        }
+        fillChild(lastPlanEnd, r.path_qi, r.path_param, r.path_rho, r.path_type, r.w_speed, r.w_start_time, r.w_end_time,
+                  r.infeasible != 0, r.approx_cost, r.true_cost, r.collision_penalty, r.g, r.h, r.coverage_completed_time,
+                  r.ribbons_changed != 0, m_RibbonBuf.data(), r.n_ribbons_after);
+        if (visualize) { // AStarPlanner.cpp:78-79
+            lastPlanEnd->computeApproxToGo(m_Config);
+            visualizeVertex(lastPlanEnd, "lastPlanEnd", false);
+        }
+        if (lastPlanEnd->parentEdge()->infeasible()) {
+            lastPlanEnd = startV;
+            break;
+        }
+        if (goalCondition(lastPlanEnd)) break;
+    }
+    return lastPlanEnd;
+}
+
+// AStarPlanner::expandToCoverSpecificSamples (AStarPlanner.cpp:150-162): the Brown-path states, both speeds, coverage
+// radius -- one engine batch per call.
+void BatchedAStarPlanner::expandSpecific(const Vertex::SharedPtr& root, const std::vector<State>& samples, bool coverageAllowed) {
+    if (!(m_Config.coverageTurningRadius() > 0) || samples.empty()) return;
+    const State& src = root->state();
+    const int32_t setId = internRibbons(root->ribbonManager());
+    m_Edges.clear();
+    for (auto s : samples) {
+        for (const auto& speed : {m_Config.maxSpeed(), m_Config.slowSpeed()}) {
+            ppe_edge e;
+            std::memset(&e, 0, sizeof e);
+            e.src[0] = src.x(); e.src[1] = src.y(); e.src[2] = src.heading(); e.src[3] = src.speed(); e.src[4] = src.time();
+            e.src_g = root->currentCost();
+            e.ribbon_set = setId;
+            e.dst[0] = s.x(); e.dst[1] = s.y(); e.dst[2] = s.heading(); e.dst[3] = speed;
+            e.has_path = 0;
+            e.coverage_allowed = coverageAllowed; // radius of the edge follows from it (Edge.cpp:73-77)
+            m_Edges.push_back(e);
+        }
+    }
+    m_Results.resize(m_Edges.size());
+    check(ppe_true_cost_batch(m_Ctx, (int64_t)m_Edges.size(), m_Edges.data(), m_Results.data()), "ppe_true_cost_batch");
+    m_TrueCostEdges += (long)m_Edges.size();
+    m_Batches++;
+    for (size_t i = 0; i < m_Edges.size(); i++) {
+        const ppe_edge& e = m_Edges[i];
+        const ppe_edge_result& r = m_Results[i];
+        if (r.status != PPE_EDGE_OK)
+            throw std::runtime_error("edge evaluation failed where the reference throws (status " + std::to_string(r.status) + ")");
+        State end(r.end[0], r.end[1], r.end[2], r.end[3], r.end[4]);
+        auto v = Vertex::connect(root, end, m_Config.coverageTurningRadius(), coverageAllowed);
+        if (r.ribbons_changed) {
+            m_RibbonBuf.resize((size_t)std::max(1, r.n_ribbons_after) * 4);
+            check(ppe_get_ribbons_after(m_Ctx, (int64_t)i, m_RibbonBuf.data(), r.n_ribbons_after), "ppe_get_ribbons_after");
+        }
+        fillChild(v, r.path_qi, r.path_param, r.path_rho, r.path_type, r.w_speed, r.w_start_time, r.w_end_time, r.infeasible != 0,
+                  r.approx_cost, r.true_cost, r.collision_penalty, r.g, r.h, r.coverage_completed_time, r.ribbons_changed != 0,
+                  m_RibbonBuf.data(), r.n_ribbons_after);
+        pushVertexQueue(v);
+        (void)e;
+    }
+}
+
+// AStarPlanner::plan (AStarPlanner.cpp:12-132), statement for statement where the order is observable (every now()
+// call, every push into the open list, the sample generator's draw sequence), with the engine behind the three places
+// that evaluate edges or test samples.
 Planner::Stats BatchedAStarPlanner::plan(const RibbonManager& ribbonManager, const State& start, PlannerConfig config,
                                          const DubinsPlan& previousPlan, double timeRemaining) {
-    uploadWorld(ribbonManager, start, config);
-    m_TrueCostEdges = m_DubinsSolves = m_Batches = 0;
-    m_Perm.clear(); // AStarPlanner::plan starts from an empty sample set (AStarPlanner.cpp:24)
-    m_SampleXY.clear();
-    return AStarPlanner::plan(ribbonManager, start, std::move(config), previousPlan, timeRemaining);
+    m_TrueCostEdges = m_DubinsSolves = m_Batches = m_FrontierVertices = m_FrontierHits = m_ExactExpansions = 0;
+    m_Config = std::move(config); // before the first now(), :14
+    const double endTime = timeRemaining + now();
+    m_Config.setStartStateTime(start.time());
+    prepareWorld(ribbonManager, start, m_Config);
+    m_RibbonManager = ribbonManager;
+    m_RibbonManager.changeHeuristicIfTooManyRibbons();
+    if (m_RibbonManager.done()) m_RibbonManager.setCoverageCompletedTime(start.time());
+    m_Stats = Stats();
+    m_IterationCount = 0;
+    m_StartStateTime = start.time();
+    m_Samples.clear();
+    m_AttemptedSamples = 0;
+    const double minSpeed = m_Config.maxSpeed(), maxSpeed = m_Config.maxSpeed();
+    const double magnitude = m_Config.maxSpeed() * m_Config.timeHorizon();
+    const double* mapExtremes = m_Config.map()->extremes();
+    const double minX = fmax(start.x() - magnitude, mapExtremes[0]);
+    const double maxX = fmin(start.x() + magnitude, mapExtremes[1]);
+    const double minY = fmax(start.y() - magnitude, mapExtremes[2]);
+    const double maxY = fmin(start.y() + magnitude, mapExtremes[3]);
+    const auto seed = (unsigned long)endTime; // :33
+    StateGenerator generator(minX, maxX, minY, maxY, minSpeed, maxSpeed, seed, m_RibbonManager);
+    auto startV = Vertex::makeRoot(start, m_RibbonManager);
+    startV->state().speed() = m_Config.maxSpeed();
+    startV->computeApproxToGo(m_Config);
+    m_BestVertex = nullptr;
+    std::vector<State> brownPathSamples;
+    if (m_Config.useBrownPaths()) brownPathSamples = m_RibbonManager.findNearStatesOnRibbons(start, m_Config.coverageTurningRadius());
+
+    Vertex::SharedPtr lastPlanEnd = revalidatePreviousPlan(startV, previousPlan, false); // :46-59
+
+    while (now() < endTime) { // :61
+        clearVertexQueue();
+        // cached frontier results refer to vertices of the search tree that is being thrown away; their ribbon sets go too
+        m_Expansions.clear();
+        check(ppe_clear_ribbon_sets(m_Ctx), "ppe_clear_ribbon_sets");
+        if (m_BestVertex && m_BestVertex->f() <= startV->f()) {
+            *m_Config.output() << "Found best possible plan, assuming heuristic admissibility" << std::endl;
+            break;
+        }
+        visualizeVertex(startV, "start", false);
+        if (m_Config.visualizations()) {
+            lastPlanEnd = revalidatePreviousPlan(startV, previousPlan, true); // :69-86
+            m_Config.visualizationStream() << "Incumbent f-value: " << (m_BestVertex ? m_BestVertex->f() : 0) << std::endl;
+            m_Config.visualizationStream() << m_RibbonManager.dumpRibbons() << "End Ribbons" << std::endl;
+        }
+        pushVertexQueue(startV);
+        if (lastPlanEnd != startV) pushVertexQueue(lastPlanEnd);
+        expandSpecific(startV, brownPathSamples, true); // :99
+        if (m_Samples.size() < (size_t)m_Config.initialSamples()) addSamplesResident(generator, m_Config.initialSamples());
+        else addSamplesResident(generator, (int)m_Samples.size()); // double the samples, :101-102
+        if (m_Config.visualizations()) {
+            for (const auto& s : m_Samples)
+                m_Config.visualizationStream() << "State: (" << s.toStringRad() << "), f: " << 0 << ", g: " << 0 << ", h: " << 0
+                                               << " sample" << std::endl;
+        }
+        auto v = aStar(m_Config.obstaclesManager(), endTime); // the reference's own loop; it calls our expand()
+        if (!m_BestVertex || (v && v->f() + 0.0 < m_BestVertex->f())) {
+            m_BestVertex = v;
+            if (v && m_Config.visualizations()) {
+                visualizePlan(tracePlan(v, false, m_Config.obstaclesManager()));
+                visualizeVertex(v, "goal", false);
+            }
+        }
+        m_Stats.Iterations++;
+    }
+    m_Expansions.clear();
+    m_Stats.Samples = m_Samples.size();
+    if (!m_BestVertex) {
+        *m_Config.output() << "Failed to find a plan" << std::endl;
+    } else {
+        m_Stats.PlanFValue = m_BestVertex->f();
+        m_Stats.PlanDepth = m_BestVertex->getDepth();
+        m_Stats.PlanTimePenalty = (m_BestVertex->state().time() - m_StartStateTime) * Edge::timePenaltyFactor();
+        m_Stats.PlanHValue = m_BestVertex->approxToGo();
+        m_Stats.Plan = std::move(tracePlan(m_BestVertex, false, m_Config.obstaclesManager()));
+    }
+    return m_Stats;
 }
 
 void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, const DynamicObstaclesManager& obstacles) {
     (void)obstacles;
+    if (m_Frontier <= 0 || m_Config.branchingFactor() > 16 || m_Config.branchingFactor() < 1) expandExact(sourceVertex);
+    else expandFrontier(sourceVertex);
+}
+
+// Applies the logged device expansions to the (m_Keys, m_Perm) arrangement: what std::make_heap and the pop_heap calls
+// of each of those expansions would have left in the reference's m_Samples.
+void BatchedAStarPlanner::syncSampleHeap() {
+    if (m_Perm.size() > m_Samples.size()) { m_Perm.clear(); m_SampleXY.clear(); }
+    for (; m_LogApplied < m_Log.size(); m_LogApplied++) {
+        const ExpansionLog& e = m_Log[m_LogApplied];
+        const size_t nAll = e.nSamples;
+        for (size_t i = m_Perm.size(); i < nAll; i++) {
+            m_Perm.push_back((uint32_t)i);
+            m_SampleXY.push_back(m_Samples[i].x());
+            m_SampleXY.push_back(m_Samples[i].y());
+        }
+        m_Dist.resize(nAll);
+        const double* xy = m_SampleXY.data();
+        for (size_t i = 0; i < nAll; i++) {
+            const double x = xy[2 * i], y = xy[2 * i + 1];
+            m_Dist[i] = sqrt((x - e.x) * (x - e.x) + (y - e.y) * (y - e.y));
+        }
+        m_Keys.resize(nAll);
+        for (size_t i = 0; i < nAll; i++) m_Keys[i] = m_Dist[m_Perm[i]];
+        ppe_heap::make_heap(m_Keys.data(), m_Perm.data(), (std::ptrdiff_t)nAll);
+        for (uint32_t q = 0; q < e.pops; q++) ppe_heap::pop_heap(m_Keys.data(), m_Perm.data(), (std::ptrdiff_t)(nAll - q));
+    }
+}
+
+// The vertex the reference's loop just popped, plus the best vertices still on the open list, in one engine call.
+void BatchedAStarPlanner::speculate(const std::shared_ptr<Vertex>& first) {
+    std::vector<std::shared_ptr<Vertex>> batch;
+    batch.push_back(first);
+    if (m_Frontier > 1) {
+        // best-first walk over the open list's heap (front = smallest f, AStarPlanner.cpp:6-10) without modifying it
+        const std::vector<std::shared_ptr<Vertex>>& open = this->*get(OpenList());
+        typedef std::pair<double, size_t> Node;
+        auto worse = [](const Node& a, const Node& b) { return a.first > b.first || (a.first == b.first && a.second > b.second); };
+        std::vector<Node> walk;
+        if (!open.empty()) walk.push_back(Node(open[0]->f(), 0));
+        size_t visited = 0;
+        while ((int)batch.size() < m_Frontier && !walk.empty() && visited < 4 * (size_t)m_Frontier) {
+            std::pop_heap(walk.begin(), walk.end(), worse);
+            const size_t idx = walk.back().second;
+            walk.pop_back();
+            visited++;
+            const std::shared_ptr<Vertex>& u = open[idx];
+            if (u != first && !goalCondition(u) && !m_Expansions.count(u.get())) batch.push_back(u);
+            for (size_t child = 2 * idx + 1; child <= 2 * idx + 2 && child < open.size(); child++) {
+                walk.push_back(Node(open[child]->f(), child));
+                std::push_heap(walk.begin(), walk.end(), worse);
+            }
+        }
+    }
+    const int n = (int)batch.size();
+    const double inc = m_Config.collisionCheckingIncrement();
+    m_Verts.resize(n);
+    for (int i = 0; i < n; i++) {
+        const Vertex& u = *batch[i];
+        ppe_vertex& pv = m_Verts[i];
+        std::memset(&pv, 0, sizeof pv);
+        const State& st = u.state();
+        pv.state[0] = st.x(); pv.state[1] = st.y(); pv.state[2] = st.heading(); pv.state[3] = st.speed(); pv.state[4] = st.time();
+        pv.g = u.currentCost();
+        pv.ribbon_set = internRibbons(u.ribbonManager());
+        if (!u.done()) { // SamplingBasedPlanner.cpp:65-68
+            const State s = u.getNearestPointAsState();
+            if (st.distanceTo(s) > inc) {
+                pv.has_endpoint = 1;
+                pv.endpoint[0] = s.x(); pv.endpoint[1] = s.y(); pv.endpoint[2] = s.heading();
+            }
+        }
+    }
+    const int stride = ppe_expand_stride(m_Ctx);
+    m_Children.resize((size_t)n * stride);
+    m_NChildren.resize(n); m_Flags.resize(n); m_Popped.resize(n);
+    const int64_t solves0 = ppe_expand_solve_count(m_Ctx);
+    check(ppe_expand_batch(m_Ctx, n, m_Verts.data(), m_NChildren.data(), m_Children.data(), m_Flags.data(), m_Popped.data()),
+          "ppe_expand_batch");
+    m_DubinsSolves += (long)(ppe_expand_solve_count(m_Ctx) - solves0);
+    m_Batches++;
+    m_FrontierVertices += n;
+    int64_t nPool = 0;
+    const double* pool = ppe_ribbon_pool(m_Ctx, &nPool);
+    for (int i = 0; i < n; i++) {
+        Expansion& ex = m_Expansions[batch[i].get()];
+        ex.vertex = batch[i];
+        ex.flags = m_Flags[i];
+        ex.popped = m_Popped[i];
+        const int nc = m_NChildren[i];
+        ex.children.assign(m_Children.begin() + (size_t)i * stride, m_Children.begin() + (size_t)i * stride + nc);
+        ex.ribbonStart.assign(nc, -1);
+        ex.ribbons.clear();
+        for (int c = 0; c < nc; c++) {
+            const ppe_child& ch = ex.children[c];
+            if (ch.status == PPE_EDGE_OK && ch.ribbons_changed) {
+                if (ch.ribbons_offset < 0 || ch.ribbons_offset + ch.n_ribbons_after > nPool)
+                    throw std::runtime_error("ppe_expand_batch: ribbons-after of a child were not materialised");
+                ex.ribbonStart[c] = (int)(ex.ribbons.size() / 4);
+                ex.ribbons.insert(ex.ribbons.end(), pool + 4 * ch.ribbons_offset, pool + 4 * (ch.ribbons_offset + ch.n_ribbons_after));
+            }
+        }
+        m_TrueCostEdges += nc;
+    }
+}
+
+void BatchedAStarPlanner::expandFrontier(const std::shared_ptr<Vertex>& sourceVertex) {
+    // callers that filled m_Samples through the base class (SamplingBasedPlanner::addSamples is not virtual): mirror it
+    if ((size_t)ppe_sample_count(m_Ctx) != m_Samples.size()) {
+        check(ppe_clear_samples(m_Ctx), "ppe_clear_samples");
+        const size_t n = m_Samples.size();
+        m_GenX.resize(n); m_GenY.resize(n); m_GenH.resize(n); m_Keep.resize(n);
+        for (size_t i = 0; i < n; i++) { m_GenX[i] = m_Samples[i].x(); m_GenY[i] = m_Samples[i].y(); m_GenH[i] = m_Samples[i].heading(); }
+        const int64_t kept = n ? ppe_add_samples(m_Ctx, (int64_t)n, m_GenX.data(), m_GenY.data(), m_GenH.data(), m_Keep.data()) : 0;
+        if (kept != (int64_t)n) throw std::runtime_error("BatchedAStarPlanner: m_Samples holds states the map blocks");
+    }
+    auto it = m_Expansions.find(sourceVertex.get());
+    if (it == m_Expansions.end()) {
+        speculate(sourceVertex);
+        it = m_Expansions.find(sourceVertex.get());
+    } else {
+        m_FrontierHits++;
+    }
+    static const bool forceExact = getenv("PPE_HARNESS_TEST_FORCE_EXACT") != nullptr; // tests: every 3rd expansion replays on the host
+    if ((it->second.flags & (PPE_EXPAND_TIE | PPE_EXPAND_OVERFLOW)) || (forceExact && m_Stats.Expanded % 3 == 2)) {
+        m_Expansions.erase(it);
+        expandExact(sourceVertex);
+        return;
+    }
+    visualizeVertex(sourceVertex, "vertex", true);
+    const Expansion& ex = it->second;
+    const State& src = sourceVertex->state();
+    const double qi[3] = {src.x(), src.y(), src.yaw()};
+    for (size_t c = 0; c < ex.children.size(); c++) {
+        const ppe_child& ch = ex.children[c];
+        if (ch.status != PPE_EDGE_OK)
+            throw std::runtime_error("edge evaluation failed where the reference throws (status " + std::to_string(ch.status) + ")");
+        State end(ch.end[0], ch.end[1], ch.end[2], ch.end[3], ch.end[4]);
+        const double rho = ch.coverage_allowed ? m_Config.coverageTurningRadius() : m_Config.turningRadius();
+        auto v = Vertex::connect(sourceVertex, end, rho, ch.coverage_allowed != 0);
+        const double* rib = ex.ribbonStart[c] >= 0 ? ex.ribbons.data() + 4 * (size_t)ex.ribbonStart[c] : nullptr;
+        fillChild(v, qi, ch.path_param, rho, ch.path_type, ch.end[3], src.time(), ch.w_end_time, ch.infeasible != 0, ch.approx_cost,
+                  ch.true_cost, ch.collision_penalty, ch.g, ch.h, ch.coverage_completed_time, ch.ribbons_changed != 0, rib,
+                  ch.n_ribbons_after);
+        pushVertexQueue(v);
+    }
+    ExpansionLog lg;
+    lg.x = src.x(); lg.y = src.y(); lg.pops = (uint32_t)ex.popped; lg.nSamples = (uint32_t)m_Samples.size();
+    m_Log.push_back(lg);
+    m_Expansions.erase(it);
+    m_Stats.Expanded++;
+}
+
+void BatchedAStarPlanner::expandExact(const std::shared_ptr<Vertex>& sourceVertex) {
+    m_ExactExpansions++;
+    syncSampleHeap(); // the arrangement of m_Samples as the reference would have it right now
     visualizeVertex(sourceVertex, "vertex", true);
     const State& src = sourceVertex->state();
     const double inc = m_Config.collisionCheckingIncrement();
@@ -171,15 +609,7 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
                                                 m_Config.coverageTurningRadius() == m_Config.turningRadius() ? -1 : m_Config.coverageTurningRadius()};
 
     // intern the parent's ribbon set once; every edge of this expansion refers to it
-    const RibbonManager& parentRibbons = sourceVertex->ribbonManager();
-    m_RibbonBuf.clear();
-    for (const auto& r : parentRibbons.get()) {
-        m_RibbonBuf.push_back(r.start().first); m_RibbonBuf.push_back(r.start().second);
-        m_RibbonBuf.push_back(r.end().first); m_RibbonBuf.push_back(r.end().second);
-    }
-    int32_t setId = -1;
-    check(ppe_put_ribbon_set(m_Ctx, (int)(m_RibbonBuf.size() / 4), m_RibbonBuf.data(), parentRibbons.coverageCompletedTime(), &setId),
-          "ppe_put_ribbon_set");
+    const int32_t setId = internRibbons(sourceVertex->ribbonManager());
 
     m_Edges.clear();
     auto baseEdge = [&]() {
@@ -414,35 +844,13 @@ void BatchedAStarPlanner::expand(const std::shared_ptr<Vertex>& sourceVertex, co
         State end(r.end[0], r.end[1], r.end[2], r.end[3], r.end[4]);
         const double rho = e.coverage_allowed ? m_Config.coverageTurningRadius() : m_Config.turningRadius();
         auto v = Vertex::connect(sourceVertex, end, rho, e.coverage_allowed != 0);
-        Edge& edge = *v->parentEdge();
-        // Edge members written by computeTrueCost (Edge.cpp:177-199)
-        DubinsPath p;
-        p.qi[0] = r.path_qi[0]; p.qi[1] = r.path_qi[1]; p.qi[2] = r.path_qi[2];
-        p.param[0] = r.path_param[0]; p.param[1] = r.path_param[1]; p.param[2] = r.path_param[2];
-        p.rho = r.path_rho; p.type = (DubinsPathType)r.path_type;
-        DubinsWrapper w;
-        w.fill(p, r.w_speed, r.w_start_time);
-        if (r.w_end_time < w.getEndTime()) w.updateEndTime(r.w_end_time);
-        edge.*get(EdgeWrapper()) = w;
-        edge.*get(EdgeInfeasible()) = r.infeasible != 0;
-        edge.*get(EdgeApprox()) = r.approx_cost;
-        edge.*get(EdgeTrue()) = r.true_cost;
-        edge.*get(EdgePenalty()) = r.collision_penalty;
-        // Vertex members (Vertex.cpp:102-104, :49-64)
-        (*v).*get(VertexG()) = r.g;
-        RibbonManager& rm = v->ribbonManager();
         if (r.ribbons_changed) {
             m_RibbonBuf.resize((size_t)std::max(1, r.n_ribbons_after) * 4);
-            const int n = ppe_get_ribbons_after(m_Ctx, (int64_t)i, m_RibbonBuf.data(), r.n_ribbons_after);
-            check(n, "ppe_get_ribbons_after");
-            std::list<Ribbon>& list = rm.*get(RibbonList());
-            list.clear();
-            for (int k2 = 0; k2 < n; k2++)
-                list.emplace_back(m_RibbonBuf[4 * k2], m_RibbonBuf[4 * k2 + 1], m_RibbonBuf[4 * k2 + 2], m_RibbonBuf[4 * k2 + 3]);
+            check(ppe_get_ribbons_after(m_Ctx, (int64_t)i, m_RibbonBuf.data(), r.n_ribbons_after), "ppe_get_ribbons_after");
         }
-        rm.*get(RibbonCct()) = r.coverage_completed_time;
-        if (m_Heuristic == PPE_H_MAX_DISTANCE) (*v).*get(VertexH()) = r.h;
-        else v->computeApproxToGo(m_Config); // TSP heuristics stay on the host (RibbonManager.cpp:53-140)
+        fillChild(v, r.path_qi, r.path_param, r.path_rho, r.path_type, r.w_speed, r.w_start_time, r.w_end_time, r.infeasible != 0,
+                  r.approx_cost, r.true_cost, r.collision_penalty, r.g, r.h, r.coverage_completed_time, r.ribbons_changed != 0,
+                  m_RibbonBuf.data(), r.n_ribbons_after);
         pushVertexQueue(v);
     }
     (void)nEndpointEdges;

@@ -128,7 +128,7 @@ def describe(bad, got, want, limit=3):
 # ---- whole-plan runs: the reference's AStarPlanner and the product's BatchedAStarPlanner --------------
 HARNESS_SO = os.path.join(ORACLE_DIR, "_ref", "libppe_harness.so")
 PLAN_STATS = ("samples", "generated", "expanded", "iterations", "f", "collision_penalty", "time_penalty", "h", "depth",
-              "now_calls", "true_cost_edges", "dubins_solves", "batches")
+              "now_calls", "true_cost_edges", "dubins_solves", "batches", "frontier_vertices", "frontier_hits", "exact_expansions")
 
 
 def have_harness():
@@ -145,22 +145,29 @@ def load_harness(path=None):
     w.lib.ref_plan.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D, C.c_int, D]
     w.lib.harness_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                    C.c_int, D, C.c_int, D]
+    w.lib.ref_plan2.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D, C.c_int, D,
+                                C.c_int, D]
+    w.lib.harness_plan2.argtypes = [C.c_void_p, C.c_int, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, D, C.c_int, D, C.c_int, D]
     return w
 
 
 def run_plan(w, which, ribbon_set, start, time_remaining, clock0, tick, initial_samples=100, brown=0, knn_chunk=128,
-             device=0, cap=256):
+             device=0, cap=256, frontier=-1, previous=None):
     """which = "ref" (AStarPlanner) or "harness" (BatchedAStarPlanner on `device`).  tick > 0 selects the
-    virtual clock (now() = clock0 + calls * tick).  Returns (plan [n,12], stats dict)."""
+    virtual clock (now() = clock0 + calls * tick).  `frontier`: vertices per ppe_expand_batch (-1 default, 0 = exact host
+    replay).  `previous`: a plan [n, 12] handed in as previousPlan.  Returns (plan [n,12], stats dict)."""
     start = np.ascontiguousarray(start, dtype=np.float64)
     plan = np.zeros((cap, 12))
-    stats = np.zeros(13)
+    stats = np.zeros(16)
+    prev = np.ascontiguousarray(previous if previous is not None else np.zeros((0, 12)), dtype=np.float64).reshape(-1, 12)
+    pp = abi.dptr(prev) if len(prev) else None
     if which == "ref":
-        n = w.lib.ref_plan(w.ctx, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples, brown,
-                           abi.dptr(plan), cap, abi.dptr(stats))
+        n = w.lib.ref_plan2(w.ctx, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples, brown,
+                            pp, len(prev), abi.dptr(plan), cap, abi.dptr(stats))
     else:
-        n = w.lib.harness_plan(w.ctx, device, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples,
-                               brown, knn_chunk, abi.dptr(plan), cap, abi.dptr(stats))
+        n = w.lib.harness_plan2(w.ctx, device, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples,
+                                brown, knn_chunk, frontier, pp, len(prev), abi.dptr(plan), cap, abi.dptr(stats))
     if n < 0:
         raise RuntimeError("%s plan failed (%d): %s" % (which, n, (w.lib.ref_last_error(w.ctx) or b"").decode()))
     return plan[:min(n, cap)].copy(), dict(zip(PLAN_STATS, stats.tolist()))

@@ -28,19 +28,70 @@ CASES = [
 CASE_IDS = [c[0] for c in CASES]
 
 
-def compare(lib, case, exact, knn_chunk=128, clock0=1000.0):
-    """Runs both planners; asserts plan identity.  Returns (harness stats, reference plan)."""
-    _, wname, start, budget, tick, initial = case
+# follow-up cycles of the Executive's plan loop (executive.cpp:146,189): the plan of a first cycle is handed back as
+# previousPlan and re-validated edge by edge (AStarPlanner.cpp:46-59); `advance` seconds later along that plan, or from
+# the very same start state (advance = 0); with and without Brown paths (AStarPlanner.cpp:43-45,99,150-162).
+# name, world key, start, budget, tick, initial samples, advance s, brown
+FOLLOWUP_CASES = [
+    ("c1-previous-plan", "c1", None, 0.95, 5e-4, 100, 1.0, 0),
+    ("c2-previous-plan", "c2", (395.0, 390.0, 0.3, 2.5, 1.0), 0.95, 2e-3, 100, 1.0, 0),
+    ("c2-previous-plan-same-start", "c2", (395.0, 390.0, 0.3, 2.5, 1.0), 0.95, 2e-3, 100, 0.0, 0),
+    ("c3-previous-plan", "c3", (420.0, 395.0, 0.0, 2.5, 1.0), 0.95, 4e-3, 100, 2.0, 0),
+    ("c1-brown-paths", "c1", (3.0, 2.0, 0.4, 2.5, 1.0), 0.95, 5e-4, 100, None, 1),
+    ("c2-brown-paths", "c2", (395.0, 390.0, 0.3, 2.5, 1.0), 0.95, 2e-3, 100, None, 1),
+    ("c2-brown-paths+previous-plan", "c2", (402.0, 395.0, 0.1, 2.5, 1.0), 0.95, 2e-3, 100, 1.0, 1),
+]
+FOLLOWUP_IDS = [c[0] for c in FOLLOWUP_CASES]
+
+
+def make_world(wname):
     if wname == "c1-tsp":
         world = synth.world_c1()
         world.cfg.heuristic = abi.H_TSP_POINT_ROBOT_NO_SPLIT_K
         world.ribbons = np.array([[0.0, 10.0, 0.0, 30.0], [6.0, 30.0, 6.0, 10.0]])
-    else:
-        world = synth.WORLDS[wname]()
+        return world
+    return synth.WORLDS[wname]()
+
+
+def state_along(plan, t):
+    """State (x, y, heading, speed, t) at time t on a plan [n, 12] -- DubinsPlan::sample (DubinsPlan.cpp:11-19) through the
+    oracle's restatement of DubinsWrapper::sample; what the controller hands back as the next start state."""
+    import ctypes as C
+    ora = common.load_oracle("glibc")
+    D, I = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    ora.lib.oracle_wrapper_sample.argtypes = [D, D, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, D, D, D, D, I]
+    for seg in plan:
+        if seg[9] <= t <= seg[10]:
+            x, y, h = np.zeros(1), np.zeros(1), np.zeros(1)
+            ok = np.zeros(1, dtype=np.int32)
+            tt = np.array([t])
+            qi, pr = np.ascontiguousarray(seg[0:3]), np.ascontiguousarray(seg[3:6])
+            ora.lib.oracle_wrapper_sample(abi.dptr(qi), abi.dptr(pr), float(seg[6]), int(seg[7]), float(seg[9]), float(seg[8]), 1,
+                                          abi.dptr(tt), abi.dptr(x), abi.dptr(y), abi.dptr(h), abi.iptr(ok))
+            return np.array([x[0], y[0], h[0], seg[8], t])
+    raise ValueError("time %g is not on the plan" % t)
+
+
+def compare_followup(lib, case, exact, frontier=-1, clock0=1000.0):
+    """First cycle by the reference; second cycle (previous plan and / or Brown paths) by both planners."""
+    _, wname, start, budget, tick, initial, advance, brown = case
+    world = make_world(wname)
     start = world.start if start is None else np.array(start, dtype=np.float64)
     sid = world.upload_ref(lib)
-    want_plan, want = common.run_plan(lib, "ref", sid, start, budget, clock0, tick, initial)
-    got_plan, got = common.run_plan(lib, "harness", sid, start, budget, clock0, tick, initial, knn_chunk=knn_chunk)
+    previous = None
+    if advance is not None:
+        previous, first = common.run_plan(lib, "ref", sid, start, budget, clock0, tick, initial)
+        assert len(previous) >= 1
+        if advance > 0:
+            start = state_along(previous, start[4] + advance)
+    want_plan, want = common.run_plan(lib, "ref", sid, start, budget, clock0 + 7, tick, initial, brown=brown, previous=previous)
+    got_plan, got = common.run_plan(lib, "harness", sid, start, budget, clock0 + 7, tick, initial, brown=brown, previous=previous,
+                                    frontier=frontier)
+    _assert_same(got, got_plan, want, want_plan, exact)
+    return got, want_plan
+
+
+def _assert_same(got, got_plan, want, want_plan, exact):
     for k in COUNTERS:
         assert got[k] == want[k], (k, got, want)
     assert got_plan.shape == want_plan.shape
@@ -55,4 +106,15 @@ def compare(lib, case, exact, knn_chunk=128, clock0=1000.0):
         assert np.array_equal(got_plan[:, 6], want_plan[:, 6]), "radii differ"
         assert np.allclose(got_plan, want_plan, rtol=common.RTOL, atol=common.ATOL), (got_plan, want_plan)
     assert got["true_cost_edges"] > 0 and got["batches"] > 0
+
+
+def compare(lib, case, exact, knn_chunk=128, clock0=1000.0, frontier=-1):
+    """Runs both planners; asserts plan identity.  Returns (harness stats, reference plan)."""
+    _, wname, start, budget, tick, initial = case
+    world = make_world(wname)
+    start = world.start if start is None else np.array(start, dtype=np.float64)
+    sid = world.upload_ref(lib)
+    want_plan, want = common.run_plan(lib, "ref", sid, start, budget, clock0, tick, initial)
+    got_plan, got = common.run_plan(lib, "harness", sid, start, budget, clock0, tick, initial, knn_chunk=knn_chunk, frontier=frontier)
+    _assert_same(got, got_plan, want, want_plan, exact)
     return got, want_plan

@@ -28,10 +28,38 @@ def test_batched_planner_reproduces_the_reference_plan_bit_for_bit(lib, case):
     assert got["expanded"] >= 2
 
 
+def test_default_path_is_the_frontier_path(lib):
+    """Default width: vertices travel to ppe_expand_batch in groups, most expansions are served from a cached group
+    result, and no expansion needs the exact host replay (no two samples at exactly equal distance)."""
+    got, _ = plan_cases.compare(lib, plan_cases.CASES[0], exact=True)
+    assert got["frontier_vertices"] >= got["expanded"] and got["frontier_hits"] > 0.5 * got["expanded"]
+    assert got["exact_expansions"] == 0
+    assert got["batches"] < 0.5 * got["expanded"]
+
+
+@pytest.mark.parametrize("frontier", [0, 1, 7])
+@pytest.mark.parametrize("i", [0, 6, 8])
+def test_frontier_width_does_not_change_the_plan(lib, i, frontier):
+    """Width 0 = the exact host replay for every vertex (k-nearest heaps on the host, K1 per chunk, K2 per vertex);
+    width 1 = one vertex per device call; any width must give the reference's plan bit for bit."""
+    got, _ = plan_cases.compare(lib, plan_cases.CASES[i], exact=True, frontier=frontier)
+    if frontier == 0:
+        assert got["exact_expansions"] == got["expanded"] and got["frontier_vertices"] == 0
+
+
+@pytest.mark.parametrize("case", plan_cases.FOLLOWUP_CASES, ids=plan_cases.FOLLOWUP_IDS)
+def test_previous_plan_and_brown_paths_through_the_engine(lib, case):
+    """The other callers of the path: previous-plan re-validation (AStarPlanner.cpp:46-59) and the Brown-path
+    expansion (:150-162) are evaluated by the engine in BatchedAStarPlanner::plan; the second planning cycle must be the
+    reference's bit for bit."""
+    got, plan = plan_cases.compare_followup(lib, case, exact=True)
+    assert len(plan) >= 1
+
+
 def test_knn_chunk_only_changes_the_launch_count(lib):
     case = plan_cases.CASES[0][:4] + (2e-3, 100)
-    a, plan_a = plan_cases.compare(lib, case, exact=True, knn_chunk=16)
-    b, plan_b = plan_cases.compare(lib, case, exact=True, knn_chunk=512)
+    a, plan_a = plan_cases.compare(lib, case, exact=True, knn_chunk=16, frontier=0)
+    b, plan_b = plan_cases.compare(lib, case, exact=True, knn_chunk=512, frontier=0)
     assert np.array_equal(plan_a, plan_b)
     assert a["dubins_solves"] < b["dubins_solves"] and a["batches"] > b["batches"]
 
@@ -49,7 +77,27 @@ def test_mispredicted_chunks_do_not_change_the_plan():
         "from tests import common, plan_cases\n"
         "lib = common.load_harness(%r)\n"
         "for i in (0, 2, 5):\n"
-        "    got, plan = plan_cases.compare(lib, plan_cases.CASES[i], exact=True, knn_chunk=16)\n"
+        "    got, plan = plan_cases.compare(lib, plan_cases.CASES[i], exact=True, knn_chunk=16, frontier=0)\n"
+        "print('ok')\n" % (common.ROOT, CPU_SO))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_mixing_device_and_exact_expansions_does_not_change_the_plan():
+    """An expansion the device flags (two samples at exactly equal distance) is replayed on the host, whose sample heap must
+    then be in the arrangement the reference's m_Samples has at that moment: the logged device expansions are replayed into
+    it first.  PPE_HARNESS_TEST_FORCE_EXACT sends every third expansion down that path."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys\n"
+        "os.environ['PPE_HARNESS_TEST_FORCE_EXACT'] = '1'\n"
+        "sys.path.insert(0, %r)\n"
+        "from tests import common, plan_cases\n"
+        "lib = common.load_harness(%r)\n"
+        "for i in (0, 6, 8):\n"
+        "    got, plan = plan_cases.compare(lib, plan_cases.CASES[i], exact=True)\n"
+        "    assert got['exact_expansions'] > 0 and got['frontier_vertices'] > 0, got\n"
         "print('ok')\n" % (common.ROOT, CPU_SO))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

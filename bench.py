@@ -185,7 +185,7 @@ def plan_at_budget(budget_s, device):
     from path_planner_b200 import synth
     from tests import common
     if not common.have_harness():
-        return {"unavailable": "oracle/_ref/libppe_harness.so not built (needs the reference sources at build time)"}
+        return {"unavailable": "oracle/_ref/libplan_compare.so not built (needs the reference sources at build time)"}
     lib = common.load_harness()
     reps = 3
     out = {"budget_s": budget_s, "repetitions": reps,

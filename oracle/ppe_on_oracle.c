@@ -3,7 +3,7 @@
  * Implements the subset of include/ppe.h that the C++ host adapter
  * (path_planner_b200/harness/BatchedAStarPlanner.cpp) calls by forwarding to the CPU oracle
  * (oracle/ppe_oracle.c, glibc variant == the compiled reference bit for bit).  Linked ONLY into
- * oracle/_ref/libppe_harness_cpu.so so that `-m "not gpu"` tests can check the adapter's host
+ * oracle/_ref/libplan_compare_cpu.so so that `-m "not gpu"` tests can check the adapter's host
  * logic -- batch assembly, the replay of the k-nearest heaps, the push order into the open list --
  * in a container without a GPU: with a bit-identical evaluator behind it, BatchedAStarPlanner must
  * return the reference's plan bit for bit.  The product library libppe.so has no such path.

@@ -1,4 +1,5 @@
-// oracle/ref_prefix.h -- TEST INFRASTRUCTURE (oracle/_ref build), not product code.
+// compat/ref_compat.h -- toolchain fixes for compiling the reference's translation units in this image (g++ 13); used by
+// the harness build (path_planner_b200/harness/Makefile) and by the oracle build (oracle/Makefile).
 //
 // Force-included (-include) in front of every reference translation unit when the reference is
 // compiled *where it lies* under /root/reference (no source is copied).  Two fixes, both needed

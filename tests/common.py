@@ -126,7 +126,7 @@ def describe(bad, got, want, limit=3):
 
 
 # ---- whole-plan runs: the reference's AStarPlanner and the product's BatchedAStarPlanner --------------
-HARNESS_SO = os.path.join(ORACLE_DIR, "_ref", "libppe_harness.so")
+HARNESS_SO = os.path.join(ORACLE_DIR, "_ref", "libplan_compare.so")
 PLAN_STATS = ("samples", "generated", "expanded", "iterations", "f", "collision_penalty", "time_penalty", "h", "depth",
               "now_calls", "true_cost_edges", "dubins_solves", "batches", "frontier_vertices", "frontier_hits", "exact_expansions")
 
@@ -136,9 +136,10 @@ def have_harness():
 
 
 def load_harness(path=None):
-    """libppe_harness.so = the compiled reference objects + ref_shim + the product's C++ host adapter
-    (path_planner_b200/harness/BatchedAStarPlanner.cpp) linked against libppe.so.  One ref_ctx holds the
-    world both planners read, so `ref_plan` and `harness_plan` see identical inputs."""
+    """oracle/_ref/libplan_compare.so = the compiled reference objects + ref_shim + a TEST BUILD of the product's C++ host
+    adapter (path_planner_b200/harness/BatchedAStarPlanner.cpp) linked against libppe.so.  One ref_ctx holds the
+    world both planners read, so `ref_plan` and `harness_plan` see identical inputs.  (The product's own build of the
+    harness is path_planner_b200/libppe_harness.so, bound in path_planner_b200/harness.py.)"""
     w = _load(path or HARNESS_SO, "ref_")
     D = C.POINTER(C.c_double)
     w.lib.ref_get_obstacles.argtypes = [C.c_void_p, D, C.c_int]

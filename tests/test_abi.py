@@ -65,3 +65,18 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"libppe_oracle|ppe_oracle\.c|oracle_true_cost|from tests|import tests", text):
                     offenders.append(os.path.join(dirpath, f))
     assert not offenders, offenders
+
+
+def test_harness_library_exports_every_declared_symbol():
+    """include/ppe_harness.h (the standalone harness's C ABI) against path_planner_b200/libppe_harness.so; skipped where the
+    harness was not built (it compiles against the reference's headers)."""
+    from path_planner_b200 import harness as ph
+    if not ph.available():
+        pytest.skip("libppe_harness.so not built (needs /root/reference at build time)")
+    text = open(os.path.join(ROOT, "include", "ppe_harness.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(pph_[a-z0-9_]+)\s*\(", text)))
+    assert "pph_plan" in syms and "pph_create" in syms
+    lib = C.CDLL(ph.HARNESS_PATH)
+    assert not [s for s in syms if not hasattr(lib, s)]
+    assert C.sizeof(ph.PlanStats) == 18 * 8 and C.sizeof(ph.PlanOptions) == 56 and ph.PATH_DTYPE.itemsize == 88

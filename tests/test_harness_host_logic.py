@@ -1,6 +1,6 @@
 """Host logic of the C++ adapter (path_planner_b200/harness/BatchedAStarPlanner.cpp) without a GPU.
 
-oracle/_ref/libppe_harness_cpu.so links the adapter against a TEST DOUBLE of the C ABI
+oracle/_ref/libplan_compare_cpu.so links the adapter against a TEST DOUBLE of the C ABI
 (oracle/ppe_on_oracle.c: ppe_* forwarded to the CPU oracle, which is bit-identical to the compiled
 reference).  With a bit-identical evaluator behind it, everything the adapter does on the host --
 batch assembly for the three call sites of SamplingBasedPlanner::expand (:76, :119, :145), the
@@ -12,9 +12,9 @@ import pytest
 
 from tests import common, plan_cases
 
-CPU_SO = common.HARNESS_SO.replace("libppe_harness.so", "libppe_harness_cpu.so")
+CPU_SO = common.HARNESS_SO.replace("libplan_compare.so", "libplan_compare_cpu.so")
 pytestmark = pytest.mark.skipif(not __import__("os").path.exists(CPU_SO),
-                                reason="oracle/_ref/libppe_harness_cpu.so not built (needs /root/reference)")
+                                reason="oracle/_ref/libplan_compare_cpu.so not built (needs /root/reference)")
 
 
 @pytest.fixture(scope="module")

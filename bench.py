@@ -1,25 +1,31 @@
 #!/usr/bin/env python3
 """bench.py -- Dubins edge true-cost evaluations per second (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c3b|c5|c1] [--edges E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c2|c3|c3b|c4|c1] [--edges E] [--scaling strong|weak]
     python bench.py --impl reference ...      # the reference's own CPU implementation of the path
 
 One "step" = one pass of the hot path (Edge::computeTrueCost incl. the Dubins solve, Edge.cpp:68-206)
-over one batch of E synthetic edges per GPU.  Default workload: BASELINE.json configs[1] -- the 1 km^2
-grid map with static obstacles and 10 survey ribbons -- as a 2^20-edge sweep per GPU (weak scaling).
+over one batch of E synthetic edges.  Default workload: BASELINE.json configs[4], the 1M-edge batch config --
+2^20 edges on the 4096^2 map with 100 ribbons and 50 Gaussian obstacles (C5).  With N GPUs that ONE batch is
+split into N contiguous shards (strong scaling, path_planner_b200.sharding.shard_range) and the per-shard best
+records are all-gathered over NCCL; --scaling weak gives every GPU its own E-edge batch instead.  At N = 1 the
+line also carries the other configs (C2 = configs[1], C3, C4) under "workloads", the 64-scenario sweep of
+configs[4] under "scenarios" and the plan-cost comparison under "plan".
 
   value     edges/s, whole job, inputs already resident in HBM, timed with CUDA events on the
             launching stream (max over ranks).
   e2e       the same metric through the public host-buffer call (EdgeEngine.true_cost_batch ->
             ppe_true_cost_batch): pinned host inputs, H2D + kernels + D2H inside the timed region.
-  roofline  the dominant kernel (k2_true_cost) against the MEASURED fp64 FMA peak of this GPU
-            (tensor cores are not used; HBM is not the bound -- its fraction is reported too).
+  roofline  the launch group of one step against the MEASURED fp64 FMA peak of this GPU (tensor cores are not
+            used; HBM is not the bound -- its fraction is reported too); fp64_pipe_pct / traffic come from the
+            committed ncu captures of this very command (profiles/r02_ncu_metrics.json).
   cpu_baseline  the compiled reference (oracle/_ref/libref_planner.so, kind "reference") or the C
             restatement (kind "port") single-threaded on this host, on a bounded sample.
   dubins    secondary line: K1 Dubins solves per second (HBM-resident), BASELINE metric part (ii).
-  plan      BASELINE metric part (iii), "plan cost at 1 s budget": the reference's AStarPlanner (CPU) and the
-            product's BatchedAStarPlanner (this GPU) each get the same world, start state and a REAL 1.0 s
-            wall-clock budget; f-value of the returned plan (lower is better) and search effort of both.
+  plan      BASELINE metric part (iii), "plan cost at 1 s budget": the reference's AStarPlanner (CPU,
+            oracle/_ref/libref_planner.so) and the product's standalone harness (path_planner_b200/libppe_harness.so:
+            BatchedAStarPlanner on this GPU) each get the same world, start state and a REAL 1.0 s wall-clock
+            budget; f-value of the returned plan (lower is better), expansions and expansions/s of both.
 """
 import argparse
 import ctypes as C
@@ -162,12 +168,12 @@ def cpu_rate(world, edges, budget_s, threads):
         world.upload_ref(w)
     else:
         world.upload(w)
-    probe = edges[: min(len(edges), 512)]
+    probe = edges[: min(len(edges), 256 if threads == 1 else 1024)]
     t0 = time.perf_counter()
     common.true_cost_mt(w, probe, threads)
     dt = time.perf_counter() - t0
     rate = len(probe) / max(dt, 1e-9)
-    n = int(max(512, min(len(edges), rate * budget_s)))
+    n = int(max(len(probe), min(len(edges), rate * budget_s)))
     sample = edges[:n]
     t0 = time.perf_counter()
     common.true_cost_mt(w, sample, threads)
@@ -176,43 +182,92 @@ def cpu_rate(world, edges, budget_s, threads):
 
 
 PLAN_SCENARIOS = (("c1", None), ("c2", None), ("c2", (470.0, 610.0, 3.0, 2.5, 1.0)), ("c3", (420.0, 395.0, 0.0, 2.5, 1.0)),
-                  ("c3b", (420.0, 395.0, 0.0, 2.5, 1.0)))
+                  ("c3b", (420.0, 395.0, 0.0, 2.5, 1.0)), ("c4", None))
 
 
-def plan_at_budget(budget_s, device):
-    """Reference AStarPlanner vs BatchedAStarPlanner with a real wall-clock budget (tick = 0 -> real clock) on
-    the BASELINE worlds C1-C3 (the start states of tests/plan_cases.py)."""
+def plan_at_budget(budget_s, device, reps=3):
+    """Reference AStarPlanner (CPU) vs the product harness (BatchedAStarPlanner on `device`) with a real wall-clock
+    budget (tick = 0 -> real clock) on the BASELINE worlds (the start states of tests/plan_cases.py)."""
+    from path_planner_b200 import harness as ph
     from path_planner_b200 import synth
     from tests import common
-    if not common.have_harness():
-        return {"unavailable": "oracle/_ref/libplan_compare.so not built (needs the reference sources at build time)"}
-    lib = common.load_harness()
-    reps = 3
+    if not ph.available():
+        return {"unavailable": "path_planner_b200/libppe_harness.so not built (needs the reference sources at build time)"}
+    ref = common.load_ref() if common.have_ref() else None
+    h = ph.PlanningHarness(device)
     out = {"budget_s": budget_s, "repetitions": reps,
            "unit": "f = g + h of the returned plan, seconds (lower is better); the planner seeds its sampler from the wall "
                    "clock (AStarPlanner.cpp:33), so every scenario is planned `repetitions` times by each planner: median f, "
-                   "best f, mean expansions",
+                   "best f, mean expansions and expansions per second of wall time",
            "scenarios": []}
     for wname, start in PLAN_SCENARIOS:
         world = synth.WORLDS[wname]()
-        sid = world.upload_ref(lib)
         st0 = world.start if start is None else np.array(start, dtype=np.float64)
         rec = {"world": wname, "start": [float(v) for v in st0]}
-        for which in ("ref", "harness"):
+        initial = 10000 if wname == "c4" else 100  # SURVEY 8d: C4 runs with initialSamples = 10 000
+        if ref is not None:
+            sid = world.upload_ref(ref)
             fs, exp, smp, wall = [], [], [], []
             for _ in range(reps):
                 t0 = time.perf_counter()
-                plan, st = common.run_plan(lib, which, sid, st0, budget_s, 0.0, 0.0, 100, device=device)
+                plan, st = common.run_plan(ref, "ref", sid, st0, budget_s, 0.0, 0.0, initial)
                 wall.append(time.perf_counter() - t0)
                 if len(plan):
                     fs.append(st["f"])
                 exp.append(st["expanded"])
                 smp.append(st["samples"])
-            rec["reference_cpu" if which == "ref" else "engine"] = {
-                "f_median": statistics.median(fs) if fs else None, "f_best": min(fs) if fs else None, "plans_found": len(fs),
-                "expanded_mean": sum(exp) / reps, "samples_mean": sum(smp) / reps, "wall_s_mean": round(sum(wall) / reps, 3)}
+            rec["reference_cpu"] = {"f_median": statistics.median(fs) if fs else None, "f_best": min(fs) if fs else None,
+                                    "plans_found": len(fs), "expanded_mean": sum(exp) / reps, "samples_mean": sum(smp) / reps,
+                                    "expansions_per_s": sum(exp) / sum(wall), "wall_s_mean": round(sum(wall) / reps, 3)}
+        h.set_world(world)
+        fs, exp, smp, wall, hits, batches = [], [], [], [], [], []
+        for _ in range(reps):
+            plan, st = h.plan(st0, budget_s, initial_samples=initial)
+            wall.append(st["wall_seconds"])
+            if len(plan):
+                fs.append(st["plan_f"])
+            exp.append(st["expanded"])
+            smp.append(st["samples"])
+            hits.append(st["frontier_hits"])
+            batches.append(st["engine_batches"])
+        rec["engine"] = {"f_median": statistics.median(fs) if fs else None, "f_best": min(fs) if fs else None, "plans_found": len(fs),
+                         "expanded_mean": sum(exp) / reps, "samples_mean": sum(smp) / reps, "expansions_per_s": sum(exp) / sum(wall),
+                         "frontier_hit_rate": sum(hits) / max(1, sum(exp)), "engine_batches_mean": sum(batches) / reps,
+                         "wall_s_mean": round(sum(wall) / reps, 3)}
+        if ref is not None and rec["reference_cpu"]["expansions_per_s"] > 0:
+            rec["expansions_per_s_ratio"] = rec["engine"]["expansions_per_s"] / rec["reference_cpu"]["expansions_per_s"]
         out["scenarios"].append(rec)
     return out
+
+
+def scenario_world(s):
+    """Scenario s of BASELINE configs[4]: a C3-style world (C2 map and ribbons, 50 Gaussian obstacles from seed 100 + s)
+    and a start state drawn from seed 1000 + s."""
+    from path_planner_b200 import synth
+    w = synth.world_c2()
+    w.name = "scenario-%d" % s
+    synth._add_obstacles(w, "gaussian", 50, 300.0, 700.0, 100 + s)
+    rng = np.random.default_rng(1000 + s)
+    start = np.array([rng.uniform(385, 595), rng.uniform(385, 615), rng.uniform(0, 2 * np.pi), 2.5, 1.0])
+    return w, start
+
+
+def scenario_sweep(n_scenarios, rank, world_size, device, tick):
+    """Independent planning scenarios sharded over the ranks (scenario s -> rank s mod N, replicas only): each one is a
+    whole Planner::plan call of the product harness on a virtual clock (0.95 s budget, `tick` s per now() call), so
+    the work per scenario is deterministic.  Returns (wall seconds of this rank, expansions, [(s, f)])."""
+    from path_planner_b200 import harness as ph
+    from path_planner_b200 import sharding
+    h = ph.PlanningHarness(device)
+    out, expanded = [], 0
+    t0 = time.perf_counter()
+    for s in sharding.scenario_assignment(n_scenarios, rank, world_size):
+        w, start = scenario_world(s)
+        h.set_world(w)
+        plan, st = h.plan(start, 0.95, clock0=1000.0, tick=tick)
+        out.append((s, st["plan_f"] if len(plan) else float("inf")))
+        expanded += st["expanded"]
+    return time.perf_counter() - t0, expanded, out
 
 
 def dubins_rate(eng, torch, dev, sh, n=1 << 22, steps=5):
@@ -241,18 +296,19 @@ def dubins_rate(eng, torch, dev, sh, n=1 << 22, steps=5):
     return n * steps / (a.elapsed_time(b) * 1e-3)
 
 
-def measured_traffic(workload, n):
-    """DRAM bytes of one k2_true_cost launch from the committed `ncu --set full` capture of this very command
-    (profiles/r01_k2_traffic.json), or None when the capture is for another workload / batch size."""
+def ncu_metrics(workload, n):
+    """fp64 pipe utilisation (time-weighted over the kernels of one step) and DRAM bytes per step from the committed
+    `ncu --set full` captures of this very command (profiles/r02_ncu_metrics.json, written by tools/ncu_summary.py), or
+    {} when there is no capture for this workload / batch size."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")) as f:
             t = json.load(f)
         for rec in t.get("captures", []):
             if rec.get("workload") == workload and rec.get("edges") == n:
-                return rec.get("dram_bytes_read", 0) + rec.get("dram_bytes_write", 0)
+                return rec
     except (OSError, ValueError):
         pass
-    return None
+    return {}
 
 
 def run_reference(args, world, edges_fn):
@@ -267,13 +323,13 @@ def run_reference(args, world, edges_fn):
     else:
         world.upload(w)
     cores = os.cpu_count() or 1
-    edges = edges_fn(0)
+    edges = edges_fn(0, 1)
     probe = edges[:1024]
     t0 = time.perf_counter()
     common.true_cost_mt(w, probe, 0)
     rate = len(probe) / (time.perf_counter() - t0)
     total_steps = args.steps + args.warmup
-    n = int(max(1024, min(len(edges), rate * (120.0 / total_steps))))
+    n = int(max(1024, min(len(edges), rate * (100.0 / total_steps))))
     sample = edges[:n]
     for _ in range(args.warmup):
         common.true_cost_mt(w, sample, 0)
@@ -282,18 +338,58 @@ def run_reference(args, world, edges_fn):
         common.true_cost_mt(w, sample, 0)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
+    # north_star's stated baseline is the SINGLE-threaded planner: time that too, on a smaller sample
+    rate1, _, n1, dt1 = cpu_rate(world, edges, 10.0, 1)
     line = {
         "impl": "reference", "metric": "dubins_edge_true_cost_evals_per_sec", "value": value, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload], "edges_per_gpu": args.edges,
-                   "note": "CPU arm: each step evaluates a bounded sample of the same edge batch"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload], "edges_total": args.edges if args.scaling == "strong" else args.edges * args.gpus,
+                   "note": "CPU arm: each step evaluates a bounded sample of the same edge batch on all host threads"},
         "cpu_baseline": {"value": value, "unit": "edges/s", "cores": cores, "kind": kind,
                          "sample": "%d edges of the %d-edge batch per step, %d host threads" % (n, len(edges), cores)},
+        "cpu_baseline_1thread": {"value": rate1, "unit": "edges/s", "cores": 1, "kind": kind,
+                                 "sample": "first %d edges of the same batch, single thread, %.1f s" % (n1, dt1)},
         "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def measure(torch, eng, world, edges, steps, warmup, stream, after_step=None):
+    """Device-timed steps of one resident batch through ppe_true_cost_batch_device.  Returns a dict of timings and
+    the per-batch work counters read back from the result records."""
+    from path_planner_b200 import abi
+    n = len(edges)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    h_edges = torch.from_numpy(edges.view(np.uint8).reshape(n, abi.EDGE_DTYPE.itemsize)).pin_memory()
+    d_edges = h_edges.to(dev, non_blocking=True)
+    d_results = torch.empty((n, abi.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    sh = stream.cuda_stream
+    torch.cuda.synchronize()
+
+    def step():
+        eng.true_cost_batch_device(n, d_edges.data_ptr(), d_results.data_ptr(), sh)
+        if after_step is not None:
+            after_step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    return step, h_edges, d_results
+
+
+def work_counters(torch, d_results, n):
+    from path_planner_b200 import abi
+    r32 = d_results.view(torch.int32).reshape(n, abi.RESULT_DTYPE.itemsize // 4)
+    return {
+        "culled_samples": int((r32[:, 51] & 0xFFFFFF).to(torch.int64).sum().item()),   # `reserved` bits 0-23
+        "thread_walked": int(((r32[:, 51] >> 24) & 1).to(torch.int64).sum().item()),   # bit 24: walked by a K2t thread
+        "sum_samples": int(r32[:, 47].to(torch.int64).sum().item()),
+        "sum_cp": int(r32[:, 48].to(torch.int64).sum().item()),
+        "infeasible": int(r32[:, 45].to(torch.int64).sum().item()),
+        "bad_status": int((r32[:, 46] != 0).sum().item()),
+    }
 
 
 def main():
@@ -302,22 +398,30 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--edges", type=int, default=1 << 20, help="edges per GPU per step")
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--edges", type=int, default=1 << 20, help="edges of the batch (strong: in total; weak: per GPU)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU baseline sample budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--near-ribbons", type=float, default=0.0)
     ap.add_argument("--no-plan", action="store_true", help="skip the plan-cost-at-1-s-budget comparison")
     ap.add_argument("--plan-budget", type=float, default=1.0)
+    ap.add_argument("--no-extra", action="store_true", help="skip the other workloads, the scenario sweep and the Dubins line")
+    ap.add_argument("--scenarios", type=int, default=64)
+    ap.add_argument("--scenario-tick", type=float, default=4e-3, help="virtual seconds per now() call in the scenario sweep")
     args = ap.parse_args()
 
-    from path_planner_b200 import abi, synth
+    from path_planner_b200 import abi, sharding, synth
 
     world = synth.WORLDS[args.workload]()
-    n = args.edges
 
-    def edges_fn(rank):
-        return synth.make_edges(world, n, seed=5 + 1000 * rank, near_ribbons=args.near_ribbons)
+    def edges_fn(rank, world_size):
+        """This rank's edges: a shard of ONE seeded batch (strong) or the rank's own batch (weak)."""
+        if args.scaling == "strong" or world_size == 1:
+            e = synth.make_edges(world, args.edges, seed=5, near_ribbons=args.near_ribbons)
+            lo, hi = sharding.shard_range(args.edges, rank, world_size)
+            return e[lo:hi]
+        return synth.make_edges(world, args.edges, seed=5 + 1000 * rank, near_ribbons=args.near_ribbons)
 
     if args.impl == "reference":
         run_reference(args, world, edges_fn)
@@ -353,29 +457,23 @@ def main():
 
     eng = EdgeEngine(local_rank)
     set_id = world.upload(eng)
-    edges = edges_fn(rank)
+    edges = edges_fn(rank, world_size)
     edges["ribbon_set"] = set_id
+    n = len(edges)
+    lo = sharding.shard_range(args.edges, rank, world_size)[0] if args.scaling == "strong" else 0
+    n_total = args.edges if (args.scaling == "strong" or not distributed) else args.edges * world_size
 
-    # device-resident inputs / outputs (torch = plumbing: memory, streams, events)
-    h_edges = torch.from_numpy(edges.view(np.uint8).reshape(n, abi.EDGE_DTYPE.itemsize)).pin_memory()
-    d_edges = h_edges.to(dev, non_blocking=True)
-    d_results = torch.empty((n, abi.RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     best_local = torch.zeros(2, dtype=torch.float64, device=dev)  # {f64 f, i64 idx} as 16 raw bytes
     best_all = torch.zeros(2 * world_size, dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
-    torch.cuda.synchronize()
 
-    def step():
-        eng.true_cost_batch_device(n, d_edges.data_ptr(), d_results.data_ptr(), sh)
-        if distributed:
-            # the path's only exchange: one (best f, edge index) record per GPU back to the planner
-            eng.best_copy_device(best_local.data_ptr(), 0, sh)
-            dist.all_gather_into_tensor(best_all, best_local)
+    def gather_best():
+        # the path's only exchange: one (best f, GLOBAL edge index) record per GPU back to the planning rank
+        eng.best_copy_device(best_local.data_ptr(), lo, sh)
+        dist.all_gather_into_tensor(best_all, best_local)
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
+    step, h_edges, d_results = measure(torch, eng, world, edges, args.steps, args.warmup, stream, gather_best if distributed else None)
     fp64_peak = eng.measure_fp64_peak(sh) if rank == 0 else 0.0
     torch.cuda.synchronize()
 
@@ -401,15 +499,21 @@ def main():
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
+    wc = work_counters(torch, d_results, n)
 
-    # per-batch work counters from the result records (int32 columns 47 / 48 = n_samples / n_checkpoints)
-    r32 = d_results.view(torch.int32).reshape(n, abi.RESULT_DTYPE.itemsize // 4)
-    culled_chunks = int((r32[:, 51] & 0xFFFFF).to(torch.int64).sum().item())  # `reserved` low bits: chunks proved clean by the probe pass
-    thread_walked = int(((r32[:, 51] >> 20) & 1).to(torch.int64).sum().item())  # bit 20: walked by a K2t thread
-    sum_samples = int(r32[:, 47].to(torch.int64).sum().item())
-    sum_cp = int(r32[:, 48].to(torch.int64).sum().item())
-    infeasible = int(r32[:, 45].to(torch.int64).sum().item())
-    bad_status = int((r32[:, 46] != 0).sum().item())
+    gather_check = None
+    if distributed:
+        # the gathered record must be the minimum of the per-rank records, with GLOBAL edge indices
+        f_loc, i_loc = eng.best_device(sh)
+        mine = torch.tensor([f_loc if i_loc >= 0 else float("inf"), float(lo + i_loc if i_loc >= 0 else -1)], dtype=torch.float64, device=dev)
+        allr = torch.zeros(2 * world_size, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        rec = best_all.cpu().numpy().reshape(world_size, 2)
+        fs, idx = rec[:, 0].copy(), rec[:, 1].copy().view(np.int64)
+        exp = allr.cpu().numpy().reshape(world_size, 2)
+        gather_check = bool(np.array_equal(fs, exp[:, 0]) and np.array_equal(idx, exp[:, 1].astype(np.int64)))
+        if not gather_check:
+            raise SystemExit("bench.py: the NCCL-gathered best records differ from the per-rank ppe_best_device records")
 
     # ---- end to end through the public host-buffer API -----------------------------------------
     res_host = torch.empty((n, abi.RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
@@ -435,13 +539,41 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s_max = float(te.item())
 
+    # ---- BASELINE configs[4], second half: independent scenarios sharded over the ranks ----------
+    scen = None
+    if not args.no_extra and args.scenarios > 0:
+        from path_planner_b200 import harness as ph
+        if ph.available():
+            if distributed:
+                dist.barrier()
+            wall, expanded, mine = scenario_sweep(args.scenarios, rank, world_size, local_rank, args.scenario_tick)
+            costs = torch.full((args.scenarios,), float("-inf"), dtype=torch.float64, device=dev)
+            for s_, f_ in mine:
+                costs[s_] = f_
+            st = torch.tensor([wall, float(expanded)], dtype=torch.float64, device=dev)
+            if distributed:  # the gather of the 64 final plan costs: each rank filled its own slots
+                dist.all_reduce(costs, op=dist.ReduceOp.MAX)
+                tmax = st[:1].clone()
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                dist.all_reduce(st[1:], op=dist.ReduceOp.SUM)
+                st[0] = tmax[0]
+            c = costs.cpu().numpy()
+            fin = np.isfinite(c)
+            scen = {"metric": "planning_scenarios_per_sec", "value": args.scenarios / float(st[0]), "unit": "scenarios/s",
+                    "scenarios": args.scenarios, "wall_s": float(st[0]), "expanded_total": int(st[1]), "plans_found": int(fin.sum()),
+                    "f_checksum": float(c[fin].sum()), "scaling": "strong",
+                    "config": "C3-style worlds (seeds 100..), whole Planner::plan per scenario, virtual clock 0.95 s / %g s per now(); "
+                              "scenario s -> rank s mod N, replicas only" % args.scenario_tick}
+        else:
+            scen = {"unavailable": "path_planner_b200/libppe_harness.so not built"}
+
     if rank == 0:
         ms_per_step = total_ms_max / args.steps
-        value = world_size * n * args.steps / (total_ms_max * 1e-3)
+        value = n_total * args.steps / (total_ms_max * 1e-3)
         n_rib = len(world.ribbons)
         n_obs = 0 if world.obstacle_kind == "none" else len(world.obstacles["x"])
-        flops = algorithmic_flops(n, sum_samples, sum_cp, n_rib, n_obs, world.obstacle_kind)
-        kernel_s = total_ms * 1e-3 / args.steps  # rank 0's own average launch duration
+        flops = algorithmic_flops(n, wc["sum_samples"], wc["sum_cp"], n_rib, n_obs, world.obstacle_kind)
+        kernel_s = total_ms * 1e-3 / args.steps  # rank 0's own average launch-group duration
         achieved_tf = flops / kernel_s / 1e12
         peaks = {}
         try:
@@ -451,22 +583,27 @@ def main():
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        bytes_alg = algorithmic_bytes(n, sum_samples)
+        bytes_alg = algorithmic_bytes(n, wc["sum_samples"])
+        nm = ncu_metrics(args.workload, n)
         line = {
             "metric": "dubins_edge_true_cost_evals_per_sec", "value": value, "unit": "edges/s",
             "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOADS[args.workload], "edges_per_gpu": n, "edge_bytes": abi.EDGE_DTYPE.itemsize,
-                       "result_bytes": abi.RESULT_DTYPE.itemsize, "l2": "inputs+outputs (%.0f MB per GPU) larger than L2" %
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOADS[args.workload], "edges_total": n_total, "edges_rank0": n, "edge_bytes": abi.EDGE_DTYPE.itemsize,
+                       "result_bytes": abi.RESULT_DTYPE.itemsize, "l2": "inputs+outputs (%.0f MB on rank 0) larger than L2" %
                        (n * (abi.EDGE_DTYPE.itemsize + abi.RESULT_DTYPE.itemsize) / 1e6),
-                       "mean_samples_per_edge": sum_samples / n, "mean_checkpoints_per_edge": sum_cp / n,
-                       "infeasible_edges": infeasible, "edges_with_status": bad_status,
-                       "culled_sample_fraction": 32.0 * culled_chunks / max(1, sum_samples),
-                       "thread_walked_edge_fraction": thread_walked / n,
-                       "parallelism": "edges sharded over %d GPU(s), one process per GPU" % world_size},
-            "e2e": {"value": world_size * n * e2e_steps / e2e_s_max, "unit": "edges/s",
+                       "mean_samples_per_edge": wc["sum_samples"] / n, "mean_checkpoints_per_edge": wc["sum_cp"] / n,
+                       "infeasible_edges": wc["infeasible"], "edges_with_status": wc["bad_status"],
+                       "culled_sample_fraction": wc["culled_samples"] / max(1, wc["sum_samples"]),
+                       "thread_walked_edge_fraction": wc["thread_walked"] / n,
+                       "parallelism": ("one %d-edge batch split into %d contiguous shards (sharding.shard_range), one process per GPU, "
+                                       "16-byte best record all-gathered over NCCL" % (n_total, world_size)) if args.scaling == "strong" or not distributed
+                       else "one %d-edge batch per GPU, %d GPUs" % (args.edges, world_size),
+                       "best_gather_verified": gather_check},
+            "e2e": {"value": n_total * e2e_steps / e2e_s_max, "unit": "edges/s",
                     "h2d_bytes_per_step": n * abi.EDGE_DTYPE.itemsize, "d2h_bytes_per_step": n * abi.RESULT_DTYPE.itemsize + 8,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "note": "bytes are rank 0's share per step"},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {
@@ -474,17 +611,51 @@ def main():
                 "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak if fp64_peak > 0 else None,
                 "peak_source": "measured live: ppe_measure_fp64_peak (DFMA chain, 2 flop/FMA) -- MEASURED_PEAKS.json has no fp64 entry",
-                "flops_per_launch": flops, "traffic": measured_traffic(args.workload, n),
+                "flops_per_launch": flops,
+                "fp64_pipe_pct": nm.get("fp64_pipe_pct"), "traffic": nm.get("dram_bytes"),
+                "ncu_source": nm.get("source"),
                 "note": "achieved = ALGORITHMIC flops (SURVEY 8d: every executed sample point of the reference loop) / launch time; "
-                        "the kernel proves config.culled_sample_fraction of the sample points clean in 32-sample chunks and does "
-                        "not evaluate them, so frac measures work done per second in the reference's units and can exceed 1",
+                        "the kernels prove config.culled_sample_fraction of the sample points clean in 32-sample chunks and do "
+                        "not evaluate them, so frac measures work done per second in the reference's units and can exceed 1; "
+                        "fp64_pipe_pct is what the hardware's FP64 pipe was busy with (ncu, time-weighted over the step's kernels)",
                 "hbm": {"achieved": bytes_alg / kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / kernel_s / 1e9 / hbm_peak, "peak_source": hbm_src,
                         "bytes_moved_per_launch": n * (abi.EDGE_DTYPE.itemsize + abi.RESULT_DTYPE.itemsize)},
             },
         }
-        line["dubins"] = {"metric": "dubins_solves_per_sec", "value": dubins_rate(eng, torch, dev, sh), "unit": "solves/s",
-                          "n": 1 << 22, "note": "K1, one GPU, HBM-resident, correctly rounded transcendentals"}
+        if scen is not None:
+            line["scenarios"] = scen
+        if world_size == 1 and not args.no_extra:
+            # the other BASELINE configs as secondary lines: same metric, fewer steps
+            others = {}
+            for wname in ("c2", "c3", "c4"):
+                if wname == args.workload:
+                    continue
+                w2 = synth.WORLDS[wname]()
+                e2 = synth.make_edges(w2, args.edges, seed=5, near_ribbons=args.near_ribbons)
+                e2["ribbon_set"] = w2.upload(eng)
+                step2, h2, r2 = measure(torch, eng, w2, e2, 3, 2, stream)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(3):
+                    step2()
+                b.record(stream)
+                torch.cuda.synchronize()
+                ms2 = a.elapsed_time(b) / 3
+                wc2 = work_counters(torch, r2, len(e2))
+                nobs2 = 0 if w2.obstacle_kind == "none" else len(w2.obstacles["x"])
+                fl2 = algorithmic_flops(len(e2), wc2["sum_samples"], wc2["sum_cp"], len(w2.ribbons), nobs2, w2.obstacle_kind)
+                nm2 = ncu_metrics(wname, len(e2))
+                others[wname] = {"workload": WORKLOADS[wname], "value": len(e2) / (ms2 * 1e-3), "unit": "edges/s", "ms_per_step": ms2,
+                                 "steps": 3, "roofline_frac": fl2 / (ms2 * 1e-3) / 1e12 / fp64_peak if fp64_peak > 0 else None,
+                                 "culled_sample_fraction": wc2["culled_samples"] / max(1, wc2["sum_samples"]),
+                                 "thread_walked_edge_fraction": wc2["thread_walked"] / len(e2),
+                                 "fp64_pipe_pct": nm2.get("fp64_pipe_pct"), "traffic": nm2.get("dram_bytes")}
+                del step2, h2, r2
+            line["workloads"] = others
+            world.upload(eng)
+            line["dubins"] = {"metric": "dubins_solves_per_sec", "value": dubins_rate(eng, torch, dev, sh), "unit": "solves/s",
+                              "n": 1 << 22, "note": "K1, one GPU, HBM-resident, correctly rounded transcendentals"}
         if world_size == 1 and not args.no_plan:
             try:
                 line["plan"] = plan_at_budget(args.plan_budget, local_rank)

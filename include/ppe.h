@@ -126,7 +126,8 @@ typedef struct {
     int32_t n_checkpoints;      /* executions of the ribbon branch (Edge.cpp:155-171) */
     int32_t n_ribbons_after;    /* size of end()->ribbonManager().get() after the call */
     int32_t ribbons_changed;    /* 0: identical to the parent's set                   */
-    int32_t reserved;           /* engine instrumentation: 32-sample chunks skipped by the culling probe */
+    int32_t reserved;           /* engine instrumentation: bits 0-23 executed samples proved clean by the culling probe
+                                   (never evaluated one by one), bit 24 set when a K2t thread walked the edge */
 } ppe_edge_result;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

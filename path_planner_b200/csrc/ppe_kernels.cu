@@ -820,7 +820,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 nskip = nskip < to_cp ? nskip : to_cp;
                 if (nskip > 0) {
                     n_samples += nskip * kChunk;
-                    n_culled += nskip;
+                    n_culled += nskip * kChunk;
                     base += (nskip - 1) * kChunk;
                     continue;
                 }
@@ -837,7 +837,6 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             bool valid, blocked = false;
             int limit = kChunk, fstop = kChunk;
             unsigned m_stop = 0;
-            n_culled += clean ? 1 : 0;
             const double t_i = time_at_from(tt, base + lane, run, dt);
             valid = clean || (t_i < endTime);
             {
@@ -920,6 +919,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             }
 
             n_samples += limit;
+            n_culled += clean ? limit : 0;
             if (limit < kChunk) {
                 // the loop ends inside this chunk.  The iteration at sample `limit` was entered and broke
                 // out only if that sample is still inside the (possibly truncated) end time.
@@ -1039,7 +1039,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
         r->n_checkpoints = ok ? n_cp : 0;
         r->n_ribbons_after = ok ? nr : 0;
         r->ribbons_changed = (ok && modified) ? 1 : 0;
-        r->reserved = n_culled; // instrumentation: chunks the probe pass proved clean
+        r->reserved = n_culled & 0xffffff; // instrumentation: executed samples the probe pass proved clean (never evaluated)
     }
 }
 
@@ -1254,8 +1254,11 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             // per-sample work beyond the budget belongs to the warp walker (lanes = samples)
             if (more_dirty && n_exec == n_valid) heavy = true;
             n_samples = n_exec + (infeasible && n_exec < n_valid ? 1 : 0); // the breaking iteration was entered
-            const int chunks_run = (n_exec + kChunk - 1) / kChunk;           // instrumentation: clean chunks that ran
-            n_culled = __popcll(~dirty & (chunks_run >= 64 ? ~0ull : ((1ull << chunks_run) - 1ull)));
+            // instrumentation: executed samples that lie in chunks proved clean (the last chunk may be partial)
+            const int chunks_run = (n_exec + kChunk - 1) / kChunk;
+            const unsigned long long clean_run = ~dirty & (chunks_run >= 64 ? ~0ull : ((1ull << chunks_run) - 1ull));
+            n_culled = __popcll(clean_run) * kChunk;
+            if (chunks_run > 0 && ((clean_run >> (chunks_run - 1)) & 1ull)) n_culled -= chunks_run * kChunk - n_exec;
         }
 
         // ---- phase C: the ribbon check-points of the executed samples (Edge.cpp:153-172) -----------------------------------
@@ -1356,7 +1359,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     r->n_checkpoints = n_cp;
     r->n_ribbons_after = nr;
     r->ribbons_changed = 0;
-    r->reserved = n_culled | (1 << 20); // instrumentation: culled chunks; bit 20 = walked by a thread (K2t)
+    r->reserved = (n_culled & 0xffffff) | (1 << 24); // instrumentation: culled samples; bit 24 = walked by a thread (K2t)
 }
 
 // K2a: one thread per edge

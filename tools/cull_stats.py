@@ -9,8 +9,8 @@ for name, near in [("c1", 0.0), ("c2", 0.0), ("c2", 0.6), ("c3", 0.0), ("c3b", 0
     edges = synth.make_edges(world, 20000, seed=5, near_ribbons=near)
     edges["ribbon_set"] = world.upload(eng)
     r = eng.true_cost_batch(edges)
-    who = (r["reserved"] >> 20) & 3   # 1: K2t thread walker, 2: K2h heavy thread walker, 0: K2b warp walker
-    culled = r["reserved"] & 0xFFFFF
+    who = (r["reserved"] >> 24) & 1   # 1: K2t thread walker, 2: K2h heavy thread walker, 0: K2b warp walker
+    culled = r["reserved"] & 0xFFFFFF
     ch = np.ceil(r["n_samples"] / 32)
     hv = who != 1
     print("%-4s near %.1f: chunks/edge %.1f culled %.3f  check-points/edge %.2f  walked by K2t %.3f K2h %.3f K2b %.4f  (not K2t: changed %.3f, mean cps %.1f)" % (

@@ -25,7 +25,7 @@ for name, near, n, seed in [("c1", 0.3, 60000, 101), ("c2", 0.0, 150000, 102), (
     bad = common.diff_results(got, want)
     nbad = len(set().union(*[set(v.tolist()) for v in bad.values()])) if bad else 0
     bad_total += nbad
-    who = (got["reserved"] >> 20) & 1
+    who = (got["reserved"] >> 24) & 1
     print("%-4s near %.1f n %6d: mismatching edges %d %s | oracle %.1f s, engine %.3f s | K2t %.3f, infeasible %.3f, changed %.3f" % (
         name, near, n, nbad, sorted(bad.keys()) if bad else "", t1 - t0, t2 - t1, who.mean(), got["infeasible"].mean(), got["ribbons_changed"].mean()), flush=True)
     if bad:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PPE_ABI_VERSION 2
+#define PPE_ABI_VERSION 3
 
 typedef struct ppe_ctx ppe_ctx;
 
@@ -48,8 +48,9 @@ enum { PPE_LSL = 0, PPE_LSR = 1, PPE_RSL = 2, PPE_RSR = 3, PPE_RLR = 4, PPE_LRL 
 /* error codes of the dubins library (dubins.h), reported per solve in ppe_dubins_batch */
 enum { PPE_EDUBOK = 0, PPE_EDUBCOCONFIGS = 1, PPE_EDUBPARAM = 2, PPE_EDUBBADRHO = 3, PPE_EDUBNOPATH = 4 };
 
-/* RibbonManager::Heuristic (RibbonManager.h:19-25).  Only MaxDistance is evaluated on the
- * device; for the TSP variants the engine returns h = -1 and the host adapter calls the
+/* RibbonManager::Heuristic (RibbonManager.h:19-25).  MaxDistance and the two point-robot TSP
+ * variants (RibbonManager.cpp:53-95; lists of up to 8 ribbons) are evaluated on the device; for the
+ * Dubins TSP variants (and longer lists) the engine returns h = -1 and the host adapter calls the
  * reference's Vertex::computeApproxToGo on the returned ribbon set. */
 enum {
     PPE_H_MAX_DISTANCE = 0,
@@ -75,6 +76,8 @@ typedef struct {
     double time_penalty_factor;          /* Edge::timePenaltyFactor()                 1           */
     int32_t heuristic;                   /* PPE_H_*                                               */
     int32_t branching_factor;            /* PlannerConfig::branchingFactor()          default 9   */
+    int32_t tsp_k;                       /* RibbonManager::m_K of the K-ribbon TSP heuristics (executive.cpp:391: 2) */
+    int32_t reserved0;
 } ppe_config;
 
 /* One edge = the inputs Edge::computeTrueCost reads (Edge.cpp:68-96). */

@@ -184,6 +184,43 @@ static double ribs_max_distance(const rib_t* ribs, int n, double x, double y, do
 /* ------------------------------------------------------------------------------------------- */
 /* Map::isBlocked (Map.cpp:4-6) / GridWorldMap::isBlocked (GridWorldMap.cpp:84-93)               */
 /* ------------------------------------------------------------------------------------------- */
+/* RibbonManager::tspPointRobotNoSplitAllRibbons (RibbonManager.cpp:53-67) and ...KRibbons (:69-95): depth-first over
+ * the ribbons left, both directions of each; the K variant first sorts the list it was handed with std::list::sort (stable)
+ * by "nearest end point farther than" (the comparator's own comment says it should be the other way round) and tries
+ * the first K.  `order` holds the ribbons left in list order. */
+static double ribs_tsp_point_robot(const rib_t* ribs, const int* order, int n, double soFar, double px, double py, int K, double W) {
+    int ord[64];
+    double key[64];
+    double mn = DBL_MAX;
+    int i, j, tried = 0;
+    if (n == 0) return soFar;
+    for (i = 0; i < n; i++) ord[i] = order[i];
+    if (K > 0) { /* stable insertion sort, comp(a, b) = key(a) > key(b) */
+        for (i = 0; i < n; i++)
+            key[i] = fmin(pt_distance(px, py, ribs[ord[i]].sx, ribs[ord[i]].sy), pt_distance(px, py, ribs[ord[i]].ex, ribs[ord[i]].ey));
+        for (i = 1; i < n; i++) {
+            const int o = ord[i];
+            const double kv = key[i];
+            j = i;
+            while (j > 0 && kv > key[j - 1]) { ord[j] = ord[j - 1]; key[j] = key[j - 1]; j--; }
+            ord[j] = o; key[j] = kv;
+        }
+    }
+    for (i = 0; i < n; i++) {
+        int rest[64];
+        const rib_t* r;
+        int m = 0;
+        if (K > 0 && tried++ >= K) break;
+        r = &ribs[ord[i]];
+        for (j = 0; j < n; j++) if (j != i) rest[m++] = ord[j];
+        mn = fmin(mn, ribs_tsp_point_robot(ribs, rest, m, fmax(soFar + rib_length(r) - 2 * W + pt_distance(px, py, r->sx, r->sy), 0),
+                                           r->ex, r->ey, K, W));
+        mn = fmin(mn, ribs_tsp_point_robot(ribs, rest, m, fmax(soFar + rib_length(r) - 2 * W + pt_distance(px, py, r->ex, r->ey), 0),
+                                           r->sx, r->sy, K, W));
+    }
+    return mn;
+}
+
 static int map_blocked(const oracle_ctx* c, double x, double y) {
     size_t r, col;
     if (c->map_kind == 0) return 0;
@@ -422,8 +459,15 @@ static void true_cost_one(const oracle_ctx* c, const ppe_edge* e, ppe_edge_resul
     if (cfg->heuristic == PPE_H_MAX_DISTANCE) {                                  /* Vertex.cpp:49-64, RibbonManager.cpp:28-51 */
         double d = n == 0 ? 0 : ribs_max_distance(ribs, n, r->end[0], r->end[1], W);
         r->h = d / cfg->max_speed * cfg->time_penalty_factor;
+    } else if ((cfg->heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_ALL || cfg->heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K) && n <= 8) {
+        int order[8];
+        double d;
+        for (i = 0; i < n; i++) order[i] = i;
+        d = n == 0 ? 0 : ribs_tsp_point_robot(ribs, order, n, 0, r->end[0], r->end[1],
+                                              cfg->heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K ? (cfg->tsp_k > 0 ? cfg->tsp_k : 2) : 0, W);
+        r->h = d / cfg->max_speed * cfg->time_penalty_factor;
     } else {
-        r->h = -1;
+        r->h = -1; /* Dubins TSP variants, lists longer than the device serves */
     }
     r->coverage_completed_time = cct;
     r->path_qi[0] = w.path.qi[0]; r->path_qi[1] = w.path.qi[1]; r->path_qi[2] = w.path.qi[2];

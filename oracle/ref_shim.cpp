@@ -211,7 +211,7 @@ int ref_get_obstacles(ref_ctx* ctx, double* out, int cap) {
 }
 
 int ref_put_ribbon_set(ref_ctx* ctx, int n, const double* xyxy, double coverageCompletedTime, int32_t* id) {
-    RibbonManager m(heuristicOf(ctx->cfg.heuristic), ctx->cfg.turning_radius, 2);
+    RibbonManager m(heuristicOf(ctx->cfg.heuristic), ctx->cfg.turning_radius, ctx->cfg.tsp_k > 0 ? ctx->cfg.tsp_k : 2);
     // verbatim list, as a child vertex copies its parent's (Vertex.cpp:24,32); RibbonManager::add would
     // drop ribbons shorter than 2 * RibbonWidth (RibbonManager.cpp:154-158) that a strict cover keeps
     std::list<Ribbon>& list = m.*get(ManagerRibbons());

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-PPE_ABI_VERSION = 2
+PPE_ABI_VERSION = 3
 
 # ppe_status
 PPE_OK = 0
@@ -57,6 +57,8 @@ class PpeConfig(C.Structure):
         ("time_penalty_factor", C.c_double),
         ("heuristic", C.c_int32),
         ("branching_factor", C.c_int32),
+        ("tsp_k", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
     def __init__(self, **kw):
@@ -74,6 +76,7 @@ class PpeConfig(C.Structure):
         self.time_penalty_factor = 1.0
         self.heuristic = H_MAX_DISTANCE
         self.branching_factor = 9
+        self.tsp_k = 2
         for k, v in kw.items():
             if not hasattr(self, k):
                 raise AttributeError(k)

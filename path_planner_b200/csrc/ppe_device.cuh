@@ -1,6 +1,8 @@
 // ppe_device.cuh -- device helpers shared by ppe_kernels.cu (K1-K3) and ppe_expand.cu (frontier expansion).
 #pragma once
 
+#include <float.h>
+
 #include "ppe_kernels.cuh"
 
 namespace ppe {
@@ -38,5 +40,96 @@ static __device__ __forceinline__ bool map_safe(const WorldD& w, double x, doubl
     return (word >> (c & 31)) & 1u;
 }
 
+
+// RibbonManager::tspPointRobotNoSplitAllRibbons (RibbonManager.cpp:53-67) / ...KRibbons (:69-95) for the lists of up to
+// kTspMaxRibbons ribbons a vertex holds when Executive's default heuristic is in force (executive.cpp:391; more than five
+// ribbons at the root force MaxDistance, RibbonManager.cpp:381-385).  The reference recurses with list copies; here the
+// depth-first search runs on an explicit stack.  A level holds the ribbons left IN LIST ORDER (4 bits each) -- the K variant
+// sorts the list it was handed with std::list::sort (stable) by "nearest end point farther first" (comparator :73-77) and
+// tries the first K -- so ties resolve as the reference's.  Sums and fmax / fmin run in the reference's order.
+constexpr int kTspMaxRibbons = 8;
+
+static __device__ __noinline__ double tsp_point_robot(const double4* rib, int n, double x, double y, int K, double W) {
+    struct Level {
+        unsigned long long order; // ribbons left, list order, 4 bits each
+        double soFar, px, py, mn;
+        int cnt, b;               // b: next branch = 2 * position + direction
+    };
+    Level st[kTspMaxRibbons + 1];
+    int l = 0;
+    {
+        unsigned long long o = 0;
+        for (int i = 0; i < n; i++) o |= (unsigned long long)i << (4 * i);
+        st[0].order = o; st[0].cnt = n; st[0].soFar = 0; st[0].px = x; st[0].py = y; st[0].mn = DBL_MAX; st[0].b = -1;
+    }
+    double ret = 0;
+    for (;;) {
+        Level& L = st[l];
+        if (L.b < 0) { // entering the level
+            if (L.cnt == 0) { // :54 / :71: nothing left
+                ret = L.soFar;
+                if (l == 0) return ret;
+                l--;
+                st[l].mn = fmin(st[l].mn, ret);
+                continue;
+            }
+            if (K > 0) { // ribbonsLeft.sort(comp), stable
+                int ord[kTspMaxRibbons];
+                double key[kTspMaxRibbons];
+                for (int i = 0; i < L.cnt; i++) {
+                    ord[i] = (int)((L.order >> (4 * i)) & 15ull);
+                    const double4 r = rib[ord[i]];
+                    key[i] = fmin(sqrt((L.px - r.x) * (L.px - r.x) + (L.py - r.y) * (L.py - r.y)),
+                                  sqrt((L.px - r.z) * (L.px - r.z) + (L.py - r.w) * (L.py - r.w)));
+                }
+                for (int i = 1; i < L.cnt; i++) {
+                    const int o = ord[i];
+                    const double kv = key[i];
+                    int j = i;
+                    while (j > 0 && kv > key[j - 1]) { ord[j] = ord[j - 1]; key[j] = key[j - 1]; j--; }
+                    ord[j] = o; key[j] = kv;
+                }
+                unsigned long long o2 = 0;
+                for (int i = 0; i < L.cnt; i++) o2 |= (unsigned long long)ord[i] << (4 * i);
+                L.order = o2;
+            }
+            L.mn = DBL_MAX;
+            L.b = 0;
+        }
+        const int pos = L.b >> 1, dir = L.b & 1;
+        const int limit = (K > 0 && K < L.cnt) ? K : L.cnt;
+        if (pos >= limit) { // all branches of this level done
+            ret = L.mn;
+            if (l == 0) return ret;
+            l--;
+            st[l].mn = fmin(st[l].mn, ret);
+            continue;
+        }
+        L.b++;
+        const int ri = (int)((L.order >> (4 * pos)) & 15ull);
+        const double4 r = rib[ri];
+        const double len = sqrt((r.z - r.x) * (r.z - r.x) + (r.w - r.y) * (r.w - r.y)); // Ribbon::length()
+        const double tx = dir == 0 ? r.x : r.z, ty = dir == 0 ? r.y : r.w;             // the end approached first
+        const double d = sqrt((L.px - tx) * (L.px - tx) + (L.py - ty) * (L.py - ty));
+        Level& C2 = st[l + 1];
+        const unsigned long long low = L.order & ((1ull << (4 * pos)) - 1ull);
+        const unsigned long long high = pos + 1 < 16 ? (L.order >> (4 * (pos + 1))) : 0ull;
+        C2.order = low | (high << (4 * pos));
+        C2.cnt = L.cnt - 1;
+        C2.soFar = fmax(L.soFar + len - 2 * W + d, 0.0);
+        C2.px = dir == 0 ? r.z : r.x; C2.py = dir == 0 ? r.w : r.y; // leave from the other end
+        C2.b = -1;
+        l++;
+    }
+}
+
+// Vertex::computeApproxToGo (Vertex.cpp:49-64) for the heuristics the device evaluates besides MaxDistance; -1 otherwise
+static __device__ __forceinline__ double tsp_heuristic_or_unset(const ppe_config& cfg, const double4* rib, int nr, double x, double y) {
+    const bool pr = cfg.heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_ALL || cfg.heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K;
+    if (!pr || nr > kTspMaxRibbons) return -1.0;
+    const int K = cfg.heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K ? (cfg.tsp_k > 0 ? cfg.tsp_k : 2) : 0;
+    const double d = nr == 0 ? 0.0 : tsp_point_robot(rib, nr, x, y, K, cfg.ribbon_width);
+    return d / cfg.max_speed * cfg.time_penalty_factor;
+}
 
 } // namespace ppe

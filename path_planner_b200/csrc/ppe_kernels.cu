@@ -697,6 +697,78 @@ __device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, co
     *safe_out = probe_one(*wp, pe, t_first, t_mid, t_last, s_obs, end_time, rad, edge_mask, mask_out);
 }
 
+// ---- check-point fast path of the warp walker ---------------------------------------------------------------------------
+// An edge that runs along a survey line executes a check-point at EVERY sample (toCoverDistance is 0 inside a ribbon),
+// hundreds in a row, and each one only moves the start of the one ribbon it is on (Ribbon::split returns a piece too
+// short to keep, RibbonManager.cpp:14-22).  The general check-point (warp_checkpoint) walks all R ribbons with lanes,
+// ballots and a prefix sum per check-point.  The fast path does the same arithmetic for the few ribbons that can be
+// touched at all in this chunk of 32 samples -- those whose bounding box, grown by the ribbon width, meets the bounding
+// box of the chunk's poses -- as uniform scalar work, and updates the ribbon in place.  It applies only when it can
+// prove the outcome equals the general one: some relevant ribbon contains the point (so minDistanceFrom is 0 whatever
+// the other ribbons are), no ribbon of the list is short enough to be erased by cover() regardless of containment,
+// and the split leaves the list's structure alone (piece dropped, remainder kept).  Anything else takes the general path.
+constexpr int kRelCap = 8;
+
+// ribbons of the list that any pose inside [x0, x1] x [y0, y1] could be contained in; -1 when more than kRelCap
+__device__ __noinline__ int relevant_ribbons(const double4* cur, int nr, double x0, double x1, double y0, double y1, double W,
+                                              int lane, int* rel) {
+    const double grow = W * (1 + 1e-9) + 2e-3;
+    int n = 0;
+#pragma unroll 1
+    for (int base = 0; base < nr; base += 32) {
+        const int r = base + lane;
+        bool near = false;
+        if (r < nr) {
+            const RibbonD rb = load_ribbon(cur + r);
+            near = !(x1 < fmin(rb.sx, rb.ex) - grow || x0 > fmax(rb.sx, rb.ex) + grow || y1 < fmin(rb.sy, rb.ey) - grow ||
+                     y0 > fmax(rb.sy, rb.ey) + grow);
+        }
+        unsigned m = __ballot_sync(kFull, near);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (n < kRelCap && lane == 0) rel[n] = base + b;
+            n++;
+        }
+    }
+    __syncwarp();
+    return n <= kRelCap ? n : -1;
+}
+
+// One check-point on the relevant ribbons only (uniform across the warp).  Returns true when it handled the check-point
+// (minDistanceFrom == 0, cover applied in place); false = nothing was modified, take the general path.
+__device__ __noinline__ bool fast_checkpoint(double4* cur, const int* rel, int n_rel, double x, double y, double W, bool do_cover,
+                                                bool tame, int lane, bool* changed) {
+    bool inside = false;
+    int upd = -1;          // at most one in-place update per check-point on this path
+    double upx = 0, upy = 0;
+    bool ch = false;
+#pragma unroll 1
+    for (int q = 0; q < n_rel; q++) {
+        const int r = rel[q];
+        const RibbonD rb = load_ribbon(cur + r);
+        if (!ribbon_may_contain(rb, x, y, W, tame)) continue;
+        double px, py;
+        ribbon_projection(rb, x, y, &px, &py);
+        if (!ribbon_contains_projection(rb, px, py)) continue;
+        const double d = ribbon_distance(rb, x, y);
+        inside = inside || (d < W);
+        if (do_cover && d < W / 2.0) {
+            RibbonD piece = {rb.sx, rb.sy, px, py};
+            RibbonD rest = {px, py, rb.ex, rb.ey};
+            if (!ribbon_covered(piece, true, W) || ribbon_covered(rest, true, W)) return false; // the list's structure changes
+            if (upd >= 0) return false;                                                           // two ribbons at once: general path
+            upd = r; upx = px; upy = py;
+            ch = (px != rb.sx) || (py != rb.sy);
+        }
+    }
+    if (!inside) return false; // minDistanceFrom needs the nearest end point over the whole list
+    if (upd >= 0 && lane == 0) cur[upd] = pack_ribbon(upx, upy, cur[upd].z, cur[upd].w);
+    __syncwarp();
+    *changed = ch;
+    return true;
+}
+
 // One edge, one warp.  Per-edge scalars that every lane would hold identically live in the warp's
 // shared-memory copy of the prepared record (`pe`) and in the time table (`tt`).  The sample loop of
 // Edge.cpp:125-175 runs in chunks of 32 consecutive samples:
@@ -708,7 +780,7 @@ __device__ __noinline__ void probe_chunks(const WorldD* wp, const double* pe, co
 // back the pose of a sample index either from the lanes (shuffle) or by direct evaluation.
 __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* __restrict__ edge,
                              const PreparedEdge* __restrict__ prep, ppe_edge_result* __restrict__ result,
-                             const ObstacleD* s_obs, double4* bufA, double4* bufB, double* pe, TimeTable* tt, int lane) {
+                             const ObstacleD* s_obs, double4* bufA, double4* bufB, double* pe, TimeTable* tt, int* rel, int lane) {
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width;
     const double inc = cfg.collision_checking_increment;
@@ -734,11 +806,18 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
     __syncwarp();
     if (status == PPE_EDGE_OK && pe[kStatus] != 0.0) status = (int)pe[kStatus];
     bool tame;
+    bool any_short; // some ribbon of the list is short enough for cover() to erase it wherever the point is
     {
         bool t_ = fabs(pe[kX0]) + fabs(pe[kLength]) < 1e7 && fabs(pe[kY0]) + fabs(pe[kLength]) < 1e7 && fabs(edge->src[0]) < 1e7 &&
                   fabs(edge->src[1]) < 1e7;
-        for (int r = lane; r < nr; r += 32) t_ = t_ && coords_tame(load_ribbon(bufA + r));
+        bool s_ = false;
+        for (int r = lane; r < nr; r += 32) {
+            const RibbonD rb = load_ribbon(bufA + r);
+            t_ = t_ && coords_tame(rb);
+            s_ = s_ || ribbon_covered(rb, true, W);
+        }
         tame = __all_sync(kFull, t_);
+        any_short = __any_sync(kFull, s_);
     }
 
     const double src_t = edge->src[4];
@@ -854,6 +933,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             }
 
             // ---- ribbon check-points of this chunk, in order (Edge.cpp:153-172) ---------------------------------
+            int n_rel = -2; // relevant-ribbon list of this chunk: -2 not built yet, -1 too many, else count
             while (next_cp < base + limit) {
                 const int l = next_cp - base;
                 if (nr == 0 && cct != -1 && !(cct + cfg.time_minimum < endTime)) {
@@ -886,11 +966,28 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 }
                 double toCover;
                 bool changed = false;
-                const int nn = warp_checkpoint(cur, alt, nr, cap, cx, cy, W, do_cover, tame, lane, &toCover, &changed, &overflow);
-                if (changed) {
-                    double4* tmp = cur; cur = alt; alt = tmp;
-                    nr = nn;
-                    modified = true;
+                bool handled = false;
+                if (tame && !any_short && nr > 0) {
+                    if (n_rel == -2) { // relevant ribbons of this chunk: bounding box of the chunk's executed poses
+                        const bool in = lane < limit;
+                        const double bx0 = warp_min(in ? x : DBL_MAX), bx1 = warp_max(in ? x : -DBL_MAX);
+                        const double by0 = warp_min(in ? y : DBL_MAX), by1 = warp_max(in ? y : -DBL_MAX);
+                        n_rel = relevant_ribbons(cur, nr, bx0, bx1, by0, by1, W, lane, rel);
+                    }
+                    if (n_rel > 0) handled = fast_checkpoint(cur, rel, n_rel, cx, cy, W, do_cover, tame, lane, &changed);
+                }
+                if (handled) {
+                    toCover = 0.0;
+                    if (changed) modified = true;
+                } else {
+                    const int nn = warp_checkpoint(cur, alt, nr, cap, cx, cy, W, do_cover, tame, lane, &toCover, &changed, &overflow);
+                    if (do_cover) any_short = false; // cover() erased every ribbon short enough, contained or not
+                    if (changed) {
+                        double4* tmp = cur; cur = alt; alt = tmp;
+                        nr = nn;
+                        modified = true;
+                        n_rel = -2; // indices moved
+                    }
                 }
                 if (nr == 0) {
                     if (cct == -1) cct = ct;
@@ -993,7 +1090,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             const double d = nr == 0 ? 0.0 : warp_max_distance(cur, nr, ex, ey, W, lane, (double*)alt);
             h = d / cfg.max_speed * cfg.time_penalty_factor;
         } else {
-            h = -1;
+            h = tsp_heuristic_or_unset(cfg, cur, nr, ex, ey); // point-robot TSP variants; -1: left to the host
         }
         if (overflow) status = PPE_EDGE_ERR_RIBBON_CAPACITY;
         else if (sample_fault) status = PPE_EDGE_ERR_END_SAMPLE;
@@ -1335,8 +1432,9 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     const double T = fmax(netTime - 0.0, 0.0);
     const double true_cost = T * cfg.time_penalty_factor + penalty;
     const double g = edge->src_g + true_cost;
-    double h = -1;
+    double h;
     if (cfg.heuristic == PPE_H_MAX_DISTANCE) h = seq_max_distance(rib, nr, ex, ey, W) / cfg.max_speed * cfg.time_penalty_factor;
+    else h = tsp_heuristic_or_unset(cfg, rib, nr, ex, ey);
     ppe_edge_result* r = results + ei;
     r->true_cost = true_cost;
     r->collision_penalty = penalty;
@@ -1388,6 +1486,7 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
     double4* bufB = bufA + w.ribbon_cap;
     __shared__ double s_pe[kWarpsPerBlock][kPrepDoubles];
     __shared__ TimeTable s_tt[kWarpsPerBlock];
+    __shared__ int s_rel[kWarpsPerBlock][kRelCap];
     double* pe = s_pe[warp];
 
     const unsigned long long n_front = heavy_list ? (unsigned long long)heavy_count[0] : 0ull;
@@ -1407,7 +1506,7 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
         k = __shfl_sync(kFull, k, 0);
         if (k >= todo) break;
         const unsigned long long ei = !heavy_list ? k : (unsigned long long)(k < n_front ? heavy_list[k] : heavy_list[n - 1 - (k - n_front)]);
-        process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], lane);
+        process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], s_rel[warp], lane);
         __syncwarp();
     }
 }

@@ -70,7 +70,9 @@ struct K2Tuning {
 };
 K2Tuning clamp_tuning(K2Tuning t);
 // heuristics other than MaxDistance that the kernels evaluate themselves (h >= 0 in the result records)
-inline bool tsp_on_device(int heuristic) { (void)heuristic; return false; }
+inline bool tsp_on_device(int heuristic) {
+    return heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_ALL || heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K;
+}
 
 // ---- frontier expansion (ppe_expand.cu) ------------------------------------------------------------------------------
 struct ExpandParamsD {

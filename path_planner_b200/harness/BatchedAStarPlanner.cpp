@@ -50,6 +50,7 @@ PPE_ACCESS(VertexH, Vertex, double, m_ApproxToGo)
 PPE_ACCESS(RibbonList, RibbonManager, std::list<Ribbon>, m_Ribbons)
 PPE_ACCESS(RibbonHeuristic, RibbonManager, RibbonManager::Heuristic, m_Heuristic)
 PPE_ACCESS(RibbonCct, RibbonManager, double, m_CoverageCompletedTime)
+PPE_ACCESS(RibbonK, RibbonManager, int, m_K)
 PPE_ACCESS(OpenList, SamplingBasedPlanner, std::vector<std::shared_ptr<Vertex>>, m_VertexQueue)
 #undef PPE_ACCESS
 
@@ -90,8 +91,12 @@ void BatchedAStarPlanner::uploadWorld(const RibbonManager& ribbonManager, const 
     RibbonManager::Heuristic h = ribbonManager.*get(RibbonHeuristic());
     if (ribbonManager.get().size() > 5) h = RibbonManager::MaxDistance;
     m_Heuristic = heuristicId(h);
-    m_HOnDevice = m_Heuristic == PPE_H_MAX_DISTANCE;
+    // MaxDistance and the point-robot TSP variants are evaluated by the kernels (h >= 0 in the results; -1 = not evaluated)
+    m_HOnDevice = m_Heuristic == PPE_H_MAX_DISTANCE || m_Heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_ALL ||
+                  m_Heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K;
     c.heuristic = m_Heuristic;
+    c.tsp_k = (m_Heuristic == PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K || m_Heuristic == PPE_H_TSP_DUBINS_NO_SPLIT_K) ? ribbonManager.*get(RibbonK()) : 0;
+    c.reserved0 = 0;
     check(ppe_set_config(m_Ctx, &c), "ppe_set_config");
 
     // static map: rasterise Map::isBlocked at cell centres (GridWorldMap cells are res x res squares).  The Executive
@@ -227,8 +232,8 @@ void BatchedAStarPlanner::fillChild(const std::shared_ptr<Vertex>& v, const doub
         for (int k2 = 0; k2 < nRibbons; k2++) list.emplace_back(ribbons[4 * k2], ribbons[4 * k2 + 1], ribbons[4 * k2 + 2], ribbons[4 * k2 + 3]);
     }
     rm.*get(RibbonCct()) = cct;
-    if (m_HOnDevice) (*v).*get(VertexH()) = h;
-    else v->computeApproxToGo(m_Config); // heuristics the engine does not evaluate stay on the host (RibbonManager.cpp:53-140)
+    if (m_HOnDevice && h >= 0) (*v).*get(VertexH()) = h;
+    else v->computeApproxToGo(m_Config); // what the engine does not evaluate stays on the host (Dubins TSP variants, long lists)
     if (m_Config.visualizations()) dumpTrajectory(v);
 }
 

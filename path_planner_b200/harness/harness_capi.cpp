@@ -181,7 +181,7 @@ int pph_set_obstacles_gaussian(pph_ctx* ctx, int n, const double* x, const doubl
 
 int pph_set_ribbons(pph_ctx* ctx, int n, const double* xyxy) {
     if (!ctx || n < 0 || (n > 0 && !xyxy)) return PPE_ERR_INVALID;
-    ctx->ribbons = RibbonManager(heuristicOf(ctx->cfg.heuristic), ctx->cfg.turning_radius, 2); // executive.cpp:391
+    ctx->ribbons = RibbonManager(heuristicOf(ctx->cfg.heuristic), ctx->cfg.turning_radius, ctx->cfg.tsp_k > 0 ? ctx->cfg.tsp_k : 2); // executive.cpp:391
     for (int i = 0; i < n; i++) ctx->ribbons.add(xyxy[4 * i], xyxy[4 * i + 1], xyxy[4 * i + 2], xyxy[4 * i + 3]);
     return PPE_OK;
 }

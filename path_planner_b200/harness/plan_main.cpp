@@ -53,6 +53,7 @@ int main(int argc, char** argv) {
     cfg.ribbon_width = 2; cfg.collision_penalty_factor = 600; cfg.time_penalty_factor = 1;
     cfg.heuristic = PPE_H_TSP_POINT_ROBOT_NO_SPLIT_K; // Executive's default (executive.cpp:391)
     cfg.branching_factor = 9;
+    cfg.tsp_k = 2;
     std::string mapKind = "none", mapFile;
     std::vector<double> ribbons, bin[7], gau[5];
     double start[5] = {0, 0, 0, 2.5, 1};

@@ -24,6 +24,8 @@ CASES = [
     # Executive's default heuristic (executive.cpp:391, TspPointRobotNoSplitKRibbons) on <= 5 ribbons: the engine returns
     # h = -1 and the adapter calls the reference's Vertex::computeApproxToGo on the returned ribbon set
     ("c1-tsp-heuristic", "c1-tsp", None, 0.95, 2e-3, 100),
+    # three ribbons, K-ribbon TSP heuristic, static obstacles: h comes from the device (lists of up to 8 ribbons)
+    ("c2-tsp-3-ribbons", "c2-tsp3", (395.0, 390.0, 0.3, 2.5, 1.0), 0.95, 4e-3, 100),
 ]
 CASE_IDS = [c[0] for c in CASES]
 
@@ -49,6 +51,11 @@ def make_world(wname):
         world = synth.world_c1()
         world.cfg.heuristic = abi.H_TSP_POINT_ROBOT_NO_SPLIT_K
         world.ribbons = np.array([[0.0, 10.0, 0.0, 30.0], [6.0, 30.0, 6.0, 10.0]])
+        return world
+    if wname == "c2-tsp3":
+        world = synth.world_c2()
+        world.cfg.heuristic = abi.H_TSP_POINT_ROBOT_NO_SPLIT_K
+        world.ribbons = world.ribbons[:3].copy()
         return world
     return synth.WORLDS[wname]()
 

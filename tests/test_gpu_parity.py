@@ -140,6 +140,20 @@ def test_map_resolutions(engine, oracle, oracle_glibc, name, res, near, n):
     _vs_glibc_reference(engine, oracle_glibc, world, edges, got, world.name)
 
 
+@pytest.mark.parametrize("heuristic", [abi.H_TSP_POINT_ROBOT_NO_SPLIT_K, abi.H_TSP_POINT_ROBOT_NO_SPLIT_ALL])
+@pytest.mark.parametrize("n_ribbons", [1, 3, 5])
+def test_tsp_heuristics_on_device(engine, oracle, oracle_glibc, heuristic, n_ribbons):
+    """Executive's default heuristic (TspPointRobotNoSplitKRibbons, K = 2, executive.cpp:391) and the all-ribbons variant
+    are evaluated by the kernels on the ribbons-after of every edge (RibbonManager.cpp:53-95): h within 1e-9, and the
+    prune record of ppe_best is available for them."""
+    from tests.test_oracle_vs_ref import tsp_world
+    world = tsp_world(heuristic, n_ribbons)
+    edges = synth.make_edges(world, 2500, seed=15, near_ribbons=0.7)
+    got, want = _check_batch(engine, oracle, world, edges)
+    assert (got["h"] >= 0).all() and want["n_ribbons_after"].max() > n_ribbons
+    _vs_glibc_reference(engine, oracle_glibc, world, edges, got, world.name)
+
+
 def test_non_default_covariances(engine, oracle, oracle_glibc):
     """Per-obstacle SPD covariances instead of the manager default (GaussianDynamicObstaclesManager.h:24-25,39-44)."""
     for base in ("c3", "c5"):

@@ -78,6 +78,36 @@ def test_oracle_is_bit_identical_on_epoch_times_resolutions_and_covariances(key)
     assert want["ribbons_changed"].sum() > 0 and (want["infeasible"] == 1).any()
 
 
+def tsp_world(heuristic, n_ribbons):
+    """C2 with its first n ribbons and one of the point-robot TSP heuristics (Executive installs the K variant with K = 2,
+    executive.cpp:391; more than five ribbons would force MaxDistance, RibbonManager.cpp:381-385)."""
+    w = synth.world_c2()
+    w.cfg.heuristic = heuristic
+    w.ribbons = w.ribbons[:n_ribbons].copy()
+    w.name = "C2-tsp%d-%dr" % (heuristic, n_ribbons)
+    return w
+
+
+@needs_ref
+@pytest.mark.parametrize("heuristic", [abi.H_TSP_POINT_ROBOT_NO_SPLIT_K, abi.H_TSP_POINT_ROBOT_NO_SPLIT_ALL])
+@pytest.mark.parametrize("n_ribbons", [1, 3, 5])
+def test_oracle_tsp_heuristics_are_bit_identical_to_the_reference(heuristic, n_ribbons):
+    """h of RibbonManager::tspPointRobotNoSplitKRibbons / ...AllRibbons (RibbonManager.cpp:53-95) on the ribbons-after of
+    every edge, including lists that splits have grown to 7 ribbons."""
+    ref = common.load_ref()
+    ora = common.load_oracle("glibc")
+    world = tsp_world(heuristic, n_ribbons)
+    sid = world.upload_ref(ref)
+    assert world.upload(ora) == sid
+    edges = synth.make_edges(world, 1200, seed=12, near_ribbons=0.7)
+    edges["ribbon_set"] = sid
+    want = ref.true_cost_batch(edges)
+    got = ora.true_cost_batch(edges)
+    bad = common.diff_results(got, want, exact=True, check_counts=False)
+    assert not bad, common.describe(bad, got, want)
+    assert (got["h"] >= 0).all() and want["n_ribbons_after"].max() > n_ribbons
+
+
 @needs_ref
 def test_oracle_has_path_edges_and_dubins_match_the_reference():
     """Winner edges of expand() (pre-solved wrapper, speed change) and previous-plan style wrappers

@@ -6,10 +6,10 @@
 //   KX  k_expand_select   one CTA per vertex: (1) all threads stream the resident samples (coalesced, L2-resident
 //                         16 B per sample) and collect those inside a search radius; (2) bitonic sort by (distance,
 //                         index) = the pop order of the reference's Euclidean heap (:85-94) whenever no two popped
-//                         distances are equal; (3) warp 0 replays the loop of :91-133 on 32 candidates at a time --
-//                         lanes solve the Dubins words of the next 32 candidates x 2 radii (K1's branch-free solver),
-//                         lane 0 runs the k-best max-heaps with libstdc++'s push_heap / pop_heap arrangement -- until
-//                         both radii are done; (4) the CTA emits the vertex's edges (endpoint edges :65-81, winners x
+//                         distances are equal; (3) the loop of :91-133 is replayed on 256 candidates at a time -- every
+//                         thread solves the Dubins words of one candidate x 2 radii (K1's branch-free solver), thread 0
+//                         runs the k-best max-heaps with libstdc++'s push_heap / pop_heap arrangement -- until both radii
+//                         are done; (4) the CTA emits the vertex's edges (endpoint edges :65-81, winners x
 //                         speeds :134-149) in the reference's push order as ppe_edge records for K2.
 //                         The F x N length matrix is never materialised: only ~#popped solves happen per vertex.
 //   KP  k_expand_pack     compact child records (ppe_child, 160 B) from the K2 result records.
@@ -142,10 +142,10 @@ struct SelShared {
     KBest heap[2];
     int free_id[2]; // pool slot the next push into a full heap uses (the slot of the last evicted entry)
     Winner pool[2][kMaxBranch + 1];
-    // solves of the current 32 candidates
-    double c_len[2][32];
-    double c_par[2][32][3];
-    int c_type[2][32];
+    // solves of the current kSelThreads candidates
+    double c_len[2][kSelThreads];
+    double c_par[2][kSelThreads][3];
+    int c_type[2][kSelThreads];
     int count;
     int done[2];
     int pops;
@@ -163,7 +163,7 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
     double* const s_d = sel_dyn;                                       // [kSelCap] squared distance, then distance
     int* const s_idx = reinterpret_cast<int*>(sel_dyn + kSelCap);      // [kSelCap] resident sample index
     const int v = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const ppe_vertex vx = verts[v];
     const double sx = vx.state[0], sy = vx.state[1];
     const int N = p.n_samples;
@@ -218,7 +218,7 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
                 __syncthreads();
             }
         }
-        // ---- (3) replay of the k-nearest loop, 32 candidates per step ---------------------------------------------------------
+        // ---- (3) replay of the k-nearest loop, kSelThreads candidates per step ---------------------------------------------------------
         if (tid == 0) {
             s.heap[0].size = s.heap[1].size = 0;
             s.done[0] = s.done[1] = 0;
@@ -226,11 +226,13 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
             s.pops = 0; s.solves = 0; s.consumed = 0; s.tie = 0;
         }
         __syncthreads();
-        if (warp == 0) {
+        {
+            // every thread of the CTA solves one candidate (both radii) per step; thread 0 then replays the loop body for
+            // those kSelThreads candidates in order
             const double q0[3] = {sx, sy, heading_to_yaw(vx.state[2])};
             int pos = 0;
             while (pos < n && !(s.done[0] && s.done[1])) {
-                const int c = pos + lane;
+                const int c = pos + tid;
                 if (c < n) {
                     const int si = s_idx[c];
                     const double q1[3] = {p.sx[si], p.sy[si], heading_to_yaw(p.sh[si])};
@@ -241,14 +243,14 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
                         path.param[0] = path.param[1] = path.param[2] = 0;
                         path.type = 0;
                         const int e = dubins_shortest_path(&path, q0, q1, p.rho[j]); // Edge::computeApproxCost, Edge.cpp:11-20
-                        s.c_len[j][lane] = e == kEdubOk ? dubins_path_length(path) : 0.0;
-                        s.c_par[j][lane][0] = path.param[0]; s.c_par[j][lane][1] = path.param[1]; s.c_par[j][lane][2] = path.param[2];
-                        s.c_type[j][lane] = path.type;
+                        s.c_len[j][tid] = e == kEdubOk ? dubins_path_length(path) : 0.0;
+                        s.c_par[j][tid][0] = path.param[0]; s.c_par[j][tid][1] = path.param[1]; s.c_par[j][tid][2] = path.param[2];
+                        s.c_type[j][tid] = path.type;
                     }
                 }
-                __syncwarp();
-                if (lane == 0) {
-                    const int m = n - pos < 32 ? n - pos : 32;
+                __syncthreads();
+                if (tid == 0) {
+                    const int m = n - pos < kSelThreads ? n - pos : kSelThreads;
                     int q = 0;
                     for (; q < m && !(s.done[0] && s.done[1]); q++) { // one iteration of the loop at :91
                         const double dist = s_d[pos + q];
@@ -279,16 +281,16 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
                     }
                     s.consumed = pos + q;
                 }
-                __syncwarp();
+                __syncthreads();
                 pos = s.consumed;
             }
             // exact-distance ties inside the consumed prefix (or between the last popped and the next sample): the pop
             // order then depends on the heap arrangement of the reference's m_Samples
             int tie = 0;
             const int upto = s.consumed < n ? s.consumed : n - 1;
-            for (int q = lane; q < upto; q += 32) tie |= (s_d[q] == s_d[q + 1]) ? 1 : 0;
-            tie = __any_sync(kFullMask, tie);
-            if (lane == 0) s.tie = tie;
+            for (int q = tid; q < upto; q += kSelThreads) tie |= (s_d[q] == s_d[q + 1]) ? 1 : 0;
+            tie = __syncthreads_or(tie);
+            if (tid == 0) s.tie = tie;
         }
         __syncthreads();
         // ran out of candidates before both radii finished although more samples exist: widen the disc

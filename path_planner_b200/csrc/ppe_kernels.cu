@@ -1673,7 +1673,7 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
                              const unsigned int* heavy_count, int max_blocks, int sm_count, cudaStream_t stream) {
     const size_t smem = k2_smem_bytes(kW, world.ribbon_cap, world.n_obs);
     cudaError_t e;
-    if (smem > 48 * 1024) { // per device and per function: set it whenever it is needed rather than remembering
+    if (smem > 32 * 1024) { // per device and per function (static + dynamic must fit): set it whenever it may be needed
         e = cudaFuncSetAttribute(k2_true_cost<kW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -1714,7 +1714,7 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
     unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
     if (heavy_list) {
         const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD);
-        if (smem_t > 48 * 1024) {
+        if (smem_t > 32 * 1024) {
             e = cudaFuncSetAttribute(k2t_thread_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
             if (e != cudaSuccess) return e;
         }

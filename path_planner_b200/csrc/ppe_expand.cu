@@ -23,7 +23,7 @@ namespace ppe {
 namespace {
 
 constexpr int kSelThreads = 256;
-constexpr int kSelCap = 6144;     // candidates per pass: 48 KB distances + 24 KB indices of dynamic shared memory
+constexpr int kSelCap = 8192;     // candidates per pass (a power of two: the bitonic sort pads to one): 64 KB + 32 KB of dynamic shared memory
 constexpr int kMaxBranch = 16;    // PlannerConfig::branchingFactor() upper limit served on the device (default 9)
 constexpr unsigned kFullMask = 0xffffffffu;
 

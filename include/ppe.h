@@ -272,6 +272,11 @@ int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, int64_t index_base, void* 
  * compares it to notice uploads made by anybody else. */
 uint64_t ppe_map_generation(const ppe_ctx* ctx);
 
+/* Bounding box (metres) of the edges of the batches that follow; with PPE_MAP_TILE=1 the thread walker stages the
+ * occupancy and safe bitmaps of that box in shared memory (TMA bulk copies).  x1 <= x0 clears it.  (north_star's
+ * "map tiles around each batch's bounding box"; measured A/B in profiles/, off by default.) */
+int ppe_set_map_window(ppe_ctx* ctx, double x0, double y0, double x1, double y1);
+
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* number of engine kernels launched on this ctx since creation */
 int64_t ppe_launch_count(const ppe_ctx* ctx);

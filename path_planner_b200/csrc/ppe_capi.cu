@@ -51,7 +51,11 @@ struct ppe_ctx {
     int safe_radius = -1;           // radius d_safe was built for; -1 = stale
     int map_kind = kMapNone, rows = 0, cols = 0, stride_words = 0;
     double resolution = 1;
-    uint64_t map_generation = 0;    // bumped by every ppe_set_map_*: lets a caller-side cache notice foreign uploads
+    uint64_t map_generation = 0;
+    // N2 A/B (PPE_MAP_TILE=1): bounding box in metres of the batch about to be evaluated; empty = no tile
+    double win_x0 = 0, win_y0 = 0, win_x1 = -1, win_y1 = -1;
+    int tile_mode = 0;              // PPE_MAP_TILE
+    int l2_persist = 0;             // PPE_MAP_L2_PERSIST: persisting L2 access-policy window over the two bitmaps    // bumped by every ppe_set_map_*: lets a caller-side cache notice foreign uploads
     int obs_cull_ok = 1;
 
     // dynamic obstacles
@@ -273,6 +277,27 @@ int make_world(ppe_ctx* ctx, WorldD* w) {
         w->res_pow2 = (m == 0.5 && e > -1000 && e < 1000) ? 1 : 0;
         w->inv_resolution = 1.0 / ctx->resolution;
     }
+    // N2: shared-memory tile for the thread walker when a window is set and the tile fits
+    w->tile_on = 0;
+    if (ctx->tile_mode && safe && ctx->win_x1 > ctx->win_x0 && ctx->win_y1 > ctx->win_y0 && ctx->stride_words % 4 == 0) {
+        const double res = ctx->resolution;
+        long long r0 = (long long)floor(ctx->win_y0 / res) - 1, r1 = (long long)floor(ctx->win_y1 / res) + 1;
+        long long c0 = (long long)floor(ctx->win_x0 / res) - 1, c1 = (long long)floor(ctx->win_x1 / res) + 1;
+        if (r0 < 0) r0 = 0;
+        if (c0 < 0) c0 = 0;
+        if (r1 > ctx->rows - 1) r1 = ctx->rows - 1;
+        if (c1 > ctx->cols - 1) c1 = ctx->cols - 1;
+        if (r1 >= r0 && c1 >= c0) {
+            const long long w0 = (c0 >> 5) & ~3ll;                                   // 16-byte aligned rows
+            long long w1 = (((c1 >> 5) + 4) & ~3ll);                                 // exclusive, multiple of 4 words
+            if (w1 > ctx->stride_words) w1 = ctx->stride_words;
+            const long long rows = r1 - r0 + 1, words = w1 - w0;
+            if (words > 0 && words % 4 == 0 && 2 * rows * words * 4 <= 96 * 1024) {
+                w->tile_on = 1;
+                w->tile_r0 = (int)r0; w->tile_w0 = (int)w0; w->tile_rows = (int)rows; w->tile_words = (int)words;
+            }
+        }
+    }
     w->obs_cull_ok = ctx->obs_cull_ok;
     w->obstacles = ctx->d_obs;
     w->obs_kind = ctx->n_obs > 0 ? ctx->obs_kind : kObsNone;
@@ -320,6 +345,11 @@ int ppe_create(int device, ppe_ctx** out) {
     {
         const char* env = getenv("PPE_THREAD_WALKER");
         if (env && env[0] == '0') ctx->thread_walker = false;
+        const char* env_tile = getenv("PPE_MAP_TILE");
+        ctx->tile_mode = env_tile && env_tile[0] == '1';
+        const char* env_l2 = getenv("PPE_MAP_L2_PERSIST");
+        ctx->l2_persist = env_l2 && env_l2[0] == '1';
+        if (ctx->l2_persist) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 8u << 20);
         const char* env_cp = getenv("PPE_K2T_CPS");   // tuning knob: check-points a K2t thread may walk
         if (env_cp && atoi(env_cp) > 0) ctx->tuning.cp_budget = atoi(env_cp);
         const char* env_d = getenv("PPE_K2T_DIRTY");  // tuning knob: non-clean chunks a K2t thread may evaluate
@@ -526,6 +556,26 @@ int ppe_clear_ribbon_sets(ppe_ctx* ctx) {
     return PPE_OK;
 }
 
+int ppe_set_map_window(ppe_ctx* ctx, double x0, double y0, double x1, double y1) {
+    if (!ctx) return PPE_ERR_INVALID;
+    ctx->win_x0 = x0; ctx->win_y0 = y0; ctx->win_x1 = x1; ctx->win_y1 = y1;
+    return PPE_OK;
+}
+
+// N2 A/B: persisting L2 window over the occupancy bitmap on `stream` (the safe map is allocated right after it is built;
+// one window per stream, so the occupancy map -- read per sample in non-clean chunks -- gets it)
+static void apply_l2_window(ppe_ctx* ctx, cudaStream_t stream) {
+    if (!ctx->l2_persist || !ctx->d_map) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof v);
+    v.accessPolicyWindow.base_ptr = (void*)ctx->d_map;
+    v.accessPolicyWindow.num_bytes = (size_t)ctx->rows * ctx->stride_words * sizeof(uint32_t);
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v);
+}
+
 // ---- K1 ------------------------------------------------------------------------------------------
 int ppe_dubins_batch_device(ppe_ctx* ctx, int64_t n, const double* d_q0, const double* d_q1, const double* d_rho,
                             int32_t* d_type, double* d_param, double* d_length, int32_t* d_err, void* stream) {
@@ -597,6 +647,7 @@ int ppe_true_cost_batch_device(ppe_ctx* ctx, int64_t n, const ppe_edge* d_edges,
     ctx->have_batch = false;
     ctx->out_downloaded = false;
     if (n == 0) return PPE_OK;
+    apply_l2_window(ctx, (cudaStream_t)stream);
     return run_batch_device(ctx, w, n, d_edges, d_results, (cudaStream_t)stream);
 }
 
@@ -817,6 +868,15 @@ int ppe_expand_batch(ppe_ctx* ctx, int n, const ppe_vertex* vertices, int32_t* n
     if (!ctx->have_cfg) return fail(ctx, PPE_ERR_STATE, "ppe_set_config must be called before a batch");
     const int k = ctx->cfg.branching_factor;
     if (k < 1 || k > expand_max_branch()) return fail(ctx, PPE_ERR_CAPACITY, "ppe_expand_batch: branching factor outside [1, 16]");
+    if (ctx->tile_mode) { // every edge of the batch stays within max_speed * horizon of its vertex
+        double x0 = vertices[0].state[0], x1 = x0, y0 = vertices[0].state[1], y1 = y0;
+        for (int v = 1; v < n; v++) {
+            x0 = fmin(x0, vertices[v].state[0]); x1 = fmax(x1, vertices[v].state[0]);
+            y0 = fmin(y0, vertices[v].state[1]); y1 = fmax(y1, vertices[v].state[1]);
+        }
+        const double reach = ctx->cfg.max_speed * ctx->cfg.time_horizon + 2.0;
+        ppe_set_map_window(ctx, x0 - reach, y0 - reach, x1 + reach, y1 + reach);
+    }
     WorldD w;
     int rc = make_world(ctx, &w);
     if (rc != PPE_OK) return rc;
@@ -940,7 +1000,16 @@ const double* ppe_ribbon_pool(ppe_ctx* ctx, int64_t* n_ribbons) {
 int64_t ppe_expand_solve_count(const ppe_ctx* ctx) { return ctx ? ctx->expand_solves : 0; }
 
 int64_t ppe_launch_count(const ppe_ctx* ctx) { return ctx ? ctx->launches : 0; }
+// development builds (make prof): cycle counters of the warp walker since the last read; returns 0 entries in the shipped library
+int ppe_debug_k2b_profile(ppe_ctx* ctx, unsigned long long* out16) {
+    if (!ctx || !out16) return PPE_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    return k2b_profile_read(out16);
+}
 uint64_t ppe_map_generation(const ppe_ctx* ctx) { return ctx ? ctx->map_generation : 0; }
+
+
 
 int ppe_measure_fp64_peak(ppe_ctx* ctx, double* tflops, void* stream) {
     if (!ctx || !tflops) return PPE_ERR_INVALID;

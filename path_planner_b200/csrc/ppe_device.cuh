@@ -22,22 +22,68 @@ static __device__ __forceinline__ bool map_cell(const WorldD& w, double x, doubl
     return true;
 }
 
-static __device__ __forceinline__ bool map_blocked(const WorldD& w, double x, double y) {
+// word (r, c >> 5) of bitmap `which` (0 = occupancy, 1 = safe) from the CTA's shared-memory tile when it covers the
+// cell, else from global memory (L2-resident)
+static __device__ __forceinline__ uint32_t map_word(const WorldD& w, const uint32_t* tile, int which, unsigned long long r,
+                                                    unsigned long long c) {
+    const unsigned long long cw = c >> 5;
+    if (tile != nullptr) {
+        const long long tr = (long long)r - w.tile_r0, tw = (long long)cw - w.tile_w0;
+        if (tr >= 0 && tr < w.tile_rows && tw >= 0 && tw < w.tile_words)
+            return tile[((size_t)which * w.tile_rows + (size_t)tr) * w.tile_words + (size_t)tw];
+    }
+    const uint32_t* bits = which ? w.safe_bits : w.map_bits;
+    return __ldg(&bits[r * (unsigned long long)w.stride_words + cw]);
+}
+
+static __device__ __forceinline__ bool map_blocked(const WorldD& w, double x, double y, const uint32_t* tile = nullptr) {
     if (w.map_kind == kMapNone) return false;
     unsigned long long r, c;
     if (!map_cell(w, x, y, &r, &c)) return true; // out of bounds = blocked
-    const uint32_t word = __ldg(&w.map_bits[r * (unsigned long long)w.stride_words + (c >> 5)]);
+    const uint32_t word = map_word(w, tile, 0, r, c);
     return (word >> (c & 31)) & 1u;
 }
 
 // Chunk culling: true when every cell within the dilation radius of (x, y)'s cell is in bounds and free.
-static __device__ __forceinline__ bool map_safe(const WorldD& w, double x, double y) {
+static __device__ __forceinline__ bool map_safe(const WorldD& w, double x, double y, const uint32_t* tile = nullptr) {
     if (w.map_kind == kMapNone) return true;
     if (w.safe_bits == nullptr) return false;
     unsigned long long r, c;
     if (!map_cell(w, x, y, &r, &c)) return false;
-    const uint32_t word = __ldg(&w.safe_bits[r * (unsigned long long)w.stride_words + (c >> 5)]);
+    const uint32_t word = map_word(w, tile, 1, r, c);
     return (word >> (c & 31)) & 1u;
+}
+
+// ---- TMA bulk copy of the map tile (cp.async.bulk, completion on an mbarrier) ----------------------------------------
+static __device__ __forceinline__ void tile_stage(const WorldD& w, uint32_t* tile, unsigned long long* bar) {
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned row_bytes = (unsigned)w.tile_words * 4u;
+        const unsigned total = 2u * (unsigned)w.tile_rows * row_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(total) : "memory");
+        for (int which = 0; which < 2; which++) {
+            const uint32_t* bits = which ? w.safe_bits : w.map_bits;
+            for (int r = 0; r < w.tile_rows; r++) {
+                const uint32_t* src = bits + (size_t)(w.tile_r0 + r) * w.stride_words + w.tile_w0;
+                const unsigned dst_s = (unsigned)__cvta_generic_to_shared(tile + ((size_t)which * w.tile_rows + r) * w.tile_words);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+                             "l"(src), "r"(row_bytes), "r"(bar_s)
+                             : "memory");
+            }
+        }
+    }
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar_s)
+                     : "memory");
+    }
 }
 
 

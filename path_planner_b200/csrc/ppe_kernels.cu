@@ -643,7 +643,7 @@ __device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int
 // probes chunk m of the next 32) and the thread walker (a thread probes its edge's chunks one after the other)
 __device__ __forceinline__ bool probe_one(const WorldD& w, const double* pe, double t_first, double t_mid, double t_last,
                                           const ObstacleD* s_obs, double end_time, double rad, unsigned long long edge_mask,
-                                          unsigned long long* mask_out) {
+                                          unsigned long long* mask_out, const uint32_t* tile = nullptr) {
     const double w_start = pe[kWStart], w_speed = pe[kWSpeed];
     bool ok = (t_last < end_time) && (w_start <= t_first) && (pe[kWEnd] >= t_last);
     const double d_first = (t_first - w_start) * w_speed, d_last = (t_last - w_start) * w_speed;
@@ -658,7 +658,7 @@ __device__ __forceinline__ bool probe_one(const WorldD& w, const double* pe, dou
     ok = ok && near;
     unsigned long long mask = w.n_obs >= 64 ? ~0ull : ((1ull << w.n_obs) - 1ull); // no bound: every obstacle is a candidate
     if (near) {
-        ok = ok && map_safe(w, x, y);
+        ok = ok && map_safe(w, x, y, tile);
         if (w.obs_kind != kObsNone && w.n_obs > 0) {
             if (!w.obs_cull_ok) {
                 ok = false;
@@ -769,6 +769,20 @@ __device__ __noinline__ bool fast_checkpoint(double4* cur, const int* rel, int n
     return true;
 }
 
+// -DPPE_K2B_PROFILE (make prof -> libppe_prof.so, development only): where the warp walker's cycles go, summed over the
+// edges of a launch: [0] edges [1] total [2] probe passes [3] lane poses + map [4] fast check-points [5] general
+// check-points [6] obstacle penalties [7] tail (end state, final cover, heuristic, record) [8] fast count [9] general count
+#ifdef PPE_K2B_PROFILE
+__device__ unsigned long long g_k2b_prof[16];
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, t0) prof[slot] += clock64() - (t0)
+#define PROF_INC(slot) prof[slot] += 1
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, t0)
+#define PROF_INC(slot)
+#endif
+
 // One edge, one warp.  Per-edge scalars that every lane would hold identically live in the warp's
 // shared-memory copy of the prepared record (`pe`) and in the time table (`tt`).  The sample loop of
 // Edge.cpp:125-175 runs in chunks of 32 consecutive samples:
@@ -785,6 +799,10 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
     const double W = cfg.ribbon_width;
     const double inc = cfg.collision_checking_increment;
     const int cap = w.ribbon_cap;
+#ifdef PPE_K2B_PROFILE
+    long long prof[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+    PROF_T(t_edge);
 
     // stage the prepared record (48 doubles) and the parent's ribbons into shared memory
     __syncwarp();
@@ -887,7 +905,9 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             if (probing) {
                 int m = probe_base >= 0 ? (base - probe_base) / kChunk : 32;
                 if (m >= 32) {
+                    PROF_T(t_p);
                     probe_chunks(ws, pe, tt, s_obs, base, lane, endTime, rad_max, edge_mask, &p_safe, &p_mask);
+                    PROF_ADD(2, t_p);
                     p_clean = __ballot_sync(kFull, p_safe);
                     probe_base = base;
                     m = 0;
@@ -916,6 +936,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             bool valid, blocked = false;
             int limit = kChunk, fstop = kChunk;
             unsigned m_stop = 0;
+            PROF_T(t_l);
             const double t_i = time_at_from(tt, base + lane, run, dt);
             valid = clean || (t_i < endTime);
             {
@@ -932,6 +953,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 }
             }
 
+            PROF_ADD(3, t_l);
             // ---- ribbon check-points of this chunk, in order (Edge.cpp:153-172) ---------------------------------
             int n_rel = -2; // relevant-ribbon list of this chunk: -2 not built yet, -1 too many, else count
             while (next_cp < base + limit) {
@@ -967,6 +989,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 double toCover;
                 bool changed = false;
                 bool handled = false;
+                PROF_T(t_c);
                 if (tame && !any_short && nr > 0) {
                     if (n_rel == -2) { // relevant ribbons of this chunk: bounding box of the chunk's executed poses
                         const bool in = lane < limit;
@@ -979,6 +1002,8 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 if (handled) {
                     toCover = 0.0;
                     if (changed) modified = true;
+                    PROF_ADD(4, t_c);
+                    PROF_INC(8);
                 } else {
                     const int nn = warp_checkpoint(cur, alt, nr, cap, cx, cy, W, do_cover, tame, lane, &toCover, &changed, &overflow);
                     if (do_cover) any_short = false; // cover() erased every ribbon short enough, contained or not
@@ -988,6 +1013,8 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                         modified = true;
                         n_rel = -2; // indices moved
                     }
+                    PROF_ADD(5, t_c);
+                    PROF_INC(9);
                 }
                 if (nr == 0) {
                     if (cct == -1) cct = ct;
@@ -1006,6 +1033,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             }
 
             // ---- dynamic-obstacle penalty of the executed iterations (Edge.cpp:150-151), in sample order
+            PROF_T(t_o);
             if (!clean && w.obs_kind != kObsNone && w.n_obs > 0 && (!use_mask || omask != 0)) {
                 double p = 0;
                 if (lane < limit)
@@ -1015,6 +1043,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                 }
             }
 
+            PROF_ADD(6, t_o);
             n_samples += limit;
             n_culled += clean ? limit : 0;
             if (limit < kChunk) {
@@ -1052,6 +1081,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
     }
 
     // ---- truncated end state (Edge.cpp:177-179) and the final cover (:182-191) ----------------------------------------
+    PROF_T(t_tail);
     double ex = 0, ey = 0, eh = 0;
     if (status == PPE_EDGE_OK) {
         double ea;
@@ -1138,6 +1168,13 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
         r->ribbons_changed = (ok && modified) ? 1 : 0;
         r->reserved = n_culled & 0xffffff; // instrumentation: executed samples the probe pass proved clean (never evaluated)
     }
+#ifdef PPE_K2B_PROFILE
+    PROF_ADD(7, t_tail);
+    PROF_ADD(1, t_edge);
+    prof[0] = 1;
+    if (lane == 0)
+        for (int q = 0; q < 10; q++) atomicAdd(&g_k2b_prof[q], (unsigned long long)prof[q]);
+#endif
 }
 
 // ---- K2t: the thread walker -------------------------------------------------------------------------------------------
@@ -1218,6 +1255,14 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
         for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
+    // N2: shared-memory tile of the occupancy and safe bitmaps around the batch's bounding box (TMA bulk copies)
+    const uint32_t* tile = nullptr;
+    if (w.tile_on) {
+        __shared__ unsigned long long s_tile_bar;
+        uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4)));
+        tile_stage(w, s_tile, &s_tile_bar);
+        tile = s_tile;
+    }
     const long long ei = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ei >= n) return;
     const ppe_edge* edge = edges + ei;
@@ -1306,7 +1351,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             const int last = (c0 + kChunk - 1 < n_valid - 1) ? c0 + kChunk - 1 : n_valid - 1;
             const double t_first = tm.at(c0), t_mid = tm.at(c0 + (last - c0 + 1) / 2), t_last = tm.at(last);
             unsigned long long om;
-            if (!probe_one(w, pe, t_first, t_mid, t_last, s_obs, endTime, rad_max, edge_mask, &om)) {
+            if (!probe_one(w, pe, t_first, t_mid, t_last, s_obs, endTime, rad_max, edge_mask, &om, tile)) {
                 // more dirty chunks than the budget only matter if the loop gets that far (an edge that runs into a
                 // blocked area is dirty from there on, but stops at its first blocked sample)
                 if (n_dirty == dirty_budget) { more_dirty = true; break; }
@@ -1337,7 +1382,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
                     const bool sample_ok = pose_eval(pe, t_i, &x, &y, &ang, &in_time);
                     if (!in_time) { infeasible = true; n_exec = i; break; }                        // sample() throws, Edge.cpp:126-133
                     if (!sample_ok) { heavy = true; break; }                                      // stale-pose corner: warp walker
-                    if (map_blocked(w, x, y)) {                                                   // Edge.cpp:144-147
+                    if (map_blocked(w, x, y, tile)) {                                             // Edge.cpp:144-147
                         infeasible = true;
                         n_exec = i;
                         blocked_exit = true;
@@ -1713,7 +1758,8 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
     launches++;
     unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
     if (heavy_list) {
-        const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD);
+        const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD) +
+                              (world.tile_on ? (size_t)2 * world.tile_rows * world.tile_words * sizeof(uint32_t) : 0);
         if (smem_t > 32 * 1024) {
             e = cudaFuncSetAttribute(k2t_thread_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
             if (e != cudaSuccess) return e;
@@ -1767,6 +1813,19 @@ K2Tuning clamp_tuning(K2Tuning t) {
     if (t.dirty_budget > kThreadDirtyCap) t.dirty_budget = kThreadDirtyCap;
     if (t.cp_budget < 1) t.cp_budget = 1;
     return t;
+}
+
+// development builds only (-DPPE_K2B_PROFILE): read and clear the warp walker's cycle counters; 0 entries otherwise
+int k2b_profile_read(unsigned long long* out16) {
+#ifdef PPE_K2B_PROFILE
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out16, g_k2b_prof, sizeof z) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(g_k2b_prof, z, sizeof z) != cudaSuccess) return -1;
+    return 10;
+#else
+    (void)out16;
+    return 0;
+#endif
 }
 
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t stream) {

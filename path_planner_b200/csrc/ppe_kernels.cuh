@@ -41,6 +41,9 @@ struct WorldD {
     double resolution;
     double inv_resolution;    // exact when the resolution is a power of two (res_pow2): x / res == x * inv
     int res_pow2;
+    // optional shared-memory tile of both bitmaps for the thread walker (N2 A/B, PPE_MAP_TILE): rows [tile_r0, tile_r0 +
+    // tile_rows) x words [tile_w0, tile_w0 + tile_words) staged per CTA with cp.async.bulk; look-ups outside fall back to L2
+    int tile_on, tile_r0, tile_w0, tile_rows, tile_words;
     int obs_cull_ok;          // obstacle set admits the chunk bound (SPD symmetric covariances, <= 64 obstacles)
     // dynamic obstacles
     const ObstacleD* obstacles;
@@ -113,6 +116,7 @@ cudaError_t launch_best_final(const BestD* block_best, int blocks, BestD* best, 
 cudaError_t launch_best_export(const BestD* src, BestD* dst, int64_t index_base, cudaStream_t stream);
 size_t prepared_edge_bytes();
 cudaError_t launch_fp64_peak(double* out, int blocks, int iters, cudaStream_t stream);
+int k2b_profile_read(unsigned long long* out16);
 // safe[r][c] = all cells within Chebyshev distance `radius` of (r, c) are in bounds and free
 cudaError_t launch_safe_map(const uint32_t* map_bits, uint32_t* scratch_rows, uint32_t* safe_bits, int rows, int cols,
                             int stride_words, int radius, cudaStream_t stream);

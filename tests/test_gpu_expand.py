@@ -156,3 +156,35 @@ def test_branching_factors_and_equal_radii(engine, oracle):
         gn, gc, gf, gp = _compare(engine, oracle, world, 5000, 24, seed=39)
         per = (1 if same else 2) * (1 if same else 2)
         assert gn.max() == per + per * k
+
+
+def test_map_tile_staging_gives_identical_results(oracle):
+    """N2 A/B variant (PPE_MAP_TILE=1): the thread walker reads the occupancy / safe bitmaps of the batch's bounding box
+    from a shared-memory tile staged with TMA bulk copies; every result must equal the global-memory path bit for bit --
+    for a frontier batch (window derived from the vertices) and for an edge sweep with an explicit window, including edges
+    that leave the window (they fall back to the L2 path)."""
+    world = synth.world_c4()
+    os.environ["PPE_MAP_TILE"] = "1"
+    try:
+        tiled = EdgeEngine(0)
+    finally:
+        os.environ.pop("PPE_MAP_TILE", None)
+    plain = EdgeEngine(0)
+    _compare(tiled, oracle, world, 10000, 48, seed=41)
+    cx, cy = world.start[0], world.start[1]
+    edges = synth.make_edges(world, 20000, seed=43, near_ribbons=0.0, extent=None)
+    # pull the sources into a 300 m box around the start so that the window matters
+    edges["src"][:, 0] = cx + (edges["src"][:, 0] % 300.0) - 150.0
+    edges["src"][:, 1] = cy + (edges["src"][:, 1] % 300.0) - 150.0
+    edges["dst"][:, 0] = edges["src"][:, 0] + (edges["dst"][:, 0] % 120.0) - 60.0
+    edges["dst"][:, 1] = edges["src"][:, 1] + (edges["dst"][:, 1] % 120.0) - 60.0
+    for eng in (tiled, plain):
+        edges["ribbon_set"] = world.upload(eng)
+    tiled._lib.ppe_set_map_window.argtypes = [__import__("ctypes").c_void_p] + [__import__("ctypes").c_double] * 4
+    tiled._lib.ppe_set_map_window(tiled._ctx, cx - 180.0, cy - 180.0, cx + 180.0, cy + 180.0)  # some edges reach outside
+    a = tiled.true_cost_batch(edges)
+    b = plain.true_cost_batch(edges)
+    for name in abi.RESULT_DTYPE.names:
+        if name not in ("ribbons_offset",):
+            assert np.array_equal(a[name], b[name]), name
+    assert (a["infeasible"] == 1).any() and (a["infeasible"] == 0).any()

@@ -44,7 +44,8 @@ int pph_set_ribbons(pph_ctx* ctx, int n, const double* xyxy);
 
 typedef struct {
     double time_remaining;    /* Planner::plan's budget, seconds                                          */
-    double clock0, tick;      /* tick > 0: virtual clock now() = clock0 + calls * tick (deterministic runs) */
+    double clock0, tick;      /* tick > 0: virtual clock now() = clock0 + calls * tick + samples drawn * sample_tick */
+    double sample_tick;       /* virtual seconds per generated sample (bounds the anytime loop's sample doubling)  */
     int32_t initial_samples;  /* PlannerConfig::initialSamples()                                          */
     int32_t use_brown_paths;  /* PlannerConfig::useBrownPaths()                                           */
     int32_t frontier;         /* vertices per ppe_expand_batch; < 0 default, 0 = exact host replay        */

@@ -59,6 +59,11 @@ static RibbonManager::Heuristic heuristicOf(int h) {
     }
 }
 
+// the reference's planner with read access to its sample counter (for the virtual clock of ref_run_plan)
+struct RefAStarPlanner : AStarPlanner {
+    unsigned long attemptedSamples() const { return m_AttemptedSamples; }
+};
+
 extern "C" {
 
 int ref_create(ref_ctx** out) {
@@ -377,7 +382,7 @@ int ref_max_threads(void) {
 int ref_plan(ref_ctx* ctx, int ribbon_set, const double* start5, double timeRemaining, double clock0,
              double tick, int initialSamples, int useBrownPaths, double* plan_out, int plan_cap,
              double* stats10) {
-    AStarPlanner planner;
+    RefAStarPlanner planner;
     return ref_run_plan(planner, ctx, ribbon_set, start5, timeRemaining, clock0, tick, initialSamples, useBrownPaths,
                         plan_out, plan_cap, stats10);
 }
@@ -385,9 +390,18 @@ int ref_plan(ref_ctx* ctx, int ribbon_set, const double* start5, double timeRema
 int ref_plan2(ref_ctx* ctx, int ribbon_set, const double* start5, double timeRemaining, double clock0, double tick,
               int initialSamples, int useBrownPaths, const double* prev_plan, int n_prev, double* plan_out, int plan_cap,
               double* stats10) {
-    AStarPlanner planner;
+    RefAStarPlanner planner;
     return ref_run_plan(planner, ctx, ribbon_set, start5, timeRemaining, clock0, tick, initialSamples, useBrownPaths,
                         plan_out, plan_cap, stats10, prev_plan, n_prev);
+}
+
+// + virtual time per generated sample (see ref_run_plan)
+int ref_plan3(ref_ctx* ctx, int ribbon_set, const double* start5, double timeRemaining, double clock0, double tick,
+              double sampleTick, int initialSamples, int useBrownPaths, const double* prev_plan, int n_prev, double* plan_out,
+              int plan_cap, double* stats10) {
+    RefAStarPlanner planner;
+    return ref_run_plan(planner, ctx, ribbon_set, start5, timeRemaining, clock0, tick, initialSamples, useBrownPaths,
+                        plan_out, plan_cap, stats10, prev_plan, n_prev, sampleTick);
 }
 
 int ref_expand_once(ref_ctx* ctx, int ribbon_set, int nSamples, int seed, double* f_out, int cap) {

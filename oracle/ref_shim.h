@@ -45,7 +45,7 @@ struct ref_ctx {
 template <typename PlannerT>
 int ref_run_plan(PlannerT& planner, ref_ctx* ctx, int ribbon_set, const double* start5, double timeRemaining,
                  double clock0, double tick, int initialSamples, int useBrownPaths, double* plan_out, int plan_cap,
-                 double* stats10, const double* prev_plan = nullptr, int n_prev = 0) {
+                 double* stats10, const double* prev_plan = nullptr, int n_prev = 0, double sampleTick = 0) {
     PlannerConfig config = ctx->config;
     config.setInitialSamples(initialSamples);
     config.setUseBrownPaths(useBrownPaths != 0);
@@ -53,8 +53,11 @@ int ref_run_plan(PlannerT& planner, ref_ctx* ctx, int ribbon_set, const double* 
     if (tick > 0) {
         // parity mode: deterministic clock (PlannerConfig::setNowFunction, PlannerConfig.h:110);
         // the RNG seed (AStarPlanner.cpp:33) and every deadline test then depend on call counts only
-        config.setNowFunction([ctx]() -> double {
-            double t = ctx->clockNow + (double)ctx->clockCalls * ctx->clockTick;
+        // sampleTick > 0 also charges virtual time per generated sample (planner.attemptedSamples()), which bounds the
+        // sample doubling of AStarPlanner.cpp:101-102 the way generation time bounds it on a real clock
+        PlannerT* pl = &planner;
+        config.setNowFunction([ctx, pl, sampleTick]() -> double {
+            double t = ctx->clockNow + (double)ctx->clockCalls * ctx->clockTick + sampleTick * (double)pl->attemptedSamples();
             ctx->clockCalls++;
             return t;
         });

@@ -22,7 +22,8 @@ assert PATH_DTYPE.itemsize == 88
 
 
 class PlanOptions(C.Structure):
-    _fields_ = [("time_remaining", C.c_double), ("clock0", C.c_double), ("tick", C.c_double), ("initial_samples", C.c_int32),
+    _fields_ = [("time_remaining", C.c_double), ("clock0", C.c_double), ("tick", C.c_double), ("sample_tick", C.c_double),
+                ("initial_samples", C.c_int32),
                 ("use_brown_paths", C.c_int32), ("frontier", C.c_int32), ("knn_chunk", C.c_int32), ("visualize", C.c_int32),
                 ("reserved", C.c_int32), ("visualization_path", C.c_char_p)]
 
@@ -123,10 +124,10 @@ class PlanningHarness:
         self._check(self._lib.pph_set_ribbons(self._ctx, rib.shape[0], abi.dptr(rib)), "set_ribbons")
 
     def plan(self, start, time_remaining, clock0=0.0, tick=0.0, initial_samples=100, brown=0, frontier=-1, knn_chunk=0, previous=None,
-             visualization_path=None, cap=256):
+             visualization_path=None, cap=256, sample_tick=0.0):
         """Planner::plan.  Returns (plan records [n] of PATH_DTYPE, stats dict)."""
         start = np.ascontiguousarray(start, dtype=np.float64)
-        opt = PlanOptions(time_remaining, clock0, tick, initial_samples, brown, frontier, knn_chunk, 1 if visualization_path else 0, 0,
+        opt = PlanOptions(time_remaining, clock0, tick, sample_tick, initial_samples, brown, frontier, knn_chunk, 1 if visualization_path else 0, 0,
                           visualization_path.encode() if visualization_path else None)
         prev = np.ascontiguousarray(previous if previous is not None else np.zeros(0, dtype=PATH_DTYPE), dtype=PATH_DTYPE)
         out = np.zeros(cap, dtype=PATH_DTYPE)

@@ -60,6 +60,9 @@ public:
     // copy of the sample set on the device
     void addSamplesResident(StateGenerator& generator, int n);
 
+    // states drawn from the generator so far (SamplingBasedPlanner::m_AttemptedSamples)
+    unsigned long attemptedSamples() const { return m_AttemptedSamples; }
+
     // instrumentation
     long trueCostEdges() const { return m_TrueCostEdges; }
     long dubinsSolves() const { return m_DubinsSolves; }

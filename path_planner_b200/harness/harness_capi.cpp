@@ -193,10 +193,16 @@ int pph_plan(pph_ctx* ctx, const double start5[5], const pph_dubins_path* previo
     config.setInitialSamples(opt->initial_samples > 0 ? opt->initial_samples : 100);
     config.setUseBrownPaths(opt->use_brown_paths != 0);
     ctx->clockNow = opt->clock0; ctx->clockTick = opt->tick; ctx->clockCalls = 0;
+    BatchedAStarPlanner planner(ctx->engine, opt->knn_chunk > 0 ? opt->knn_chunk : 128, &ctx->cache);
+    if (opt->frontier >= 0) planner.setFrontierWidth(opt->frontier);
     if (opt->tick > 0) {
         // deterministic clock (PlannerConfig::setNowFunction, PlannerConfig.h:110): deadline tests and the sampler's
         // seed (AStarPlanner.cpp:33) then depend on call counts only
-        config.setNowFunction([ctx]() -> double { return ctx->clockNow + (double)(ctx->clockCalls++) * ctx->clockTick; });
+        const BatchedAStarPlanner* pl = &planner;
+        const double sampleTick = opt->sample_tick;
+        config.setNowFunction([ctx, pl, sampleTick]() -> double {
+            return ctx->clockNow + (double)(ctx->clockCalls++) * ctx->clockTick + sampleTick * (double)pl->attemptedSamples();
+        });
     } else {
         config.setNowFunction([ctx]() -> double {
             ctx->clockCalls++;
@@ -215,8 +221,6 @@ int pph_plan(pph_ctx* ctx, const double start5[5], const pph_dubins_path* previo
     DubinsPlan prev;
     for (int i = 0; i < n_previous; i++) prev.append(wrapperOf(previous[i]));
     const State start(start5[0], start5[1], start5[2], start5[3], start5[4]);
-    BatchedAStarPlanner planner(ctx->engine, opt->knn_chunk > 0 ? opt->knn_chunk : 128, &ctx->cache);
-    if (opt->frontier >= 0) planner.setFrontierWidth(opt->frontier);
     Planner::Stats st;
     const auto t0 = std::chrono::steady_clock::now();
     try {

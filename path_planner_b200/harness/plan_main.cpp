@@ -15,7 +15,7 @@
 //   start <x> <y> <heading> <speed> <time>
 //   budget <seconds>             per cycle (Executive: 0.85, executive.h:183)
 //   cycles <n>   period <seconds>   initial_samples <n>   brown_paths <0|1>   frontier <m>
-//   virtual_clock <clock0> <tick>    deterministic now() for reproducible runs
+//   virtual_clock <clock0> <tick> [sample_tick]   deterministic now() for reproducible runs
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -105,7 +105,7 @@ int main(int argc, char** argv) {
         } else if (key == "initial_samples") { if (!(ls >> opt.initial_samples)) return bad();
         } else if (key == "brown_paths") { if (!(ls >> opt.use_brown_paths)) return bad();
         } else if (key == "frontier") { if (!(ls >> opt.frontier)) return bad();
-        } else if (key == "virtual_clock") { if (!(ls >> opt.clock0 >> opt.tick)) return bad();
+        } else if (key == "virtual_clock") { if (!(ls >> opt.clock0 >> opt.tick)) return bad(); ls >> opt.sample_tick;
         } else return bad();
     }
 

@@ -67,8 +67,12 @@ def load_ref():
     w.lib.ref_get_obstacles.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
     w.lib.ref_true_cost_batch_mt.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     w.lib.ref_get_ribbon_set.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
-    w.lib.ref_plan.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_double,
-                               C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double)]
+    D = C.POINTER(C.c_double)
+    w.lib.ref_plan.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D, C.c_int, D]
+    w.lib.ref_plan2.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D, C.c_int, D,
+                                C.c_int, D]
+    w.lib.ref_plan3.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D,
+                                C.c_int, D, C.c_int, D]
     return w
 
 
@@ -148,13 +152,15 @@ def load_harness(path=None):
                                    C.c_int, D, C.c_int, D]
     w.lib.ref_plan2.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D, C.c_int, D,
                                 C.c_int, D]
+    w.lib.ref_plan3.argtypes = [C.c_void_p, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, D,
+                                C.c_int, D, C.c_int, D]
     w.lib.harness_plan2.argtypes = [C.c_void_p, C.c_int, C.c_int, D, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int,
                                     C.c_int, C.c_int, D, C.c_int, D, C.c_int, D]
     return w
 
 
 def run_plan(w, which, ribbon_set, start, time_remaining, clock0, tick, initial_samples=100, brown=0, knn_chunk=128,
-             device=0, cap=256, frontier=-1, previous=None):
+             device=0, cap=256, frontier=-1, previous=None, sample_tick=0.0):
     """which = "ref" (AStarPlanner) or "harness" (BatchedAStarPlanner on `device`).  tick > 0 selects the
     virtual clock (now() = clock0 + calls * tick).  `frontier`: vertices per ppe_expand_batch (-1 default, 0 = exact host
     replay).  `previous`: a plan [n, 12] handed in as previousPlan.  Returns (plan [n,12], stats dict)."""
@@ -164,7 +170,7 @@ def run_plan(w, which, ribbon_set, start, time_remaining, clock0, tick, initial_
     prev = np.ascontiguousarray(previous if previous is not None else np.zeros((0, 12)), dtype=np.float64).reshape(-1, 12)
     pp = abi.dptr(prev) if len(prev) else None
     if which == "ref":
-        n = w.lib.ref_plan2(w.ctx, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples, brown,
+        n = w.lib.ref_plan3(w.ctx, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, sample_tick, initial_samples, brown,
                             pp, len(prev), abi.dptr(plan), cap, abi.dptr(stats))
     else:
         n = w.lib.harness_plan2(w.ctx, device, ribbon_set, abi.dptr(start), time_remaining, clock0, tick, initial_samples,

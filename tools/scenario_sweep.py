@@ -60,9 +60,9 @@ def main():
         for s in sharding.scenario_assignment(args.scenarios, 0, world_size)[: args.check]:
             w, start = bench.scenario_world(s)
             h.set_world(w)
-            plan, st = h.plan(start, 0.95, clock0=1000.0, tick=args.tick)
+            plan, st = h.plan(start, 0.95, clock0=1000.0, tick=args.tick, sample_tick=bench.SCENARIO_SAMPLE_TICK)
             sid = w.upload_ref(ref)
-            ref_plan, rs = common.run_plan(ref, "ref", sid, start, 0.95, 1000.0, args.tick, 100)
+            ref_plan, rs = common.run_plan(ref, "ref", sid, start, 0.95, 1000.0, args.tick, 100, sample_tick=bench.SCENARIO_SAMPLE_TICK)
             assert len(ref_plan) == len(plan) and np.array_equal(ref_plan[:, 7], plan["type"]), "scenario %d: plans differ" % s
             assert rs["expanded"] == st["expanded"] and rs["generated"] == st["generated"] and rs["samples"] == st["samples"], \
                 "scenario %d: search differs" % s

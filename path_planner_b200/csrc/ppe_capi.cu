@@ -805,10 +805,24 @@ static int grow_pinned(ppe_ctx* ctx, void** p, size_t* cap, size_t need) {
     return PPE_OK;
 }
 
+static int64_t add_samples_chunk(ppe_ctx* ctx, int64_t n, const double* x, const double* y, const double* heading, uint8_t* keep);
+
 int64_t ppe_add_samples(ppe_ctx* ctx, int64_t n, const double* x, const double* y, const double* heading, uint8_t* keep) {
     if (!ctx || n < 0 || (n > 0 && (!x || !y || !heading || !keep))) return fail(ctx, PPE_ERR_INVALID, "ppe_add_samples: bad arguments");
+    if ((int64_t)ctx->n_samples + n > ((int64_t)1 << 31) - 1) return fail(ctx, PPE_ERR_CAPACITY, "ppe_add_samples: more than 2^31 resident samples");
+    int64_t kept = 0;
+    const int64_t chunk = (int64_t)1 << 22; // staging buffers stay bounded however far the anytime loop doubles the sample set
+    for (int64_t lo = 0; lo < n; lo += chunk) {
+        const int64_t m = n - lo < chunk ? n - lo : chunk;
+        const int64_t k = add_samples_chunk(ctx, m, x + lo, y + lo, heading + lo, keep + lo);
+        if (k < 0) return k;
+        kept += k;
+    }
+    return kept;
+}
+
+static int64_t add_samples_chunk(ppe_ctx* ctx, int64_t n, const double* x, const double* y, const double* heading, uint8_t* keep) {
     if (n == 0) return 0;
-    if (n > ((int64_t)1 << 24)) return fail(ctx, PPE_ERR_CAPACITY, "ppe_add_samples: at most 2^24 states per call");
     PPE_CUDA(ctx, cudaSetDevice(ctx->device));
     WorldD w;
     int rc = make_world(ctx, &w);

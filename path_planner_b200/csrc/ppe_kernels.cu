@@ -735,10 +735,25 @@ __device__ __noinline__ int relevant_ribbons(const double4* cur, int nr, double 
     return n <= kRelCap ? n : -1;
 }
 
-// One check-point on the relevant ribbons only (uniform across the warp).  Returns true when it handled the check-point
-// (minDistanceFrom == 0, cover applied in place); false = nothing was modified, take the general path.
-__device__ __noinline__ bool fast_checkpoint(double4* cur, const int* rel, int n_rel, double x, double y, double W, bool do_cover,
-                                                bool tame, int lane, bool* changed) {
+// nearest ribbon end point over the whole list (lanes over ribbons): minDistanceFrom when no ribbon contains the point
+__device__ __noinline__ double warp_nearest_endpoint(const double4* cur, int nr, double x, double y, int lane) {
+    double mn = DBL_MAX;
+#pragma unroll 1
+    for (int r = lane; r < nr; r += 32) {
+        const RibbonD rb = load_ribbon(cur + r);
+        const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart);
+    }
+    return sqrt(warp_min(mn));
+}
+
+// One check-point on the relevant ribbons only (uniform across the warp).  Returns 1 when it handled the check-point with
+// minDistanceFrom == 0 (cover applied in place); 2 when NO ribbon contains the point even non-strictly -- then cover()
+// cannot touch anything either (strict containment implies it) and only the nearest end point is left to compute;
+// 0 = nothing was modified, take the general path.
+__device__ __noinline__ int fast_checkpoint(double4* cur, const int* rel, int n_rel, double x, double y, double W, bool do_cover,
+                                             bool tame, int lane, bool* changed) {
     bool inside = false;
     int upd = -1;          // at most one in-place update per check-point on this path
     double upx = 0, upy = 0;
@@ -756,17 +771,17 @@ __device__ __noinline__ bool fast_checkpoint(double4* cur, const int* rel, int n
         if (do_cover && d < W / 2.0) {
             RibbonD piece = {rb.sx, rb.sy, px, py};
             RibbonD rest = {px, py, rb.ex, rb.ey};
-            if (!ribbon_covered(piece, true, W) || ribbon_covered(rest, true, W)) return false; // the list's structure changes
-            if (upd >= 0) return false;                                                           // two ribbons at once: general path
+            if (!ribbon_covered(piece, true, W) || ribbon_covered(rest, true, W)) return 0; // the list's structure changes
+            if (upd >= 0) return 0;                                                           // two ribbons at once: general path
             upd = r; upx = px; upy = py;
             ch = (px != rb.sx) || (py != rb.sy);
         }
     }
-    if (!inside) return false; // minDistanceFrom needs the nearest end point over the whole list
+    if (!inside) return 2; // d >= W for every ribbon whose projection is contained: nothing to cover, distance from the end points
     if (upd >= 0 && lane == 0) cur[upd] = pack_ribbon(upx, upy, cur[upd].z, cur[upd].w);
     __syncwarp();
     *changed = ch;
-    return true;
+    return 1;
 }
 
 // -DPPE_K2B_PROFILE (make prof -> libppe_prof.so, development only): where the warp walker's cycles go, summed over the
@@ -997,10 +1012,13 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                         const double by0 = warp_min(in ? y : DBL_MAX), by1 = warp_max(in ? y : -DBL_MAX);
                         n_rel = relevant_ribbons(cur, nr, bx0, bx1, by0, by1, W, lane, rel);
                     }
-                    if (n_rel > 0) handled = fast_checkpoint(cur, rel, n_rel, cx, cy, W, do_cover, tame, lane, &changed);
+                    if (n_rel >= 0) {
+                        const int how = n_rel > 0 ? fast_checkpoint(cur, rel, n_rel, cx, cy, W, do_cover, tame, lane, &changed) : 2;
+                        if (how == 1) { handled = true; toCover = 0.0; }
+                        else if (how == 2) { handled = true; toCover = warp_nearest_endpoint(cur, nr, cx, cy, lane); }
+                    }
                 }
                 if (handled) {
-                    toCover = 0.0;
                     if (changed) modified = true;
                     PROF_ADD(4, t_c);
                     PROF_INC(8);
@@ -1516,8 +1534,11 @@ k2a_prepare(const ppe_config cfg, const double dt, const double horizon_end, con
 
 // K2b: one warp per edge, persistent CTAs pulling work from a global counter: the edges on the heavy list that
 // K2t left behind, or (heavy_list == nullptr) every edge of the batch
+#ifndef PPE_K2B_WARPS_PER_SM
+#define PPE_K2B_WARPS_PER_SM 16 // 16 -> 128 registers per thread; 32 -> 64 (experiment: make variant K2B_WARPS=32)
+#endif
 template <int kWarpsPerBlock>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 16 / kWarpsPerBlock)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, PPE_K2B_WARPS_PER_SM / kWarpsPerBlock)
 k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
              const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
              unsigned long long* work_counter, const unsigned int* __restrict__ heavy_list,

@@ -42,16 +42,17 @@ def available():
     return os.path.exists(HARNESS_PATH)
 
 
-_lib = None
+_libs = {}
 
 
-def load_library():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not available():
-        raise PpeError("%s is missing: build it with `make -C path_planner_b200/harness` (needs the reference sources)" % HARNESS_PATH)
-    lib = C.CDLL(HARNESS_PATH)
+def load_library(path=None):
+    """`path`: another build of the same C ABI (tests bind the CPU test double of the engine through it)."""
+    path = path or HARNESS_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
+        raise PpeError("%s is missing: build it with `make -C path_planner_b200/harness` (needs the reference sources)" % path)
+    lib = C.CDLL(path)
     D = C.POINTER(C.c_double)
     lib.pph_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.pph_destroy.argtypes = [C.c_void_p]
@@ -69,15 +70,15 @@ def load_library():
     lib.pph_plan.argtypes = [C.c_void_p, D, C.c_void_p, C.c_int, C.POINTER(PlanOptions), C.c_void_p, C.c_int, C.POINTER(PlanStats)]
     lib.pph_advance.argtypes = [C.c_void_p, C.c_double, D]
     lib.pph_write_plan_msg.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
-    _lib = lib
+    _libs[path] = lib
     return lib
 
 
 class PlanningHarness:
     """One planning thread: a pph_ctx (its own ppe_ctx on `device`)."""
 
-    def __init__(self, device=0):
-        self._lib = load_library()
+    def __init__(self, device=0, lib_path=None):
+        self._lib = load_library(lib_path)
         self._ctx = C.c_void_p()
         rc = self._lib.pph_create(int(device), C.byref(self._ctx))
         if rc != abi.PPE_OK:

@@ -16,6 +16,7 @@
 #include "common/map/GridWorldMap.h"
 #include "common/map/Map.h"
 #include "planner/utilities/RibbonManager.h"
+#include "planner/utilities/Visualizer.h"
 
 namespace {
 
@@ -209,13 +210,12 @@ int pph_plan(pph_ctx* ctx, const double start5[5], const pph_dubins_path* previo
             return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
         });
     }
-    std::ofstream vis;
-    std::ostream* visPtr = nullptr;
+    // visualization stream as Executive sets it up (executive.cpp:446-447): a Visualizer owning the file
+    Visualizer::UniquePtr visualizer;
     if (opt->visualize && opt->visualization_path) {
-        vis.open(opt->visualization_path);
-        if (!vis) { ctx->err = "cannot open the visualization file"; return PPE_ERR_INVALID; }
-        visPtr = &vis;
-        config.setVisualizationStream(&visPtr);
+        visualizer = Visualizer::UniquePtr(new Visualizer(opt->visualization_path));
+        if (!visualizer->stream()) { ctx->err = "cannot open the visualization file"; return PPE_ERR_INVALID; }
+        config.setVisualizer(&visualizer);
         config.setVisualizations(true);
     }
     DubinsPlan prev;

@@ -78,7 +78,7 @@ def test_plan_msg_export_and_visualization_stream(tmp_path):
     h = ph.PlanningHarness(0)
     h.set_world(world)
     vis = str(tmp_path / "vis.txt")
-    plan, st = h.plan(world.start, 0.95, clock0=1000.0, tick=5e-3, visualization_path=vis)
+    plan, st = h.plan(world.start, 0.95, clock0=1000.0, tick=5e-4, visualization_path=vis)
     assert len(plan) >= 1
     msg = str(tmp_path / "plan.yaml")
     h.write_plan_msg(plan, msg)

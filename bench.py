@@ -196,44 +196,55 @@ def plan_at_budget(budget_s, device, reps=3):
     ref = common.load_ref() if common.have_ref() else None
     h = ph.PlanningHarness(device)
     out = {"budget_s": budget_s, "repetitions": reps,
-           "unit": "f = g + h of the returned plan, seconds (lower is better); the planner seeds its sampler from the wall "
-                   "clock (AStarPlanner.cpp:33), so every scenario is planned `repetitions` times by each planner: median f, "
-                   "best f, mean expansions and expansions per second of wall time",
+           "unit": "f = g + h of the returned plan, seconds (lower is better); every scenario is planned `repetitions` times by "
+                   "each planner on the real clock, repetition r of both rebased to the same start instant so that the sampler "
+                   "seed (the integer second of the deadline, AStarPlanner.cpp:33) is the same: f per repetition, median, best, "
+                   "mean expansions and expansions per second of wall time",
            "scenarios": []}
     for wname, start in PLAN_SCENARIOS:
         world = synth.WORLDS[wname]()
         st0 = world.start if start is None else np.array(start, dtype=np.float64)
         rec = {"world": wname, "start": [float(v) for v in st0]}
         initial = 10000 if wname == "c4" else 100  # C4 runs with initialSamples = 10 000
+        # the planner seeds its sampler with the integer second of its deadline (AStarPlanner.cpp:33): repetition r of both
+        # planners runs on the real clock rebased to start at the same instant 1e9 + 10 r + 0.25, so they draw the same samples
+        epochs = [1.0e9 + 10.0 * r + 0.25 for r in range(reps)]
         if ref is not None:
             sid = world.upload_ref(ref)
             fs, exp, smp, wall = [], [], [], []
-            for _ in range(reps):
+            for c0 in epochs:
                 t0 = time.perf_counter()
-                plan, st = common.run_plan(ref, "ref", sid, st0, budget_s, 0.0, 0.0, initial)
+                plan, st = common.run_plan(ref, "ref", sid, st0, budget_s, c0, 0.0, initial)
                 wall.append(time.perf_counter() - t0)
-                if len(plan):
-                    fs.append(st["f"])
+                fs.append(st["f"] if len(plan) else float("inf"))
                 exp.append(st["expanded"])
                 smp.append(st["samples"])
-            rec["reference_cpu"] = {"f_median": statistics.median(fs) if fs else None, "f_best": min(fs) if fs else None,
-                                    "plans_found": len(fs), "expanded_mean": sum(exp) / reps, "samples_mean": sum(smp) / reps,
-                                    "expansions_per_s": sum(exp) / sum(wall), "wall_s_mean": round(sum(wall) / reps, 3)}
+            rec["reference_cpu"] = {"f": fs, "f_median": statistics.median(fs), "f_best": min(fs),
+                                    "plans_found": sum(1 for f in fs if f < float("inf")), "expanded_mean": sum(exp) / reps,
+                                    "samples_mean": sum(smp) / reps, "expansions_per_s": sum(exp) / sum(wall),
+                                    "wall_s_mean": round(sum(wall) / reps, 3)}
         h.set_world(world)
-        fs, exp, smp, wall, hits, batches = [], [], [], [], [], []
-        for _ in range(reps):
-            plan, st = h.plan(st0, budget_s, initial_samples=initial)
+        fs, exp, smp, wall, hits, batches, exact = [], [], [], [], [], [], []
+        where = {"engine_expand": 0.0, "replay": 0.0, "add_samples": 0.0, "exact": 0.0}
+        for c0 in epochs:
+            plan, st = h.plan(st0, budget_s, clock0=c0, initial_samples=initial)
             wall.append(st["wall_seconds"])
-            if len(plan):
-                fs.append(st["plan_f"])
+            fs.append(st["plan_f"] if len(plan) else float("inf"))
             exp.append(st["expanded"])
             smp.append(st["samples"])
             hits.append(st["frontier_hits"])
             batches.append(st["engine_batches"])
-        rec["engine"] = {"f_median": statistics.median(fs) if fs else None, "f_best": min(fs) if fs else None, "plans_found": len(fs),
+            exact.append(st["exact_expansions"])
+            for k in where:
+                where[k] += st["seconds_" + k]
+        rec["engine"] = {"f": fs, "f_median": statistics.median(fs), "f_best": min(fs),
+                         "plans_found": sum(1 for f in fs if f < float("inf")),
                          "expanded_mean": sum(exp) / reps, "samples_mean": sum(smp) / reps, "expansions_per_s": sum(exp) / sum(wall),
                          "frontier_hit_rate": sum(hits) / max(1, sum(exp)), "engine_batches_mean": sum(batches) / reps,
-                         "wall_s_mean": round(sum(wall) / reps, 3)}
+                         "exact_expansions_mean": sum(exact) / reps, "wall_s_mean": round(sum(wall) / reps, 3),
+                         "wall_share": {k: round(v / max(1e-9, sum(wall)), 3) for k, v in where.items()}}
+        if ref is not None:
+            rec["engine_f_not_worse"] = [bool(a <= b + 1e-9 * max(1.0, abs(b))) for a, b in zip(fs, rec["reference_cpu"]["f"])]
         if ref is not None and rec["reference_cpu"]["expansions_per_s"] > 0:
             rec["expansions_per_s_ratio"] = rec["engine"]["expansions_per_s"] / rec["reference_cpu"]["expansions_per_s"]
         out["scenarios"].append(rec)

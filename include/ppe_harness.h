@@ -44,7 +44,10 @@ int pph_set_ribbons(pph_ctx* ctx, int n, const double* xyxy);
 
 typedef struct {
     double time_remaining;    /* Planner::plan's budget, seconds                                          */
-    double clock0, tick;      /* tick > 0: virtual clock now() = clock0 + calls * tick + samples drawn * sample_tick */
+    double clock0, tick;      /* tick > 0: virtual clock now() = clock0 + calls * tick + samples drawn * sample_tick;
+                                 tick == 0 and clock0 > 0: the real clock rebased so that the plan starts at clock0 (the
+                                 sampler's seed is the integer second of the deadline, AStarPlanner.cpp:33: a chosen clock0
+                                 makes runs comparable); both 0: the system clock */
     double sample_tick;       /* virtual seconds per generated sample (bounds the anytime loop's sample doubling)  */
     int32_t initial_samples;  /* PlannerConfig::initialSamples()                                          */
     int32_t use_brown_paths;  /* PlannerConfig::useBrownPaths()                                           */
@@ -76,6 +79,7 @@ typedef struct {
     uint64_t now_calls;
     uint64_t true_cost_edges, dubins_solves, engine_batches, frontier_vertices, frontier_hits, exact_expansions;
     double wall_seconds;
+    double seconds_engine_expand, seconds_replay, seconds_add_samples, seconds_exact; /* where the wall time went */
 } pph_stats;
 
 /* Planner::plan(ribbons, start, config, previousPlan, timeRemaining): start = x, y, heading, speed, time.

@@ -3,6 +3,7 @@
 #ifndef PPE_ORACLE_REF_SHIM_H
 #define PPE_ORACLE_REF_SHIM_H
 
+#include <chrono>
 #include <iostream>
 #include <memory>
 #include <string>
@@ -60,6 +61,15 @@ int ref_run_plan(PlannerT& planner, ref_ctx* ctx, int ribbon_set, const double* 
             double t = ctx->clockNow + (double)ctx->clockCalls * ctx->clockTick + sampleTick * (double)pl->attemptedSamples();
             ctx->clockCalls++;
             return t;
+        });
+    }
+    else if (clock0 > 0) {
+        // real clock rebased so that the plan starts at clock0: the sampler's seed is the integer second of the deadline
+        // (AStarPlanner.cpp:33), so a chosen clock0 gives both planners the same sample sequence at a real budget
+        const auto t_start = std::chrono::steady_clock::now();
+        config.setNowFunction([ctx, t_start, clock0]() -> double {
+            ctx->clockCalls++;
+            return clock0 + std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
         });
     }
     State start(start5[0], start5[1], start5[2], start5[3], start5[4]);

@@ -12,6 +12,7 @@
 #include "KeyedHeap.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -53,6 +54,13 @@ PPE_ACCESS(RibbonCct, RibbonManager, double, m_CoverageCompletedTime)
 PPE_ACCESS(RibbonK, RibbonManager, int, m_K)
 PPE_ACCESS(OpenList, SamplingBasedPlanner, std::vector<std::shared_ptr<Vertex>>, m_VertexQueue)
 #undef PPE_ACCESS
+
+struct Stopwatch { // adds the scope's wall time to a counter
+    double& acc;
+    std::chrono::steady_clock::time_point t0;
+    explicit Stopwatch(double& a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~Stopwatch() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
 
 int heuristicId(RibbonManager::Heuristic h) {
     switch (h) {
@@ -172,6 +180,7 @@ void BatchedAStarPlanner::prepareWorld(const RibbonManager& ribbonManager, const
 // sample sequence must be the reference's); Map::isBlocked runs on the device for the whole batch and the free
 // states are appended to the resident sample set in the same order as to m_Samples.
 void BatchedAStarPlanner::addSamplesResident(StateGenerator& generator, int n) {
+    Stopwatch sw(m_TSamples);
     m_AttemptedSamples += n;
     if (n <= 0) return;
     std::vector<State>& gen = m_Scratch;
@@ -366,6 +375,7 @@ void BatchedAStarPlanner::expandSpecific(const Vertex::SharedPtr& root, const st
 Planner::Stats BatchedAStarPlanner::plan(const RibbonManager& ribbonManager, const State& start, PlannerConfig config,
                                          const DubinsPlan& previousPlan, double timeRemaining) {
     m_TrueCostEdges = m_DubinsSolves = m_Batches = m_FrontierVertices = m_FrontierHits = m_ExactExpansions = 0;
+    m_TEngine = m_TReplay = m_TSamples = m_TExact = 0;
     m_Config = std::move(config); // before the first now(), :14
     const double endTime = timeRemaining + now();
     m_Config.setStartStateTime(start.time());
@@ -478,6 +488,7 @@ void BatchedAStarPlanner::syncSampleHeap() {
 
 // The vertex the reference's loop just popped, plus the best vertices still on the open list, in one engine call.
 void BatchedAStarPlanner::speculate(const std::shared_ptr<Vertex>& first) {
+    Stopwatch sw(m_TEngine);
     std::vector<std::shared_ptr<Vertex>> batch;
     batch.push_back(first);
     if (m_Frontier > 1) {
@@ -576,6 +587,7 @@ void BatchedAStarPlanner::expandFrontier(const std::shared_ptr<Vertex>& sourceVe
         expandExact(sourceVertex);
         return;
     }
+    Stopwatch sw(m_TReplay);
     visualizeVertex(sourceVertex, "vertex", true);
     const Expansion& ex = it->second;
     const State& src = sourceVertex->state();
@@ -601,6 +613,7 @@ void BatchedAStarPlanner::expandFrontier(const std::shared_ptr<Vertex>& sourceVe
 }
 
 void BatchedAStarPlanner::expandExact(const std::shared_ptr<Vertex>& sourceVertex) {
+    Stopwatch sw(m_TExact);
     m_ExactExpansions++;
     syncSampleHeap(); // the arrangement of m_Samples as the reference would have it right now
     visualizeVertex(sourceVertex, "vertex", true);

@@ -204,6 +204,13 @@ int pph_plan(pph_ctx* ctx, const double start5[5], const pph_dubins_path* previo
         config.setNowFunction([ctx, pl, sampleTick]() -> double {
             return ctx->clockNow + (double)(ctx->clockCalls++) * ctx->clockTick + sampleTick * (double)pl->attemptedSamples();
         });
+    } else if (opt->clock0 > 0) {
+        const auto t_start = std::chrono::steady_clock::now();
+        const double c0 = opt->clock0;
+        config.setNowFunction([ctx, t_start, c0]() -> double {
+            ctx->clockCalls++;
+            return c0 + std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        });
     } else {
         config.setNowFunction([ctx]() -> double {
             ctx->clockCalls++;
@@ -253,6 +260,8 @@ int pph_plan(pph_ctx* ctx, const double start5[5], const pph_dubins_path* previo
     stats->engine_batches = (uint64_t)planner.batches(); stats->frontier_vertices = (uint64_t)planner.frontierVertices();
     stats->frontier_hits = (uint64_t)planner.frontierHits(); stats->exact_expansions = (uint64_t)planner.exactExpansions();
     stats->wall_seconds = wall;
+    stats->seconds_engine_expand = planner.secondsInEngineExpand(); stats->seconds_replay = planner.secondsInReplay();
+    stats->seconds_add_samples = planner.secondsInAddSamples(); stats->seconds_exact = planner.secondsInExact();
     ctx->lastPlan = st.Plan;
     ctx->lastStart = start;
     return n;

@@ -134,12 +134,14 @@ int main(int argc, char** argv) {
                "\"plan_collision_penalty\": %.17g, \"plan_depth\": %llu, \"plan_endtime\": %.17g, \"samples\": %llu, \"generated\": %llu, "
                "\"expanded\": %llu, \"iterations\": %llu, \"now_calls\": %llu, \"true_cost_edges\": %llu, \"dubins_solves\": %llu, "
                "\"engine_batches\": %llu, \"frontier_vertices\": %llu, \"frontier_hits\": %llu, \"exact_expansions\": %llu, "
-               "\"wall_seconds\": %.6f}\n",
+               "\"wall_seconds\": %.6f, \"seconds_engine_expand\": %.6f, \"seconds_replay\": %.6f, \"seconds_add_samples\": %.6f, "
+               "\"seconds_exact\": %.6f}\n",
                c, n, st.plan_f, st.plan_h, st.plan_time_penalty, st.plan_collision_penalty, (unsigned long long)st.plan_depth,
                st.plan_endtime, (unsigned long long)st.samples, (unsigned long long)st.generated, (unsigned long long)st.expanded,
                (unsigned long long)st.iterations, (unsigned long long)st.now_calls, (unsigned long long)st.true_cost_edges,
                (unsigned long long)st.dubins_solves, (unsigned long long)st.engine_batches, (unsigned long long)st.frontier_vertices,
-               (unsigned long long)st.frontier_hits, (unsigned long long)st.exact_expansions, st.wall_seconds);
+               (unsigned long long)st.frontier_hits, (unsigned long long)st.exact_expansions, st.wall_seconds, st.seconds_engine_expand,
+               st.seconds_replay, st.seconds_add_samples, st.seconds_exact);
         if (n == 0) break;
         previous.assign(plan.begin(), plan.begin() + (n < (int)plan.size() ? n : (int)plan.size()));
         if (!planOut.empty()) ck(pph_write_plan_msg(previous.data(), (int)previous.size(), planOut.c_str()), "pph_write_plan_msg");

@@ -756,7 +756,7 @@ __device__ __noinline__ int fast_checkpoint(double4* cur, const int* rel, int n_
                                              bool tame, int lane, bool* changed) {
     bool inside = false;
     int upd = -1;          // at most one in-place update per check-point on this path
-    double upx = 0, upy = 0;
+    double nsx = 0, nsy = 0, nex = 0, ney = 0;
     bool ch = false;
 #pragma unroll 1
     for (int q = 0; q < n_rel; q++) {
@@ -769,16 +769,22 @@ __device__ __noinline__ int fast_checkpoint(double4* cur, const int* rel, int n_
         const double d = ribbon_distance(rb, x, y);
         inside = inside || (d < W);
         if (do_cover && d < W / 2.0) {
+            // Ribbon::split (Ribbon.cpp:9-17): piece = start -> projection, remainder = projection -> end; cover() keeps
+            // whichever is not short enough to be "covered" (RibbonManager.cpp:14-22).  Exactly one of the two survives
+            // when the boat runs along the ribbon: the remainder ahead (travelling start -> end) or the piece ahead
+            // (travelling end -> start).  Either way the list keeps its structure and the ribbon is updated in place.
             RibbonD piece = {rb.sx, rb.sy, px, py};
             RibbonD rest = {px, py, rb.ex, rb.ey};
-            if (!ribbon_covered(piece, true, W) || ribbon_covered(rest, true, W)) return 0; // the list's structure changes
-            if (upd >= 0) return 0;                                                           // two ribbons at once: general path
-            upd = r; upx = px; upy = py;
-            ch = (px != rb.sx) || (py != rb.sy);
+            const bool keep_piece = !ribbon_covered(piece, true, W), keep_rest = !ribbon_covered(rest, true, W);
+            if (keep_piece == keep_rest) return 0; // both kept (insertion) or both erased: the list's structure changes
+            if (upd >= 0) return 0;                // two ribbons at once: general path
+            upd = r;
+            if (keep_rest) { nsx = px; nsy = py; nex = rb.ex; ney = rb.ey; ch = (px != rb.sx) || (py != rb.sy); }
+            else { nsx = rb.sx; nsy = rb.sy; nex = px; ney = py; ch = true; } // the remainder was erased
         }
     }
     if (!inside) return 2; // d >= W for every ribbon whose projection is contained: nothing to cover, distance from the end points
-    if (upd >= 0 && lane == 0) cur[upd] = pack_ribbon(upx, upy, cur[upd].z, cur[upd].w);
+    if (upd >= 0 && lane == 0) cur[upd] = pack_ribbon(nsx, nsy, nex, ney);
     __syncwarp();
     *changed = ch;
     return 1;

@@ -16,11 +16,15 @@ for name in ("c2", "c5"):
     sid = world.upload(eng)
     world.upload(ora)
     rb = world.ribbons[3]
-    for cov in (1, 0):
+    for cov, rev in ((1, 0), (0, 0), (1, 1)):
         e = np.zeros(1, dtype=abi.EDGE_DTYPE)
-        # start on the ribbon's line, a little before its start, heading along it; destination 80 m further on
-        e["src"][0] = [rb[0], rb[1] + 20.0, 0.0, 2.5, 1.0]
-        e["dst"][0] = [rb[0], rb[1] + 100.0, 0.0, 2.5]
+        # on the ribbon's line, heading along it for 80 m: from its start towards its end, or (rev) the other way round
+        if not rev:
+            e["src"][0] = [rb[0], rb[1] + 20.0, 0.0, 2.5, 1.0]
+            e["dst"][0] = [rb[0], rb[1] + 100.0, 0.0, 2.5]
+        else:
+            e["src"][0] = [rb[0], rb[3] - 20.0, np.pi, 2.5, 1.0]
+            e["dst"][0] = [rb[0], rb[3] - 100.0, np.pi, 2.5]
         e["coverage_allowed"] = cov
         e["ribbon_set"] = sid
         want = ora.true_cost_batch(e)
@@ -40,6 +44,6 @@ for name in ("c2", "c5"):
             t0 = time.perf_counter()
             eng.true_cost_batch(f)
             tf.append(time.perf_counter() - t0)
-        print("%s cov=%d: survey-line edge %.3f ms (fixed cost of a 1-edge batch %.3f ms) check-points %d samples %d changed %d parity %s" % (
-            name, cov, np.median(ts) * 1e3, np.median(tf) * 1e3, int(got["n_checkpoints"][0]), int(got["n_samples"][0]),
+        print("%s cov=%d rev=%d: survey-line edge %.3f ms (fixed cost of a 1-edge batch %.3f ms) check-points %d samples %d changed %d parity %s" % (
+            name, cov, rev, np.median(ts) * 1e3, np.median(tf) * 1e3, int(got["n_checkpoints"][0]), int(got["n_samples"][0]),
             int(got["ribbons_changed"][0]), "ok" if not bad else bad))

@@ -66,6 +66,11 @@ struct ppe_ctx {
     std::vector<double> h_ribbons; // 4 doubles per ribbon
     std::vector<int> h_off, h_cnt;
     std::vector<double> h_cct;
+    std::vector<double> h_sumlen;  // per set, see WorldD::set_sumlen
+    std::vector<int> h_tame;
+    double sets_width = -1;        // ribbon width the per-set sums were computed with
+    double* d_sumlen = nullptr;
+    int* d_tame = nullptr;
     bool sets_dirty = true;
     size_t uploaded_ribbons = 0, uploaded_sets = 0; // the pool is append-only: only the tail is copied
     int max_set = 0;
@@ -191,14 +196,27 @@ int upload_sets(ppe_ctx* ctx) {
     if (!ctx->sets_dirty) return PPE_OK;
     const size_t nr = ctx->h_ribbons.size() / 4, ns = ctx->h_cnt.size();
     if (ctx->uploaded_ribbons > nr || ctx->uploaded_sets > ns) ctx->uploaded_ribbons = ctx->uploaded_sets = 0;
+    if (ctx->sets_width != ctx->cfg.ribbon_width) { // the per-set sums depend on the ribbon width: recompute and upload all
+        ctx->sets_width = ctx->cfg.ribbon_width;
+        for (size_t k = 0; k < ns; k++) {
+            double sum = 0;
+            const double* r = ctx->h_ribbons.data() + 4 * (size_t)ctx->h_off[k];
+            for (int q = 0; q < ctx->h_cnt[k]; q++, r += 4)
+                sum += sqrt((r[2] - r[0]) * (r[2] - r[0]) + (r[3] - r[1]) * (r[3] - r[1])) - 2 * ctx->sets_width;
+            ctx->h_sumlen[k] = sum;
+        }
+        ctx->uploaded_sets = 0;
+    }
     const size_t r0 = ctx->uploaded_ribbons, s0 = ctx->uploaded_sets;
     int rc = grow_keep(ctx, &ctx->d_ribbons, &ctx->cap_ribbons, nr + 1, r0, 1024);
     if (rc != PPE_OK) return rc;
     {
-        size_t c1 = ctx->cap_sets, c2 = ctx->cap_sets, c3 = ctx->cap_sets;
+        size_t c1 = ctx->cap_sets, c2 = ctx->cap_sets, c3 = ctx->cap_sets, c4 = ctx->cap_sets, c5 = ctx->cap_sets;
         rc = grow_keep(ctx, &ctx->d_off, &c1, ns + 1, s0, 64);
         if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_cnt, &c2, ns + 1, s0, 64);
         if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_cct, &c3, ns + 1, s0, 64);
+        if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_sumlen, &c4, ns + 1, s0, 64);
+        if (rc == PPE_OK) rc = grow_keep(ctx, &ctx->d_tame, &c5, ns + 1, s0, 64);
         if (rc != PPE_OK) return rc;
         ctx->cap_sets = c1;
     }
@@ -209,6 +227,8 @@ int upload_sets(ppe_ctx* ctx) {
         PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_off + s0, ctx->h_off.data() + s0, (ns - s0) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cnt + s0, ctx->h_cnt.data() + s0, (ns - s0) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cct + s0, ctx->h_cct.data() + s0, (ns - s0) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_sumlen + s0, ctx->h_sumlen.data() + s0, (ns - s0) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_tame + s0, ctx->h_tame.data() + s0, (ns - s0) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
     // batches run on other streams (caller's / the lanes'): the tail must have landed before they start
     PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -306,6 +326,8 @@ int make_world(ppe_ctx* ctx, WorldD* w) {
     w->set_offset = ctx->d_off;
     w->set_count = ctx->d_cnt;
     w->set_cct = ctx->d_cct;
+    w->set_sumlen = ctx->d_sumlen;
+    w->set_tame = ctx->d_tame;
     w->n_sets = (int)ctx->h_cnt.size();
     w->ribbon_cap = ribbon_cap_for(ctx->max_set);
     w->out_ribbons = ctx->d_out_ribbons;
@@ -376,7 +398,7 @@ void ppe_destroy(ppe_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_map); cudaFree(ctx->d_safe); cudaFree(ctx->d_safe_tmp); cudaFree(ctx->d_obs);
-    cudaFree(ctx->d_ribbons); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct);
+    cudaFree(ctx->d_ribbons); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct); cudaFree(ctx->d_sumlen); cudaFree(ctx->d_tame);
     cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_prepared); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
     cudaFree(ctx->d_work); cudaFree(ctx->d_heavy); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
@@ -540,6 +562,19 @@ int ppe_put_ribbon_set(ppe_ctx* ctx, int n, const double* xyxy, double coverage_
     ctx->h_off.push_back(off);
     ctx->h_cnt.push_back(kept);
     ctx->h_cct.push_back(coverage_completed_time);
+    {
+        // invariants of the list as it stands: the same sum RibbonManager::maxDistance accumulates (list order, IEEE sqrt)
+        double sum = 0;
+        int tame = 1;
+        for (int q = 0; q < n; q++) {
+            const double* r = xyxy + 4 * (size_t)q;
+            sum += sqrt((r[2] - r[0]) * (r[2] - r[0]) + (r[3] - r[1]) * (r[3] - r[1])) - 2 * ctx->cfg.ribbon_width;
+            if (!(fabs(r[0]) < 1e7 && fabs(r[1]) < 1e7 && fabs(r[2]) < 1e7 && fabs(r[3]) < 1e7)) tame = 0;
+        }
+        if (ctx->sets_width < 0 || ctx->h_sumlen.empty()) ctx->sets_width = ctx->cfg.ribbon_width;
+        ctx->h_sumlen.push_back(sum);
+        ctx->h_tame.push_back(tame);
+    }
     if (kept > ctx->max_set) ctx->max_set = kept;
     ctx->sets_dirty = true;
     *set_id = (int32_t)ctx->h_cnt.size() - 1;
@@ -548,7 +583,7 @@ int ppe_put_ribbon_set(ppe_ctx* ctx, int n, const double* xyxy, double coverage_
 
 int ppe_clear_ribbon_sets(ppe_ctx* ctx) {
     if (!ctx) return PPE_ERR_INVALID;
-    ctx->h_ribbons.clear(); ctx->h_off.clear(); ctx->h_cnt.clear(); ctx->h_cct.clear();
+    ctx->h_ribbons.clear(); ctx->h_off.clear(); ctx->h_cnt.clear(); ctx->h_cct.clear(); ctx->h_sumlen.clear(); ctx->h_tame.clear();
     ctx->max_set = 0;
     ctx->uploaded_ribbons = ctx->uploaded_sets = 0;
     ctx->sets_dirty = true;

@@ -987,6 +987,48 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                     next_cp = base + limit;
                     break;
                 }
+                // ---- run along ONE ribbon: consecutive check-points (toCoverDistance stays 0 inside a ribbon) that all
+                // fall on the single relevant ribbon of this chunk and leave the list's structure alone.  The ribbon lives in
+                // registers for the whole run; each step is the arithmetic of fast_checkpoint for that ribbon, nothing else.
+                // The first step that is not of this kind leaves the run untouched and goes through the code below.
+                if (n_rel == 1 && tame && !any_short && (cov || l > 0)) {
+                    PROF_T(t_r);
+                    const int ri = rel[0];
+                    RibbonD rb = load_ribbon(cur + ri);
+                    bool dirty = false;
+                    int q = l;
+#pragma unroll 1
+                    for (; q < limit; q++) {
+                        const double rx = __shfl_sync(kFull, x, q), ry = __shfl_sync(kFull, y, q);
+                        bool do_cover = cov;
+                        if (!cov) do_cover = heading_of(__shfl_sync(kFull, ang, q - 1)) == heading_of(__shfl_sync(kFull, ang, q));
+                        if (!ribbon_may_contain(rb, rx, ry, W, true)) break;
+                        double px, py;
+                        ribbon_projection(rb, rx, ry, &px, &py);
+                        if (!ribbon_contains_projection(rb, px, py)) break;
+                        const double d = ribbon_distance(rb, rx, ry);
+                        if (!(d < W)) break; // not inside: minDistanceFrom needs the end points
+                        if (do_cover && d < W / 2.0) {
+                            const RibbonD piece = {rb.sx, rb.sy, px, py};
+                            const RibbonD rest = {px, py, rb.ex, rb.ey};
+                            const bool keep_piece = !ribbon_covered(piece, true, W), keep_rest = !ribbon_covered(rest, true, W);
+                            if (keep_piece == keep_rest) break; // the list's structure changes
+                            if (keep_rest) { if (px != rb.sx || py != rb.sy) modified = true; rb.sx = px; rb.sy = py; }
+                            else { modified = true; rb.ex = px; rb.ey = py; }
+                            dirty = true;
+                        }
+                        n_cp++;
+#ifdef PPE_K2B_PROFILE
+                        prof[8] += 1;
+#endif
+                    }
+                    if (dirty) {
+                        if (lane == 0) cur[ri] = pack_ribbon(rb.sx, rb.sy, rb.ex, rb.ey);
+                        __syncwarp();
+                    }
+                    PROF_ADD(4, t_r);
+                    if (q > l) { next_cp = base + q; continue; } // toCoverDistance was 0 at every step: the next sample is a check-point
+                }
                 const double cx = __shfl_sync(kFull, x, l), cy = __shfl_sync(kFull, y, l);
                 const double ct = __shfl_sync(kFull, t_i, l);
                 const double ch = heading_of(__shfl_sync(kFull, ang, l));
@@ -1251,12 +1293,12 @@ __device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib
     return inside ? 0.0 : sqrt(mn);
 }
 
-__device__ __forceinline__ double seq_max_distance(const double4* __restrict__ rib, int nr, double x, double y, double W) {
-    double sumLength = 0, mn = DBL_MAX, mx = 0;
+// the same with the list's length sum taken from the per-set invariant (the unchanged parent list)
+__device__ __forceinline__ double seq_max_distance_presummed(const double4* __restrict__ rib, int nr, double x, double y, double sumLength) {
+    double mn = DBL_MAX, mx = 0;
 #pragma unroll 1
-    for (int r = 0; r < nr; r++) { // list order, as the reference sums (RibbonManager.cpp:234-248)
+    for (int r = 0; r < nr; r++) {
         const RibbonD rb = load_ribbon(rib + r);
-        sumLength += sqrt(ribbon_sqlen(rb)) - 2 * W;
         const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
         const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
         mn = fmin(fmin(mn, dEnd), dStart); // squared
@@ -1316,10 +1358,7 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     }
     bool tame = fabs(pe[kX0]) + fabs(pe[kLength]) < 1e7 && fabs(pe[kY0]) + fabs(pe[kLength]) < 1e7 && fabs(edge->src[0]) < 1e7 &&
                 fabs(edge->src[1]) < 1e7;
-    if (!heavy) {
-#pragma unroll 1
-        for (int r = 0; r < nr; r++) tame = tame && coords_tame(load_ribbon(rib + r));
-    }
+    if (!heavy) tame = tame && w.set_tame[set] != 0;
     const double src_t = edge->src[4];
     const bool cov = edge->coverage_allowed != 0;
     const double endTime = fmin(w.horizon_end, pe[kWEnd]);
@@ -1502,7 +1541,8 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     const double true_cost = T * cfg.time_penalty_factor + penalty;
     const double g = edge->src_g + true_cost;
     double h;
-    if (cfg.heuristic == PPE_H_MAX_DISTANCE) h = seq_max_distance(rib, nr, ex, ey, W) / cfg.max_speed * cfg.time_penalty_factor;
+    if (cfg.heuristic == PPE_H_MAX_DISTANCE)
+        h = seq_max_distance_presummed(rib, nr, ex, ey, w.set_sumlen[set]) / cfg.max_speed * cfg.time_penalty_factor;
     else h = tsp_heuristic_or_unset(cfg, rib, nr, ex, ey);
     ppe_edge_result* r = results + ei;
     r->true_cost = true_cost;

@@ -53,6 +53,10 @@ struct WorldD {
     const int* set_offset;
     const int* set_count;
     const double* set_cct;      // coverageCompletedTime
+    // per-set invariants of the UNCHANGED list (what the thread walker evaluates): sum over the list, in list order, of
+    // length - 2 * RibbonWidth (RibbonManager::maxDistance, RibbonManager.cpp:238-240) and "all coordinates below 1e7"
+    const double* set_sumlen;
+    const int* set_tame;
     int n_sets;
     int ribbon_cap;             // per-warp working capacity (ribbons)
     // ribbons-after output pool

@@ -169,32 +169,48 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
     const int N = p.n_samples;
     int flag = 0;
 
-    double r2 = p.r2_init;
+    // Candidates are taken in BANDS of increasing distance: (r_lo2, r_hi2] in squared distance, first band a disc sized from
+    // the sample density.  A band that does not fit the shared-memory capacity is shrunk; when a band is consumed and the
+    // loop of :91 is still running, the next band continues with the heaps as they stand -- the consumed prefix can be
+    // arbitrarily long (deep anytime iterations: 10^6..10^7 samples) with a fixed shared-memory footprint.
+    double r_lo2 = -1.0, r_hi2 = p.r2_init > 0 ? p.r2_init : 1.0;
     int n = 0;
-    bool complete = false; // the candidate list holds every resident sample
-    bool shrunk = false;   // the disc had to shrink to fit the candidate capacity
-    for (int pass = 0; pass < 64; pass++) {
-        // ---- (1) collect the samples within sqrt(r2) of the vertex ---------------------------------------------------
+    long long seen = 0;      // samples in the bands consumed so far
+    bool complete = false;   // every resident sample lies in a band consumed so far
+    bool tie_probe = false;  // both radii finished exactly at the end of a band: only the first sample beyond it is needed
+    double last_d = -1.0;    // distance of the last candidate of the previous band
+    if (tid == 0) {
+        s.heap[0].size = s.heap[1].size = 0;
+        s.done[0] = s.done[1] = 0;
+        s.free_id[0] = s.free_id[1] = p.k;
+        s.pops = 0; s.solves = 0; s.consumed = 0; s.tie = 0;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 4096; pass++) {
+        // ---- (1) collect the samples of the band ------------------------------------------------------------------------
         if (tid == 0) s.count = 0;
         __syncthreads();
         for (int i = tid; i < N; i += kSelThreads) {
             const double dx = sx - p.sx[i], dy = sy - p.sy[i];
             const double d2 = dx * dx + dy * dy; // State::distanceTo (State.cpp:91-93), squared
-            if (d2 <= r2) {
+            if (d2 > r_lo2 && d2 <= r_hi2) {
                 const int slot = atomicAdd(&s.count, 1);
                 if (slot < kSelCap) { s_d[slot] = d2; s_idx[slot] = i; }
             }
         }
         __syncthreads();
         const int cnt = s.count;
-        if (cnt > kSelCap) { // too many: shrink the disc (uniform density -> count ~ r2)
-            r2 = r2 * (0.75 * (double)kSelCap / (double)cnt);
-            shrunk = true;
+        if (cnt > kSelCap) { // too many: shrink the band (uniform density -> count ~ area)
+            const double lo = r_lo2 > 0 ? r_lo2 : 0.0;
+            const double shrunk_hi = lo + (r_hi2 - lo) * (0.75 * (double)kSelCap / (double)cnt);
+            if (!(shrunk_hi < r_hi2) || !(shrunk_hi > lo)) { flag |= PPE_EXPAND_OVERFLOW; break; } // > capacity samples at one distance
+            r_hi2 = shrunk_hi;
             __syncthreads();
             continue;
         }
         n = cnt;
-        complete = (n == N);
+        seen += n;
+        complete = (seen >= (long long)N);
         // ---- (2) sort by (distance, sample index) -------------------------------------------------------------------------
         int P = 32;
         while (P < n) P <<= 1;
@@ -218,14 +234,13 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
                 __syncthreads();
             }
         }
-        // ---- (3) replay of the k-nearest loop, kSelThreads candidates per step ---------------------------------------------------------
-        if (tid == 0) {
-            s.heap[0].size = s.heap[1].size = 0;
-            s.done[0] = s.done[1] = 0;
-            s.free_id[0] = s.free_id[1] = p.k;
-            s.pops = 0; s.solves = 0; s.consumed = 0; s.tie = 0;
-        }
+        // a sample of this band at exactly the distance of the previous band's last one (distinct squares can round to
+        // the same square root): the reference's pop order between the two depends on its heap arrangement
+        if (n > 0 && last_d >= 0 && s_d[0] == last_d) flag |= PPE_EXPAND_TIE;
+        if (tie_probe) break; // the loop had already ended: this band was only collected for the check above
+        if (tid == 0) s.consumed = 0;
         __syncthreads();
+        // ---- (3) replay of the k-nearest loop, kSelThreads candidates per step ---------------------------------------------------------
         {
             // every thread of the CTA solves one candidate (both radii) per step; thread 0 then replays the loop body for
             // those kSelThreads candidates in order
@@ -293,16 +308,18 @@ k_expand_select(const ExpandParamsD p, const ppe_vertex* __restrict__ verts, ppe
             if (tid == 0) s.tie = tie;
         }
         __syncthreads();
-        // ran out of candidates before both radii finished although more samples exist: widen the disc
-        if (!(s.done[0] && s.done[1]) && !complete && !shrunk) {
-            r2 = r2 * 4.0;
-            __syncthreads();
-            continue;
-        }
-        break;
+        if (s.tie) flag |= PPE_EXPAND_TIE;
+        const bool finished = s.done[0] && s.done[1];
+        if (complete) break;                       // nothing beyond this band
+        if (finished && s.consumed < n) break;     // the loop ended inside the band: the next candidate was compared above
+        // the band is consumed: go on with the next one -- to continue the loop, or (finished exactly at its end) only to
+        // compare its first sample with the last one popped
+        if (n > 0) last_d = s_d[n - 1];
+        tie_probe = finished;
+        r_lo2 = r_hi2;
+        r_hi2 = pass > 48 ? DBL_MAX : r_hi2 * 4.0;
+        __syncthreads();
     }
-    if (!(s.done[0] && s.done[1]) && !complete) flag |= PPE_EXPAND_OVERFLOW;
-    if (s.tie) flag |= PPE_EXPAND_TIE;
 
     // ---- (4) emit the edges in the reference's push order ---------------------------------------------------------------------
     // slot layout: [endpoint edges: speed-major, radius-minor] [radius 0 winners in heap-array order x speeds] [radius 1 ...]

@@ -815,7 +815,8 @@ __device__ unsigned long long g_k2b_prof[16];
 // back the pose of a sample index either from the lanes (shuffle) or by direct evaluation.
 __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* __restrict__ edge,
                              const PreparedEdge* __restrict__ prep, ppe_edge_result* __restrict__ result,
-                             const ObstacleD* s_obs, double4* bufA, double4* bufB, double* pe, TimeTable* tt, int* rel, int lane) {
+                             const ObstacleD* s_obs, double4* bufA, double4* bufB, double* pe, TimeTable* tt, int* rel, double* cp_pose,
+                             int lane) {
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width;
     const double inc = cfg.collision_checking_increment;
@@ -977,6 +978,13 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
             PROF_ADD(3, t_l);
             // ---- ribbon check-points of this chunk, in order (Edge.cpp:153-172) ---------------------------------
             int n_rel = -2; // relevant-ribbon list of this chunk: -2 not built yet, -1 too many, else count
+            if (next_cp < base + limit) {
+                // the chunk's poses go to shared memory once (x, y, heading per sample): the check-point loop below is
+                // uniform scalar work and reads them as broadcasts instead of shuffling them out of the lanes one by one
+                __syncwarp();
+                cp_pose[lane] = x; cp_pose[32 + lane] = y; cp_pose[64 + lane] = heading_of(ang);
+                __syncwarp();
+            }
             while (next_cp < base + limit) {
                 const int l = next_cp - base;
                 if (nr == 0 && cct != -1 && !(cct + cfg.time_minimum < endTime)) {
@@ -999,10 +1007,8 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                     int q = l;
 #pragma unroll 1
                     for (; q < limit; q++) {
-                        const double rx = __shfl_sync(kFull, x, q), ry = __shfl_sync(kFull, y, q);
-                        bool do_cover = cov;
-                        if (!cov) do_cover = heading_of(__shfl_sync(kFull, ang, q - 1)) == heading_of(__shfl_sync(kFull, ang, q));
-                        if (!ribbon_may_contain(rb, rx, ry, W, true)) break;
+                        const double rx = cp_pose[q], ry = cp_pose[32 + q];
+                        const bool do_cover = cov || cp_pose[64 + q - 1] == cp_pose[64 + q]; // lastHeading == heading, Edge.cpp:159
                         double px, py;
                         ribbon_projection(rb, rx, ry, &px, &py);
                         if (!ribbon_contains_projection(rb, px, py)) break;
@@ -1029,10 +1035,9 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                     PROF_ADD(4, t_r);
                     if (q > l) { next_cp = base + q; continue; } // toCoverDistance was 0 at every step: the next sample is a check-point
                 }
-                const double cx = __shfl_sync(kFull, x, l), cy = __shfl_sync(kFull, y, l);
+                const double cx = cp_pose[l], cy = cp_pose[32 + l];
                 const double ct = __shfl_sync(kFull, t_i, l);
-                const double ch = heading_of(__shfl_sync(kFull, ang, l));
-                const double pang = __shfl_sync(kFull, ang, l > 0 ? l - 1 : 0);
+                const double ch = cp_pose[64 + l];
                 n_cp++;
                 bool do_cover = cov;
                 if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159: heading of the sample before
@@ -1040,7 +1045,7 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
                     if (next_cp == 0) {
                         ph = edge->src[2];
                     } else if (l > 0) {
-                        ph = heading_of(pang);
+                        ph = cp_pose[64 + l - 1];
                     } else { // the last sample of the previous chunk
                         double px_, py_, pa_;
                         bool it_;
@@ -1599,6 +1604,7 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
     __shared__ double s_pe[kWarpsPerBlock][kPrepDoubles];
     __shared__ TimeTable s_tt[kWarpsPerBlock];
     __shared__ int s_rel[kWarpsPerBlock][kRelCap];
+    __shared__ double s_cp_pose[kWarpsPerBlock][96];
     double* pe = s_pe[warp];
 
     const unsigned long long n_front = heavy_list ? (unsigned long long)heavy_count[0] : 0ull;
@@ -1618,7 +1624,7 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
         k = __shfl_sync(kFull, k, 0);
         if (k >= todo) break;
         const unsigned long long ei = !heavy_list ? k : (unsigned long long)(k < n_front ? heavy_list[k] : heavy_list[n - 1 - (k - n_front)]);
-        process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], s_rel[warp], lane);
+        process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], s_rel[warp], s_cp_pose[warp], lane);
         __syncwarp();
     }
 }

@@ -200,10 +200,16 @@ int upload_sets(ppe_ctx* ctx) {
         ctx->sets_width = ctx->cfg.ribbon_width;
         for (size_t k = 0; k < ns; k++) {
             double sum = 0;
+            int any_short = 0;
+            const double ml = 2 * ctx->sets_width; // Ribbon::minLength(); covered(strict): |e|^2 < ml^2 / (2 * 2), Ribbon.cpp:23-25
             const double* r = ctx->h_ribbons.data() + 4 * (size_t)ctx->h_off[k];
-            for (int q = 0; q < ctx->h_cnt[k]; q++, r += 4)
-                sum += sqrt((r[2] - r[0]) * (r[2] - r[0]) + (r[3] - r[1]) * (r[3] - r[1])) - 2 * ctx->sets_width;
+            for (int q = 0; q < ctx->h_cnt[k]; q++, r += 4) {
+                const double sq = (r[2] - r[0]) * (r[2] - r[0]) + (r[3] - r[1]) * (r[3] - r[1]);
+                sum += sqrt(sq) - 2 * ctx->sets_width;
+                if (sq < ml * ml / (2.0 * 2.0)) any_short = 1;
+            }
             ctx->h_sumlen[k] = sum;
+            ctx->h_tame[k] = (ctx->h_tame[k] & 1) | (any_short ? 2 : 0);
         }
         ctx->uploaded_sets = 0;
     }
@@ -376,6 +382,8 @@ int ppe_create(int device, ppe_ctx** out) {
         if (env_cp && atoi(env_cp) > 0) ctx->tuning.cp_budget = atoi(env_cp);
         const char* env_d = getenv("PPE_K2T_DIRTY");  // tuning knob: non-clean chunks a K2t thread may evaluate
         if (env_d) ctx->tuning.dirty_budget = atoi(env_d);
+        const char* env_k2c = getenv("PPE_DEEP_WALKER");
+        if (env_k2c && env_k2c[0] == '0') ctx->tuning.deep_walker = 0;
         ctx->tuning = clamp_tuning(ctx->tuning);
     }
     bool ok = cudaMalloc((void**)&ctx->d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
@@ -565,15 +573,18 @@ int ppe_put_ribbon_set(ppe_ctx* ctx, int n, const double* xyxy, double coverage_
     {
         // invariants of the list as it stands: the same sum RibbonManager::maxDistance accumulates (list order, IEEE sqrt)
         double sum = 0;
-        int tame = 1;
+        int tame = 1, any_short = 0;
+        const double ml = 2 * ctx->cfg.ribbon_width; // Ribbon::minLength(); covered(strict): |e|^2 < ml^2 / (2 * 2), Ribbon.cpp:23-25
         for (int q = 0; q < n; q++) {
             const double* r = xyxy + 4 * (size_t)q;
-            sum += sqrt((r[2] - r[0]) * (r[2] - r[0]) + (r[3] - r[1]) * (r[3] - r[1])) - 2 * ctx->cfg.ribbon_width;
+            const double sq = (r[2] - r[0]) * (r[2] - r[0]) + (r[3] - r[1]) * (r[3] - r[1]);
+            sum += sqrt(sq) - 2 * ctx->cfg.ribbon_width;
+            if (sq < ml * ml / (2.0 * 2.0)) any_short = 1;
             if (!(fabs(r[0]) < 1e7 && fabs(r[1]) < 1e7 && fabs(r[2]) < 1e7 && fabs(r[3]) < 1e7)) tame = 0;
         }
         if (ctx->sets_width < 0 || ctx->h_sumlen.empty()) ctx->sets_width = ctx->cfg.ribbon_width;
         ctx->h_sumlen.push_back(sum);
-        ctx->h_tame.push_back(tame);
+        ctx->h_tame.push_back(tame | (any_short ? 2 : 0));
     }
     if (kept > ctx->max_set) ctx->max_set = kept;
     ctx->sets_dirty = true;
@@ -661,7 +672,7 @@ static int run_batch_device(ppe_ctx* ctx, const WorldD& w, int64_t n, const ppe_
     int rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, (size_t)n * prepared_edge_bytes());
     if (rc != PPE_OK) return rc;
     if (ctx->thread_walker) {
-        rc = grow(ctx, &ctx->d_heavy, &ctx->cap_heavy, (size_t)n);
+        rc = grow(ctx, &ctx->d_heavy, &ctx->cap_heavy, 2 * (size_t)n);
         if (rc != PPE_OK) return rc;
     }
     int blocks = 1, launches = 0;
@@ -753,7 +764,7 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
             rc = grow(ctx, &ln.d_prepared, &ln.cap_prepared, (size_t)cnt * prepared_edge_bytes());
             if (rc != PPE_OK) return rc;
             if (ctx->thread_walker) {
-                rc = grow(ctx, &ln.d_heavy, &ln.cap_heavy, (size_t)cnt);
+                rc = grow(ctx, &ln.d_heavy, &ln.cap_heavy, 2 * (size_t)cnt);
                 if (rc != PPE_OK) return rc;
             }
             PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_edges + lo, edges + lo, (size_t)cnt * sizeof(ppe_edge), cudaMemcpyHostToDevice, ctx->stream_in));
@@ -948,7 +959,7 @@ int ppe_expand_batch(ppe_ctx* ctx, int n, const ppe_vertex* vertices, int32_t* n
     rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, slots * prepared_edge_bytes());
     if (rc != PPE_OK) return rc;
     if (ctx->thread_walker) {
-        rc = grow(ctx, &ctx->d_heavy, &ctx->cap_heavy, slots);
+        rc = grow(ctx, &ctx->d_heavy, &ctx->cap_heavy, 2 * slots);
         if (rc != PPE_OK) return rc;
     }
     // pinned staging: [vertices][children][4 int arrays]

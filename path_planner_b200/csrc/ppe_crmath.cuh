@@ -29,10 +29,19 @@ struct dd {
 // coefficient / lookup tables: one copy for device code, one for host code
 #if defined(__CUDACC__)
 #define PPE_TABLE_DECL(name, dims, init) \
-    static __device__ const double d_##name dims = init; \
+    static __constant__ double d_##name dims = init; \
     static const double h_##name dims = init;
 #else
 #define PPE_TABLE_DECL(name, dims, init) static const double h_##name dims = init;
+#endif
+// The double-double Horner steps are ~40 instructions each.  Unrolled, the three polynomial kernels are tens of KB of
+// straight-line code that every warp streams through the instruction cache once per call (ncu: no_instruction was the top
+// stall of k2a_prepare); rolled, they are a few hundred bytes with the coefficients in constant memory.  Same operations,
+// same order, same bits.
+#if defined(__CUDACC__)
+#define PPE_ROLLED _Pragma("unroll 1")
+#else
+#define PPE_ROLLED
 #endif
 #if defined(__CUDA_ARCH__)
 #define PPE_TABLE(name) d_##name
@@ -133,7 +142,7 @@ PPE_HD dd sin_kernel(dd r) {
     const double (*C)[2] = PPE_TABLE(sin_coeffs);
     const dd z = dd_mul(r, r);
     dd p = dd{C[crtab::kSinCosTerms - 1][0], C[crtab::kSinCosTerms - 1][1]};
-#pragma unroll
+    PPE_ROLLED
     for (int k = crtab::kSinCosTerms - 2; k >= 0; k--) p = dd_add(dd_mul(p, z), dd{C[k][0], C[k][1]});
     // sin r = r + r * z * p
     return dd_add(r, dd_mul(dd_mul(r, z), p));
@@ -142,7 +151,7 @@ PPE_HD dd cos_kernel(dd r) {
     const double (*C)[2] = PPE_TABLE(cos_coeffs);
     const dd z = dd_mul(r, r);
     dd p = dd{C[crtab::kSinCosTerms - 1][0], C[crtab::kSinCosTerms - 1][1]};
-#pragma unroll
+    PPE_ROLLED
     for (int k = crtab::kSinCosTerms - 2; k >= 0; k--) p = dd_add(dd_mul(p, z), dd{C[k][0], C[k][1]});
     // cos r = 1 + z * p
     return dd_add_d(dd_mul(z, p), 1.0);
@@ -186,7 +195,7 @@ PPE_HD dd atan_dd_unit(dd q) {
     const dd t = dd_div(num, den);
     const dd z = dd_mul(t, t);
     dd p = dd{C[crtab::kAtanTerms - 1][0], C[crtab::kAtanTerms - 1][1]};
-#pragma unroll
+    PPE_ROLLED
     for (int k = crtab::kAtanTerms - 2; k >= 0; k--) p = dd_add(dd_mul(p, z), dd{C[k][0], C[k][1]});
     const dd at = dd_add(t, dd_mul(dd_mul(t, z), p));
     return dd_add(dd{T[i][0], T[i][1]}, at);

@@ -1312,30 +1312,118 @@ __device__ __forceinline__ double seq_max_distance_presummed(const double4* __re
     return fmax(sumLength + sqrt(mn), sqrt(mx));
 }
 
-__global__ void __launch_bounds__(128)
-k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
-                const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
-                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, const int dirty_budget,
-                const int cp_budget) {
-    extern __shared__ double4 smem4[];
-    ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
-    {
-        const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
-        double* dst = reinterpret_cast<double*>(s_obs);
-        const double* src = reinterpret_cast<const double*>(w.obstacles);
-        for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = src[i];
+// ---- K2c: the deep thread walker ----------------------------------------------------------------------------------------
+// Edges that K2t hands over because they COVER a ribbon (a check-point on every sample while the boat is on it, up to
+// 1500 in a row) are strictly sequential scalar work; the warp walker executes that chain redundantly in all 32 lanes.
+// K2c walks them one thread per edge -- 32 chains per warp instruction -- as long as the ribbon list keeps its STRUCTURE:
+// cover() only moves the start (or the end) of the ribbon the boat is on, which is kept in a two-entry per-thread override
+// table over the parent's interned list; per 32-sample chunk only the ribbons whose bounding box can be reached are
+// looked at.  A split that inserts or erases a ribbon, a third modified ribbon, a list with a ribbon short enough to be
+// erased wherever the point is, or more per-sample work than the dirty-chunk budget sends the edge on to the warp walker.
+struct RibbonOverrides {
+    double4 val[2];
+    int idx[2];
+    int n;
+};
+constexpr int kDeepRelCap = 4;
+
+__device__ __forceinline__ RibbonD load_ribbon_ov(const double4* __restrict__ rib, int r, const RibbonOverrides& ov) {
+    if (ov.n > 0 && r == ov.idx[0]) return RibbonD{ov.val[0].x, ov.val[0].y, ov.val[0].z, ov.val[0].w};
+    if (ov.n > 1 && r == ov.idx[1]) return RibbonD{ov.val[1].x, ov.val[1].y, ov.val[1].z, ov.val[1].w};
+    return load_ribbon(rib + r);
+}
+
+// ribbons (of the parent's list: overrides only shrink them) that a pose within `reach` of (x, y) could be contained in
+__device__ __forceinline__ int deep_relevant(const double4* __restrict__ rib, int nr, double x, double y, double reach, double W, int* rel) {
+    const double grow = W * (1 + 1e-9) + 2e-3 + reach;
+    int n = 0;
+#pragma unroll 1
+    for (int r = 0; r < nr; r++) {
+        const RibbonD rb = load_ribbon(rib + r);
+        const bool near = !(x < fmin(rb.sx, rb.ex) - grow || x > fmax(rb.sx, rb.ex) + grow || y < fmin(rb.sy, rb.ey) - grow ||
+                            y > fmax(rb.sy, rb.ey) + grow);
+        if (near) {
+            if (n < kDeepRelCap) rel[n] = r;
+            n++;
+        }
     }
-    __syncthreads();
-    // N2: shared-memory tile of the occupancy and safe bitmaps around the batch's bounding box (TMA bulk copies)
-    const uint32_t* tile = nullptr;
-    if (w.tile_on) {
-        __shared__ unsigned long long s_tile_bar;
-        uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4)));
-        tile_stage(w, s_tile, &s_tile_bar);
-        tile = s_tile;
+    return n <= kDeepRelCap ? n : -1;
+}
+
+// One check-point (minDistanceFrom, then cover when `do_cover`) on the relevant ribbons.  Returns false when the list's
+// structure would change or the override table is full (nothing has been modified then).
+__device__ __forceinline__ bool deep_checkpoint(const double4* __restrict__ rib, int nr, RibbonOverrides& ov, const int* rel, int n_rel,
+                                                double x, double y, double W, bool do_cover, double* to_cover, bool* modified) {
+    bool inside = false, ch = false;
+    int upd = -1;
+    double4 nv = make_double4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int q = 0; q < n_rel; q++) {
+        const int r = rel[q];
+        const RibbonD rb = load_ribbon_ov(rib, r, ov);
+        double px, py;
+        ribbon_projection(rb, x, y, &px, &py);
+        if (!ribbon_contains_projection(rb, px, py)) continue;
+        const double d = ribbon_distance(rb, x, y);
+        inside = inside || (d < W);
+        if (do_cover && d < W / 2.0) {
+            const RibbonD piece = {rb.sx, rb.sy, px, py};
+            const RibbonD rest = {px, py, rb.ex, rb.ey};
+            const bool keep_piece = !ribbon_covered(piece, true, W), keep_rest = !ribbon_covered(rest, true, W);
+            if (keep_piece == keep_rest) return false; // insertion or erasure
+            if (upd >= 0) return false;                // two ribbons at once
+            upd = r;
+            if (keep_rest) { nv = make_double4(px, py, rb.ex, rb.ey); ch = (px != rb.sx) || (py != rb.sy); }
+            else { nv = make_double4(rb.sx, rb.sy, px, py); ch = true; }
+        }
     }
-    const long long ei = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ei >= n) return;
+    if (inside) {
+        if (upd >= 0) {
+            int slot = -1;
+            if (ov.n > 0 && ov.idx[0] == upd) slot = 0;
+            else if (ov.n > 1 && ov.idx[1] == upd) slot = 1;
+            else if (ov.n < 2) { slot = ov.n; ov.n++; ov.idx[slot] = upd; }
+            if (slot < 0) return false; // a third modified ribbon
+            ov.val[slot] = nv;
+            *modified = *modified || ch;
+        }
+        *to_cover = 0.0;
+        return true;
+    }
+    // no ribbon contains the point even non-strictly: cover() cannot touch anything; nearest end point of the current list
+    double mn = DBL_MAX;
+#pragma unroll 1
+    for (int r = 0; r < nr; r++) {
+        const RibbonD rb = load_ribbon_ov(rib, r, ov);
+        const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart);
+    }
+    *to_cover = sqrt(mn);
+    return true;
+}
+
+// RibbonManager::maxDistance (RibbonManager.cpp:234-248) over a materialised list
+__device__ __forceinline__ double seq_max_distance(const double4* __restrict__ rib, int nr, double x, double y, double W) {
+    double sumLength = 0, mn = DBL_MAX, mx = 0;
+#pragma unroll 1
+    for (int r = 0; r < nr; r++) { // list order, as the reference sums
+        const RibbonD rb = load_ribbon(rib + r);
+        sumLength += sqrt(ribbon_sqlen(rb)) - 2 * W;
+        const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
+        const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
+        mn = fmin(fmin(mn, dEnd), dStart); // squared
+        mx = fmax(fmax(mx, dEnd), dStart);
+    }
+    return fmax(sumLength + sqrt(mn), sqrt(mx));
+}
+
+// The walk of ONE edge by ONE thread: kDeep = false is K2t (simple edges, the ribbon list is only read), kDeep = true is K2c.
+template <bool kDeep>
+__device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, const long long ei, const ppe_edge* __restrict__ edges,
+                                            const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
+                                            unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count,
+                                            const int dirty_budget, const int cp_budget, const ObstacleD* s_obs, const uint32_t* tile) {
     const ppe_edge* edge = edges + ei;
     const PreparedEdge* prep = prepared + ei;
     const double* pe = prep->v;
@@ -1363,7 +1451,12 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     }
     bool tame = fabs(pe[kX0]) + fabs(pe[kLength]) < 1e7 && fabs(pe[kY0]) + fabs(pe[kLength]) < 1e7 && fabs(edge->src[0]) < 1e7 &&
                 fabs(edge->src[1]) < 1e7;
-    if (!heavy) tame = tame && w.set_tame[set] != 0;
+    if (!heavy) {
+        tame = tame && (w.set_tame[set] & 1) != 0;
+        // K2c keeps the ribbons' structure: a list holding a ribbon short enough for cover() to erase it wherever the
+        // point is, or coordinates beyond the bounding-box shortcut's range, is the warp walker's
+        if (kDeep) heavy = !tame || (w.set_tame[set] & 2) != 0;
+    }
     const double src_t = edge->src[4];
     const bool cov = edge->coverage_allowed != 0;
     const double endTime = fmin(w.horizon_end, pe[kWEnd]);
@@ -1382,6 +1475,9 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     double ex = 0, ey = 0, eh = 0;
     const int status = PPE_EDGE_OK;
     bool long_run = false; // bailed out while covering a ribbon
+    RibbonOverrides ov;    // K2c: the (at most two) ribbons whose start / end cover() has moved
+    ov.n = 0;
+    bool modified = false;
     const int n_valid = prep->pad_[0]; // samples with t_i < endTime
     heavy = heavy || n_valid < 0 || n_valid > 64 * kChunk;
 
@@ -1476,15 +1572,16 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             int next_cp = 0;
             double prev_ang = 0;
             int prev_idx = -2;
+            int rel[kDeepRelCap];
+            int n_rel = 0, rel_chunk = -1;
 #pragma unroll 1
             while (next_cp < n_exec) {
-                if (++n_cp > cp_budget) { long_run = true; heavy = true; break; }
+                if (!kDeep && ++n_cp > cp_budget) { long_run = true; heavy = true; break; }
+                if (kDeep) n_cp++;
                 const int idx = next_cp;
                 double x, y, ang;
                 bool it_;
                 pose_eval(pe, tm.at(idx), &x, &y, &ang, &it_);
-                bool would_change;
-                const double toCover = seq_checkpoint(rib, nr, x, y, W, tame, &would_change);
                 bool do_cover = cov;
                 if (!cov) { // lastHeading == intermediate.heading(), Edge.cpp:159
                     double ph;
@@ -1497,7 +1594,26 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
                     }
                     do_cover = (ph == heading_of(ang));
                 }
-                if (do_cover && would_change) { long_run = true; heavy = true; break; }
+                double toCover;
+                if (!kDeep) {
+                    bool would_change;
+                    toCover = seq_checkpoint(rib, nr, x, y, W, tame, &would_change);
+                    if (do_cover && would_change) { long_run = true; heavy = true; break; }
+                } else {
+                    const int c = idx / kChunk;
+                    if (c != rel_chunk) { // ribbons any sample of this chunk can be contained in: around the chunk's middle pose
+                        const int c0 = c * kChunk;
+                        const int last = (c0 + kChunk - 1 < n_exec - 1) ? c0 + kChunk - 1 : n_exec - 1;
+                        const double t_first = tm.at(c0), t_mid = tm.at(c0 + (last - c0 + 1) / 2), t_last = tm.at(last);
+                        double mx_, my_, ma_;
+                        const bool ok_mid = pose_eval(pe, t_mid, &mx_, &my_, &ma_, &it_) && it_;
+                        const double reach = fmax(t_mid - t_first, t_last - t_mid) * w_speed * (1 + 1e-9) + 1e-6;
+                        n_rel = ok_mid && (t_first <= t_mid) && (t_mid <= t_last) ? deep_relevant(rib, nr, mx_, my_, reach, W, rel) : -1;
+                        rel_chunk = c;
+                        tm.at(idx); // the cursor moves forward again
+                    }
+                    if (n_rel < 0 || !deep_checkpoint(rib, nr, ov, rel, n_rel, x, y, W, do_cover, &toCover, &modified)) { heavy = true; break; }
+                }
                 prev_ang = ang;
                 prev_idx = idx;
                 next_cp = idx + 1 + skip_count(toCover, inc, kSkipCap);
@@ -1519,9 +1635,16 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
             eh = heading_of(ea);
             if (!in_time || !sample_ok) heavy = true; // the reference throws / stale pose: let the warp walker report it
             if (!heavy && (cov || lastHeading == P_h)) {
-                bool would_change;
-                seq_checkpoint(rib, nr, P_x, P_y, W, tame, &would_change);
-                if (would_change) heavy = true;
+                if (!kDeep) {
+                    bool would_change;
+                    seq_checkpoint(rib, nr, P_x, P_y, W, tame, &would_change);
+                    if (would_change) heavy = true;
+                } else { // the final cover at `intermediate` (Edge.cpp:182-184)
+                    int rel[kDeepRelCap];
+                    const int n_rel = deep_relevant(rib, nr, P_x, P_y, 0.0, W, rel);
+                    double unused;
+                    if (n_rel < 0 || !deep_checkpoint(rib, nr, ov, rel, n_rel, P_x, P_y, W, true, &unused, &modified)) heavy = true;
+                }
             }
         }
     }
@@ -1530,12 +1653,13 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
         // The heavy list is filled from both ends: edges that were caught covering a ribbon (they tend to run along
         // it for hundreds of check-points, milliseconds of strictly sequential work) from the front, the rest from
         // the back.  K2b takes the front first, so the longest items start first and the batch does not end on one.
-        if (long_run) {
+        // (the list has 2 n slots: an edge K2c passes on occupies a front and a back slot)
+        if (long_run && !kDeep) {
             const unsigned int k = atomicAdd(heavy_count, 1u);
             heavy_list[k] = (unsigned int)ei;
         } else {
             const unsigned int k = atomicAdd(heavy_count + 1, 1u);
-            heavy_list[n - 1 - k] = (unsigned int)ei;
+            heavy_list[2 * n - 1 - k] = (unsigned int)ei;
         }
         return;
     }
@@ -1546,9 +1670,29 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     const double true_cost = T * cfg.time_penalty_factor + penalty;
     const double g = edge->src_g + true_cost;
     double h;
-    if (cfg.heuristic == PPE_H_MAX_DISTANCE)
-        h = seq_max_distance_presummed(rib, nr, ex, ey, w.set_sumlen[set]) / cfg.max_speed * cfg.time_penalty_factor;
-    else h = tsp_heuristic_or_unset(cfg, rib, nr, ex, ey);
+    long long ribbons_offset = -1;
+    int out_status = status;
+    const double4* list = rib;
+    if (kDeep && modified) { // ribbons-after = the parent's list with the overrides applied, materialised in the pool
+        const unsigned long long off = atomicAdd(w.out_count, (unsigned long long)nr);
+        if (off + (unsigned long long)nr <= w.out_cap) {
+#pragma unroll 1
+            for (int q = 0; q < nr; q++) {
+                const RibbonD rb = load_ribbon_ov(rib, q, ov);
+                w.out_ribbons[off + q] = pack_ribbon(rb.sx, rb.sy, rb.ex, rb.ey);
+            }
+            ribbons_offset = (long long)off;
+            list = w.out_ribbons + off;
+        } else {
+            out_status = PPE_EDGE_ERR_RIBBON_CAPACITY; // the host grows the pool and runs the batch again
+        }
+    }
+    if (cfg.heuristic == PPE_H_MAX_DISTANCE) {
+        const double dist = (kDeep && modified) ? seq_max_distance(list, nr, ex, ey, W) : seq_max_distance_presummed(rib, nr, ex, ey, w.set_sumlen[set]);
+        h = dist / cfg.max_speed * cfg.time_penalty_factor;
+    } else {
+        h = tsp_heuristic_or_unset(cfg, list, nr, ex, ey);
+    }
     ppe_edge_result* r = results + ei;
     r->true_cost = true_cost;
     r->collision_penalty = penalty;
@@ -1563,15 +1707,62 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
     r->w_speed = w_speed;
     r->w_start_time = pe[kWStart];
     r->w_end_time = endTime;
-    r->ribbons_offset = -1;
+    r->ribbons_offset = ribbons_offset;
     r->path_type = (int)pe[kType];
     r->infeasible = infeasible ? 1 : 0;
-    r->status = status;
+    r->status = out_status;
     r->n_samples = n_samples;
     r->n_checkpoints = n_cp;
     r->n_ribbons_after = nr;
-    r->ribbons_changed = 0;
-    r->reserved = (n_culled & 0xffffff) | (1 << 24); // instrumentation: culled samples; bit 24 = walked by a thread (K2t)
+    r->ribbons_changed = (kDeep && modified) ? 1 : 0;
+    // instrumentation: culled samples; bit 24 = walked by a thread (K2t or K2c), bit 25 = by the deep walker K2c
+    r->reserved = (n_culled & 0xffffff) | (1 << 24) | (kDeep ? (1 << 25) : 0);
+}
+
+__global__ void __launch_bounds__(128)
+k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
+                const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
+                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, const int dirty_budget,
+                const int cp_budget) {
+    extern __shared__ double4 smem4[];
+    ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
+    {
+        const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
+        double* dst = reinterpret_cast<double*>(s_obs);
+        const double* src = reinterpret_cast<const double*>(w.obstacles);
+        for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    // N2: shared-memory tile of the occupancy and safe bitmaps around the batch's bounding box (TMA bulk copies)
+    const uint32_t* tile = nullptr;
+    if (w.tile_on) {
+        __shared__ unsigned long long s_tile_bar;
+        uint32_t* s_tile = reinterpret_cast<uint32_t*>(smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4)));
+        tile_stage(w, s_tile, &s_tile_bar);
+        tile = s_tile;
+    }
+    const long long ei = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ei >= n) return;
+    thread_walk<false>(w, n, ei, edges, prepared, results, heavy_list, heavy_count, dirty_budget, cp_budget, s_obs, tile);
+}
+
+// K2c: one thread per edge of the FRONT heavy list (the edges K2t caught covering a ribbon)
+__global__ void __launch_bounds__(128)
+k2c_deep_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
+              const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
+              unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, const int dirty_budget) {
+    extern __shared__ double4 smem4[];
+    ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
+    {
+        const int nd = w.n_obs * (int)(sizeof(ObstacleD) / sizeof(double));
+        double* dst = reinterpret_cast<double*>(s_obs);
+        const double* src = reinterpret_cast<const double*>(w.obstacles);
+        for (int i = threadIdx.x; i < nd; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const unsigned int n_front = heavy_count[0];
+    for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_front; k += gridDim.x * blockDim.x)
+        thread_walk<true>(w, n, (long long)heavy_list[k], edges, prepared, results, heavy_list, heavy_count, dirty_budget, 0, s_obs, nullptr);
 }
 
 // K2a: one thread per edge
@@ -1593,7 +1784,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, PPE_K2B_WARPS_PER_SM / kW
 k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
              const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
              unsigned long long* work_counter, const unsigned int* __restrict__ heavy_list,
-             const unsigned int* __restrict__ heavy_count) {
+             const unsigned int* __restrict__ heavy_count, const int front_too) {
     extern __shared__ double4 smem4[];
     ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
     double4* s_rib = smem4 + (size_t)w.n_obs * (sizeof(ObstacleD) / sizeof(double4));
@@ -1607,7 +1798,9 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
     __shared__ double s_cp_pose[kWarpsPerBlock][96];
     double* pe = s_pe[warp];
 
-    const unsigned long long n_front = heavy_list ? (unsigned long long)heavy_count[0] : 0ull;
+    // heavy list: [0, count0) the edges K2t caught covering a ribbon (K2c's work; the warp walker's too when K2c is off),
+    // [2n - count1, 2n) everything else incl. what K2c passed on
+    const unsigned long long n_front = (heavy_list && front_too) ? (unsigned long long)heavy_count[0] : 0ull;
     const unsigned long long todo = heavy_list ? n_front + (unsigned long long)heavy_count[1] : (unsigned long long)n;
     if ((unsigned long long)blockIdx.x * kWarpsPerBlock >= todo) return; // nothing for this CTA: skip the staging
     {
@@ -1623,7 +1816,7 @@ k2_true_cost(const __grid_constant__ WorldD w, const long long n, const ppe_edge
         if (lane == 0) k = atomicAdd(work_counter, 1ULL);
         k = __shfl_sync(kFull, k, 0);
         if (k >= todo) break;
-        const unsigned long long ei = !heavy_list ? k : (unsigned long long)(k < n_front ? heavy_list[k] : heavy_list[n - 1 - (k - n_front)]);
+        const unsigned long long ei = !heavy_list ? k : (unsigned long long)(k < n_front ? heavy_list[k] : heavy_list[2 * n - 1 - (k - n_front)]);
         process_edge(w, &w, edges + ei, prepared + ei, results + ei, s_obs, bufA, bufB, pe, &s_tt[warp], s_rel[warp], s_cp_pose[warp], lane);
         __syncwarp();
     }
@@ -1788,7 +1981,7 @@ size_t prepared_edge_bytes() { return sizeof(PreparedEdge); }
 template <int kW>
 static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edges, const PreparedEdge* prepared,
                              ppe_edge_result* results, unsigned long long* work_counter, const unsigned int* heavy_list,
-                             const unsigned int* heavy_count, int max_blocks, int sm_count, cudaStream_t stream) {
+                             const unsigned int* heavy_count, int front_too, int max_blocks, int sm_count, cudaStream_t stream) {
     const size_t smem = k2_smem_bytes(kW, world.ribbon_cap, world.n_obs);
     cudaError_t e;
     if (smem > 32 * 1024) { // per device and per function (static + dynamic must fit): set it whenever it may be needed
@@ -1806,7 +1999,7 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     k2_true_cost<kW><<<(unsigned)blocks, kW * 32, smem, stream>>>(world, (long long)n, edges, prepared, results, work_counter,
-                                                                 heavy_list, heavy_count);
+                                                                 heavy_list, heavy_count, front_too);
     return cudaGetLastError();
 }
 
@@ -1843,14 +2036,29 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         launches++;
+        if (tuning.deep_walker) { // K2c over the front list; what it cannot keep goes to the back list for K2b
+            const size_t smem_c = (size_t)world.n_obs * sizeof(ObstacleD);
+            if (smem_c > 32 * 1024) {
+                e = cudaFuncSetAttribute(k2c_deep_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c);
+                if (e != cudaSuccess) return e;
+            }
+            long long cblocks = (n + 127) / 128;
+            if (cblocks > (long long)sm_count * 8) cblocks = (long long)sm_count * 8;
+            k2c_deep_walk<<<(unsigned)cblocks, 128, smem_c, stream>>>(world, (long long)n, edges, prepared, results, heavy_list, heavy_count,
+                                                                     kThreadDirtyCap);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+            launches++;
+        }
     }
+    const int front_too = (heavy_list && tuning.deep_walker) ? 0 : 1;
 #ifndef PPE_K2_FORCE_NARROW
 #define PPE_K2_FORCE_NARROW 1
 #endif
     if (!PPE_K2_FORCE_NARROW && k2_smem_bytes(kWarpsWide, world.ribbon_cap, world.n_obs) <= 190 * 1024)
-        e = launch_k2<kWarpsWide>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, max_blocks, sm_count, stream);
+        e = launch_k2<kWarpsWide>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, front_too, max_blocks, sm_count, stream);
     else
-        e = launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, max_blocks, sm_count, stream);
+        e = launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, front_too, max_blocks, sm_count, stream);
     if (e != cudaSuccess) return e;
     launches++;
     long long blocks = (n + 255) / 256;

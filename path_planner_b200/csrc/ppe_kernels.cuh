@@ -56,7 +56,7 @@ struct WorldD {
     // per-set invariants of the UNCHANGED list (what the thread walker evaluates): sum over the list, in list order, of
     // length - 2 * RibbonWidth (RibbonManager::maxDistance, RibbonManager.cpp:238-240) and "all coordinates below 1e7"
     const double* set_sumlen;
-    const int* set_tame;
+    const int* set_tame;        // bit 0: tame; bit 1: the list holds a ribbon short enough for a strict cover() to erase it
     int n_sets;
     int ribbon_cap;             // per-warp working capacity (ribbons)
     // ribbons-after output pool
@@ -74,6 +74,7 @@ struct BestD {
 struct K2Tuning {
     int dirty_budget = 2; // non-clean chunks a K2t thread evaluates sample by sample before handing the edge to K2b
     int cp_budget = 6;    // ribbon check-points a K2t thread walks
+    int deep_walker = 1;  // K2c: thread-per-edge walk of the edges K2t caught covering a ribbon (PPE_DEEP_WALKER=0: K2b takes them)
 };
 K2Tuning clamp_tuning(K2Tuning t);
 // heuristics other than MaxDistance that the kernels evaluate themselves (h >= 0 in the result records)

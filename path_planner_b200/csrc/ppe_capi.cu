@@ -383,7 +383,7 @@ int ppe_create(int device, ppe_ctx** out) {
         const char* env_d = getenv("PPE_K2T_DIRTY");  // tuning knob: non-clean chunks a K2t thread may evaluate
         if (env_d) ctx->tuning.dirty_budget = atoi(env_d);
         const char* env_k2c = getenv("PPE_DEEP_WALKER");
-        if (env_k2c && env_k2c[0] == '0') ctx->tuning.deep_walker = 0;
+        if (env_k2c) ctx->tuning.deep_walker = env_k2c[0] == '1';
         ctx->tuning = clamp_tuning(ctx->tuning);
     }
     bool ok = cudaMalloc((void**)&ctx->d_work, 2 * sizeof(unsigned long long)) == cudaSuccess &&

@@ -74,7 +74,8 @@ struct BestD {
 struct K2Tuning {
     int dirty_budget = 2; // non-clean chunks a K2t thread evaluates sample by sample before handing the edge to K2b
     int cp_budget = 6;    // ribbon check-points a K2t thread walks
-    int deep_walker = 1;  // K2c: thread-per-edge walk of the edges K2t caught covering a ribbon (PPE_DEEP_WALKER=0: K2b takes them)
+    int deep_walker = 0;  // K2c: thread-per-edge walk of the edges K2t caught covering a ribbon (PPE_DEEP_WALKER=1; measured
+                          // slower than handing them to K2b -- DESIGN.md section 4.5 -- so off by default)
 };
 K2Tuning clamp_tuning(K2Tuning t);
 // heuristics other than MaxDistance that the kernels evaluate themselves (h >= 0 in the result records)

@@ -51,6 +51,26 @@ def test_harness_plans_equal_the_reference(ref, i):
     assert st["true_cost_edges"] > 0 and st["frontier_vertices"] >= st["expanded"]
 
 
+@pytest.mark.parametrize("i", [1, 6])
+def test_plan_identity_over_sampler_seeds(ref, i):
+    """The sampler's seed is the integer second of the deadline (AStarPlanner.cpp:33): other clock origins give other sample
+    sets; the plans must stay the reference's for each of them.  The virtual clock charges time per generated sample so that
+    the anytime loop's sample doubling stays bounded whatever the seed does to the length of the iterations."""
+    _, wname, start, budget, tick, initial = plan_cases.CASES[i]
+    world = plan_cases.make_world(wname)
+    start = world.start if start is None else np.array(start, dtype=np.float64)
+    sid = world.upload_ref(ref)
+    h = ph.PlanningHarness(0)
+    h.set_world(world)
+    for clock0 in (1.0e9 + 1.25, 1.0e9 + 11.25, 77.5):
+        want_plan, want = common.run_plan(ref, "ref", sid, start, budget, clock0, tick, initial, sample_tick=2e-6)
+        plan, st = h.plan(start, budget, clock0=clock0, tick=tick, initial_samples=initial, sample_tick=2e-6)
+        got = as12(plan)
+        assert got.shape == want_plan.shape and st["expanded"] == want["expanded"] and st["samples"] == want["samples"], (clock0, st, want)
+        assert np.array_equal(got[:, 7], want_plan[:, 7])
+        assert np.allclose(got, want_plan, rtol=common.RTOL, atol=plan_cases.RETRY_FLIP_SLACK), clock0
+
+
 def test_two_cycles_with_previous_plan(ref):
     """Receding-horizon use: cycle 2 starts one second along cycle 1's plan and gets it as previousPlan."""
     world = synth.world_c2()

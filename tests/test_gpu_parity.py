@@ -253,3 +253,22 @@ def test_degenerate_dubins(engine, oracle):
     assert np.allclose(gp, wp, rtol=1e-9, atol=1e-12)
     assert gt[0] == abi.LSL and gt[1] == abi.LSL
     assert gl[0] == 5 and gl[1] == 25
+
+
+def test_deep_thread_walker_matches_oracle(oracle):
+    """K2c (PPE_DEEP_WALKER=1, off by default): the edges K2t catches covering a ribbon are walked one thread per edge with a
+    two-entry override table over the parent's ribbon list; what changes the list's structure goes on to the warp walker.
+    Same bits as the oracle, and some edges must actually have taken that path (bit 25 of the instrumentation word)."""
+    import os
+    os.environ["PPE_DEEP_WALKER"] = "1"
+    try:
+        eng = EdgeEngine(0)
+    finally:
+        os.environ.pop("PPE_DEEP_WALKER", None)
+    deep = 0
+    for name, near, n in (("c2", 0.6, 4000), ("c1", 0.5, 2000), ("c5", 0.3, 600)):
+        world = synth.WORLDS[name]()
+        edges = synth.make_edges(world, n, seed=21, near_ribbons=near)
+        got, want = _check_batch(eng, oracle, world, edges)
+        deep += int(((got["reserved"] >> 25) & 1).sum())
+    assert deep > 0

@@ -68,12 +68,3 @@ def test_expand_test_1_ribbons_on_the_engine(lib):
     assert n_ref == 40 and n_har == 40
     assert np.all(np.diff(f_har[:40]) >= 0)
     assert np.allclose(f_ref[:40], f_har[:40], rtol=common.RTOL, atol=common.ATOL)
-
-
-@pytest.mark.parametrize("i", [1, 6])
-def test_plan_identity_over_sampler_seeds(lib, i):
-    """The sampler's seed is the integer second of the deadline (AStarPlanner.cpp:33): other clock origins give other
-    sample sets; the plans must stay the reference's for each of them."""
-    case = plan_cases.CASES[i]
-    for clock0 in (1.0e9 + 1.25, 1.0e9 + 11.25, 1.0e9 + 21.25, 77.5):
-        plan_cases.compare(lib, case, exact=False, clock0=clock0)

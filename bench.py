@@ -234,14 +234,15 @@ def plan_at_budget(budget_s, device, reps=3):
             smp.append(st["samples"])
             hits.append(st["frontier_hits"])
             batches.append(st["engine_batches"])
-            exact.append(st["exact_expansions"])
+            exact.append((st["exact_expansions"], st["exact_for_ties"], st["exact_for_overflow"]))
             for k in where:
                 where[k] += st["seconds_" + k]
         rec["engine"] = {"f": fs, "f_median": statistics.median(fs), "f_best": min(fs),
                          "plans_found": sum(1 for f in fs if f < float("inf")),
                          "expanded_mean": sum(exp) / reps, "samples_mean": sum(smp) / reps, "expansions_per_s": sum(exp) / sum(wall),
                          "frontier_hit_rate": sum(hits) / max(1, sum(exp)), "engine_batches_mean": sum(batches) / reps,
-                         "exact_expansions_mean": sum(exact) / reps, "wall_s_mean": round(sum(wall) / reps, 3),
+                         "exact_expansions_mean": sum(e[0] for e in exact) / reps, "exact_for_ties": sum(e[1] for e in exact),
+                         "exact_for_overflow": sum(e[2] for e in exact), "wall_s_mean": round(sum(wall) / reps, 3),
                          "wall_share": {k: round(v / max(1e-9, sum(wall)), 3) for k, v in where.items()}}
         if ref is not None:
             rec["engine_f_not_worse"] = [bool(a <= b + 1e-9 * max(1.0, abs(b))) for a, b in zip(fs, rec["reference_cpu"]["f"])]

@@ -80,6 +80,7 @@ typedef struct {
     uint64_t true_cost_edges, dubins_solves, engine_batches, frontier_vertices, frontier_hits, exact_expansions;
     double wall_seconds;
     double seconds_engine_expand, seconds_replay, seconds_add_samples, seconds_exact; /* where the wall time went */
+    uint64_t exact_for_ties, exact_for_overflow; /* why expansions were replayed on the host */
 } pph_stats;
 
 /* Planner::plan(ribbons, start, config, previousPlan, timeRemaining): start = x, y, heading, speed, time.

@@ -1320,20 +1320,29 @@ __device__ __forceinline__ double seq_max_distance_presummed(const double4* __re
 // table over the parent's interned list; per 32-sample chunk only the ribbons whose bounding box can be reached are
 // looked at.  A split that inserts or erases a ribbon, a third modified ribbon, a list with a ribbon short enough to be
 // erased wherever the point is, or more per-sample work than the dirty-chunk budget sends the edge on to the warp walker.
-struct RibbonOverrides {
-    double4 val[2];
-    int idx[2];
-    int n;
+// The ribbon list of a K2c edge = the parent's interned list + a small delta: up to two ribbons whose start / end moved
+// (or that were erased), up to two pieces a split inserted in front of a parent ribbon.  List order: for parent index r,
+// the pieces inserted before r (in insertion order), then r itself unless erased.
+struct RibbonDelta {
+    double4 val[2];   // overrides
+    double4 ins[2];   // inserted pieces
+    int idx[2];       // parent index of override k
+    int ins_pos[2];   // parent index piece k stands in front of
+    int n, n_ins;
+    unsigned erased;  // bit k: override k means "erased"
 };
 constexpr int kDeepRelCap = 4;
 
-__device__ __forceinline__ RibbonD load_ribbon_ov(const double4* __restrict__ rib, int r, const RibbonOverrides& ov) {
-    if (ov.n > 0 && r == ov.idx[0]) return RibbonD{ov.val[0].x, ov.val[0].y, ov.val[0].z, ov.val[0].w};
-    if (ov.n > 1 && r == ov.idx[1]) return RibbonD{ov.val[1].x, ov.val[1].y, ov.val[1].z, ov.val[1].w};
+// parent ribbon r as the delta sees it; *gone = erased
+__device__ __forceinline__ RibbonD load_ribbon_ov(const double4* __restrict__ rib, int r, const RibbonDelta& dl, bool* gone) {
+    *gone = false;
+    if (dl.n > 0 && r == dl.idx[0]) { *gone = (dl.erased & 1u) != 0; return RibbonD{dl.val[0].x, dl.val[0].y, dl.val[0].z, dl.val[0].w}; }
+    if (dl.n > 1 && r == dl.idx[1]) { *gone = (dl.erased & 2u) != 0; return RibbonD{dl.val[1].x, dl.val[1].y, dl.val[1].z, dl.val[1].w}; }
     return load_ribbon(rib + r);
 }
 
-// ribbons (of the parent's list: overrides only shrink them) that a pose within `reach` of (x, y) could be contained in
+// ribbons (of the parent's list: the delta only shrinks them or cuts pieces out of them) that a pose within `reach` of
+// (x, y) could be contained in
 __device__ __forceinline__ int deep_relevant(const double4* __restrict__ rib, int nr, double x, double y, double reach, double W, int* rel) {
     const double grow = W * (1 + 1e-9) + 2e-3 + reach;
     int n = 0;
@@ -1350,51 +1359,83 @@ __device__ __forceinline__ int deep_relevant(const double4* __restrict__ rib, in
     return n <= kDeepRelCap ? n : -1;
 }
 
-// One check-point (minDistanceFrom, then cover when `do_cover`) on the relevant ribbons.  Returns false when the list's
-// structure would change or the override table is full (nothing has been modified then).
-__device__ __forceinline__ bool deep_checkpoint(const double4* __restrict__ rib, int nr, RibbonOverrides& ov, const int* rel, int n_rel,
+// Ribbon::contains on one ribbon: non-strict (d < W) -> *inside, strict (d < W / 2) -> returns true with the projection
+__device__ __forceinline__ bool deep_contains(const RibbonD& rb, double x, double y, double W, bool* inside, double* px, double* py) {
+    ribbon_projection(rb, x, y, px, py);
+    if (!ribbon_contains_projection(rb, *px, *py)) return false;
+    const double d = ribbon_distance(rb, x, y);
+    *inside = *inside || (d < W);
+    return d < W / 2.0;
+}
+
+// One check-point (minDistanceFrom, then cover when `do_cover`) on the relevant ribbons.  Returns false when the delta
+// cannot hold the outcome (nothing has been modified then): a third moved ribbon, a third inserted piece, a split of an
+// inserted piece, two ribbons hit at once, or the list running empty (coverage completion is the warp walker's).
+__device__ __forceinline__ bool deep_checkpoint(const double4* __restrict__ rib, int nr, RibbonDelta& dl, const int* rel, int n_rel,
                                                 double x, double y, double W, bool do_cover, double* to_cover, bool* modified) {
-    bool inside = false, ch = false;
-    int upd = -1;
-    double4 nv = make_double4(0, 0, 0, 0);
+    bool inside = false;
+    int upd = -1, kind = 0; // kind 1: move start (rest survives), 2: move end (piece survives), 3: insert piece + move start, 4: erase
+    double4 nv = make_double4(0, 0, 0, 0), piece_v = make_double4(0, 0, 0, 0);
+    bool ch = false;
 #pragma unroll 1
     for (int q = 0; q < n_rel; q++) {
         const int r = rel[q];
-        const RibbonD rb = load_ribbon_ov(rib, r, ov);
         double px, py;
-        ribbon_projection(rb, x, y, &px, &py);
-        if (!ribbon_contains_projection(rb, px, py)) continue;
-        const double d = ribbon_distance(rb, x, y);
-        inside = inside || (d < W);
-        if (do_cover && d < W / 2.0) {
+        for (int k = 0; k < dl.n_ins; k++) { // pieces a split left in front of r
+            if (dl.ins_pos[k] != r) continue;
+            const RibbonD pc = {dl.ins[k].x, dl.ins[k].y, dl.ins[k].z, dl.ins[k].w};
+            if (deep_contains(pc, x, y, W, &inside, &px, &py) && do_cover) return false; // a piece would be split again
+        }
+        bool gone;
+        const RibbonD rb = load_ribbon_ov(rib, r, dl, &gone);
+        if (gone) continue;
+        if (deep_contains(rb, x, y, W, &inside, &px, &py) && do_cover) {
             const RibbonD piece = {rb.sx, rb.sy, px, py};
             const RibbonD rest = {px, py, rb.ex, rb.ey};
             const bool keep_piece = !ribbon_covered(piece, true, W), keep_rest = !ribbon_covered(rest, true, W);
-            if (keep_piece == keep_rest) return false; // insertion or erasure
-            if (upd >= 0) return false;                // two ribbons at once
+            if (upd >= 0) return false; // two ribbons at once
             upd = r;
-            if (keep_rest) { nv = make_double4(px, py, rb.ex, rb.ey); ch = (px != rb.sx) || (py != rb.sy); }
-            else { nv = make_double4(rb.sx, rb.sy, px, py); ch = true; }
+            if (keep_rest) {
+                nv = make_double4(px, py, rb.ex, rb.ey);
+                if (keep_piece) { kind = 3; piece_v = make_double4(rb.sx, rb.sy, px, py); ch = true; }
+                else { kind = 1; ch = (px != rb.sx) || (py != rb.sy); }
+            } else if (keep_piece) {
+                kind = 2; nv = make_double4(rb.sx, rb.sy, px, py); ch = true;
+            } else {
+                kind = 4; ch = true;
+            }
         }
     }
-    if (inside) {
-        if (upd >= 0) {
-            int slot = -1;
-            if (ov.n > 0 && ov.idx[0] == upd) slot = 0;
-            else if (ov.n > 1 && ov.idx[1] == upd) slot = 1;
-            else if (ov.n < 2) { slot = ov.n; ov.n++; ov.idx[slot] = upd; }
-            if (slot < 0) return false; // a third modified ribbon
-            ov.val[slot] = nv;
-            *modified = *modified || ch;
+    if (upd >= 0) { // cover() changes ribbon `upd` (only reached with `inside`: strict containment implies it)
+        int slot = -1;
+        if (dl.n > 0 && dl.idx[0] == upd) slot = 0;
+        else if (dl.n > 1 && dl.idx[1] == upd) slot = 1;
+        const bool need_slot = slot < 0;
+        if (need_slot && dl.n >= 2) return false;              // a third modified ribbon
+        if (kind == 3 && dl.n_ins >= 2) return false;          // a third inserted piece
+        if (kind == 4) {                                       // would the list run empty?
+            int left = nr + dl.n_ins - 1;
+            for (int k = 0; k < dl.n; k++) if ((dl.erased >> k) & 1u) left--;
+            if (left <= 0) return false;
         }
-        *to_cover = 0.0;
-        return true;
+        if (need_slot) { slot = dl.n; dl.n++; dl.idx[slot] = upd; }
+        if (kind == 4) dl.erased |= 1u << slot;
+        else dl.val[slot] = nv;
+        if (kind == 3) { dl.ins[dl.n_ins] = piece_v; dl.ins_pos[dl.n_ins] = upd; dl.n_ins++; }
+        *modified = *modified || ch;
     }
-    // no ribbon contains the point even non-strictly: cover() cannot touch anything; nearest end point of the current list
+    if (inside) { *to_cover = 0.0; return true; }
+    // no ribbon contains the point even non-strictly: nearest end point of the current list
     double mn = DBL_MAX;
 #pragma unroll 1
     for (int r = 0; r < nr; r++) {
-        const RibbonD rb = load_ribbon_ov(rib, r, ov);
+        for (int k = 0; k < dl.n_ins; k++) {
+            if (dl.ins_pos[k] != r) continue;
+            mn = fmin(fmin(mn, point_distance_sq(dl.ins[k].z, dl.ins[k].w, x, y)), point_distance_sq(dl.ins[k].x, dl.ins[k].y, x, y));
+        }
+        bool gone;
+        const RibbonD rb = load_ribbon_ov(rib, r, dl, &gone);
+        if (gone) continue;
         const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
         const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
         mn = fmin(fmin(mn, dEnd), dStart);
@@ -1475,8 +1516,8 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     double ex = 0, ey = 0, eh = 0;
     const int status = PPE_EDGE_OK;
     bool long_run = false; // bailed out while covering a ribbon
-    RibbonOverrides ov;    // K2c: the (at most two) ribbons whose start / end cover() has moved
-    ov.n = 0;
+    RibbonDelta ov;        // K2c: what cover() has done to the parent's list so far
+    ov.n = 0; ov.n_ins = 0; ov.erased = 0;
     bool modified = false;
     const int n_valid = prep->pad_[0]; // samples with t_i < endTime
     heavy = heavy || n_valid < 0 || n_valid > 64 * kChunk;
@@ -1672,14 +1713,22 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     double h;
     long long ribbons_offset = -1;
     int out_status = status;
+    int nr_after = nr;
     const double4* list = rib;
     if (kDeep && modified) { // ribbons-after = the parent's list with the overrides applied, materialised in the pool
-        const unsigned long long off = atomicAdd(w.out_count, (unsigned long long)nr);
-        if (off + (unsigned long long)nr <= w.out_cap) {
+        int erased_n = 0;
+        for (int k = 0; k < ov.n; k++) erased_n += (ov.erased >> k) & 1u;
+        nr_after = nr + ov.n_ins - erased_n;
+        const unsigned long long off = atomicAdd(w.out_count, (unsigned long long)nr_after);
+        if (off + (unsigned long long)nr_after <= w.out_cap) {
+            int o = 0;
 #pragma unroll 1
             for (int q = 0; q < nr; q++) {
-                const RibbonD rb = load_ribbon_ov(rib, q, ov);
-                w.out_ribbons[off + q] = pack_ribbon(rb.sx, rb.sy, rb.ex, rb.ey);
+                for (int k = 0; k < ov.n_ins; k++)
+                    if (ov.ins_pos[k] == q) w.out_ribbons[off + o++] = ov.ins[k];
+                bool gone;
+                const RibbonD rb = load_ribbon_ov(rib, q, ov, &gone);
+                if (!gone) w.out_ribbons[off + o++] = pack_ribbon(rb.sx, rb.sy, rb.ex, rb.ey);
             }
             ribbons_offset = (long long)off;
             list = w.out_ribbons + off;
@@ -1688,10 +1737,10 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
         }
     }
     if (cfg.heuristic == PPE_H_MAX_DISTANCE) {
-        const double dist = (kDeep && modified) ? seq_max_distance(list, nr, ex, ey, W) : seq_max_distance_presummed(rib, nr, ex, ey, w.set_sumlen[set]);
+        const double dist = (kDeep && modified) ? seq_max_distance(list, nr_after, ex, ey, W) : seq_max_distance_presummed(rib, nr, ex, ey, w.set_sumlen[set]);
         h = dist / cfg.max_speed * cfg.time_penalty_factor;
     } else {
-        h = tsp_heuristic_or_unset(cfg, list, nr, ex, ey);
+        h = tsp_heuristic_or_unset(cfg, list, nr_after, ex, ey);
     }
     ppe_edge_result* r = results + ei;
     r->true_cost = true_cost;
@@ -1713,7 +1762,7 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     r->status = out_status;
     r->n_samples = n_samples;
     r->n_checkpoints = n_cp;
-    r->n_ribbons_after = nr;
+    r->n_ribbons_after = nr_after;
     r->ribbons_changed = (kDeep && modified) ? 1 : 0;
     // instrumentation: culled samples; bit 24 = walked by a thread (K2t or K2c), bit 25 = by the deep walker K2c
     r->reserved = (n_culled & 0xffffff) | (1 << 24) | (kDeep ? (1 << 25) : 0);

@@ -33,7 +33,8 @@ class PlanStats(C.Structure):
                [(n, C.c_double) for n in ("plan_f", "plan_collision_penalty", "plan_time_penalty", "plan_h", "plan_endtime")] + \
                [(n, C.c_uint64) for n in ("now_calls", "true_cost_edges", "dubins_solves", "engine_batches", "frontier_vertices",
                                           "frontier_hits", "exact_expansions")] + \
-               [(n, C.c_double) for n in ("wall_seconds", "seconds_engine_expand", "seconds_replay", "seconds_add_samples", "seconds_exact")]
+               [(n, C.c_double) for n in ("wall_seconds", "seconds_engine_expand", "seconds_replay", "seconds_add_samples", "seconds_exact")] + \
+               [(n, C.c_uint64) for n in ("exact_for_ties", "exact_for_overflow")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -375,6 +375,7 @@ void BatchedAStarPlanner::expandSpecific(const Vertex::SharedPtr& root, const st
 Planner::Stats BatchedAStarPlanner::plan(const RibbonManager& ribbonManager, const State& start, PlannerConfig config,
                                          const DubinsPlan& previousPlan, double timeRemaining) {
     m_TrueCostEdges = m_DubinsSolves = m_Batches = m_FrontierVertices = m_FrontierHits = m_ExactExpansions = 0;
+    m_ExactTies = m_ExactOverflow = 0;
     m_TEngine = m_TReplay = m_TSamples = m_TExact = 0;
     m_Config = std::move(config); // before the first now(), :14
     const double endTime = timeRemaining + now();
@@ -583,6 +584,8 @@ void BatchedAStarPlanner::expandFrontier(const std::shared_ptr<Vertex>& sourceVe
     }
     static const bool forceExact = getenv("PPE_HARNESS_TEST_FORCE_EXACT") != nullptr; // tests: every 3rd expansion replays on the host
     if ((it->second.flags & (PPE_EXPAND_TIE | PPE_EXPAND_OVERFLOW)) || (forceExact && m_Stats.Expanded % 3 == 2)) {
+        if (it->second.flags & PPE_EXPAND_TIE) m_ExactTies++;
+        if (it->second.flags & PPE_EXPAND_OVERFLOW) m_ExactOverflow++;
         m_Expansions.erase(it);
         expandExact(sourceVertex);
         return;

@@ -70,6 +70,8 @@ public:
     long frontierVertices() const { return m_FrontierVertices; }  // vertices sent to ppe_expand_batch
     long frontierHits() const { return m_FrontierHits; }          // expansions served from a cached frontier result
     long exactExpansions() const { return m_ExactExpansions; }    // expansions replayed on the host (ties, width 0)
+    long exactForTies() const { return m_ExactTies; }             // ... because the device flagged an exact distance tie
+    long exactForOverflow() const { return m_ExactOverflow; }     // ... because the device ran out of candidate capacity
     // wall seconds spent in: ppe_expand_batch calls (incl. building the vertex records), handing cached children to the open
     // list, addSamplesResident, exact host expansions
     double secondsInEngineExpand() const { return m_TEngine; }
@@ -118,7 +120,8 @@ private:
     int m_Frontier = 64;
     int m_Heuristic = PPE_H_MAX_DISTANCE;
     bool m_HOnDevice = true;
-    long m_TrueCostEdges = 0, m_DubinsSolves = 0, m_Batches = 0, m_FrontierVertices = 0, m_FrontierHits = 0, m_ExactExpansions = 0;
+    long m_TrueCostEdges = 0, m_DubinsSolves = 0, m_Batches = 0, m_FrontierVertices = 0, m_FrontierHits = 0, m_ExactExpansions = 0, m_ExactTies = 0,
+         m_ExactOverflow = 0;
     double m_TEngine = 0, m_TReplay = 0, m_TSamples = 0, m_TExact = 0;
 
     // The reference keeps m_Samples itself heap-ordered (SamplingBasedPlanner.cpp:85-93).  Here the States stay where

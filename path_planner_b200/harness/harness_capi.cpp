@@ -262,6 +262,7 @@ int pph_plan(pph_ctx* ctx, const double start5[5], const pph_dubins_path* previo
     stats->wall_seconds = wall;
     stats->seconds_engine_expand = planner.secondsInEngineExpand(); stats->seconds_replay = planner.secondsInReplay();
     stats->seconds_add_samples = planner.secondsInAddSamples(); stats->seconds_exact = planner.secondsInExact();
+    stats->exact_for_ties = (uint64_t)planner.exactForTies(); stats->exact_for_overflow = (uint64_t)planner.exactForOverflow();
     ctx->lastPlan = st.Plan;
     ctx->lastStart = start;
     return n;

@@ -79,4 +79,4 @@ def test_harness_library_exports_every_declared_symbol():
     assert "pph_plan" in syms and "pph_create" in syms
     lib = C.CDLL(ph.HARNESS_PATH)
     assert not [s for s in syms if not hasattr(lib, s)]
-    assert C.sizeof(ph.PlanStats) == 22 * 8 and C.sizeof(ph.PlanOptions) == 64 and ph.PATH_DTYPE.itemsize == 88
+    assert C.sizeof(ph.PlanStats) == 24 * 8 and C.sizeof(ph.PlanOptions) == 64 and ph.PATH_DTYPE.itemsize == 88

@@ -554,6 +554,33 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s_max = float(te.item())
 
+    # ---- secondary line: weak scaling (every GPU its own full batch), 3 steps -------------------
+    weak = None
+    if distributed and args.scaling == "strong" and not args.no_extra:
+        e_w = synth.make_edges(world, args.edges, seed=5 + 1000 * rank, near_ribbons=args.near_ribbons)
+        e_w["ribbon_set"] = set_id
+
+        def gather_best_weak():
+            eng.best_copy_device(best_local.data_ptr(), rank * args.edges, sh)
+            dist.all_gather_into_tensor(best_all, best_local)
+
+        step_w, h_w, r_w = measure(torch, eng, world, e_w, 3, 2, stream, gather_best_weak)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a_w, b_w = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_w.record(stream)
+        for _ in range(3):
+            step_w()
+        b_w.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_w = torch.tensor([a_w.elapsed_time(b_w)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_w, op=dist.ReduceOp.MAX)
+        ms_w = float(t_w.item()) / 3
+        weak = {"scaling": "weak", "value": args.edges * world_size / (ms_w * 1e-3), "unit": "edges/s", "ms_per_step": ms_w, "steps": 3,
+                "edges_per_gpu": args.edges, "note": "one %d-edge batch per GPU (seed 5 + 1000 rank), same kernels and 16-byte gather" % args.edges}
+        del step_w, h_w, r_w
+
     # ---- BASELINE configs[4], second half: independent scenarios sharded over the ranks ----------
     scen = None
     if not args.no_extra and args.scenarios > 0:
@@ -638,6 +665,8 @@ def main():
                         "bytes_moved_per_launch": n * (abi.EDGE_DTYPE.itemsize + abi.RESULT_DTYPE.itemsize)},
             },
         }
+        if weak is not None:
+            line["weak"] = weak
         if scen is not None:
             line["scenarios"] = scen
         if world_size == 1 and not args.no_extra:

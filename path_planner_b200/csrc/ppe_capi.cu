@@ -98,7 +98,11 @@ struct ppe_ctx {
     unsigned long long* d_work = nullptr; // [0] K2b work counter, [1] heavy-list length
     unsigned int* d_heavy = nullptr;
     size_t cap_heavy = 0;
+    unsigned char* d_patch = nullptr;     // K2b's records packed, then their edge indices (pageable result arrays only)
+    size_t cap_patch = 0;
     bool thread_walker = true;            // PPE_THREAD_WALKER=0: the warp walker evaluates every edge
+    bool late_k2b = true;                 // PPE_LATE_K2B=0: slice the whole kernel sequence of host-buffer batches (A/B)
+    int64_t late_slice = 131072;          // PPE_LATE_SLICE: edges per slice of the late-K2b pipeline
     K2Tuning tuning;                      // PPE_K2T_DIRTY / PPE_K2T_CPS, read at ppe_create
     BestD* d_block_best = nullptr;
     BestD* d_best = nullptr;
@@ -382,6 +386,10 @@ int ppe_create(int device, ppe_ctx** out) {
         if (env_cp && atoi(env_cp) > 0) ctx->tuning.cp_budget = atoi(env_cp);
         const char* env_d = getenv("PPE_K2T_DIRTY");  // tuning knob: non-clean chunks a K2t thread may evaluate
         if (env_d) ctx->tuning.dirty_budget = atoi(env_d);
+        const char* env_late = getenv("PPE_LATE_K2B");
+        if (env_late) ctx->late_k2b = atoi(env_late) != 0;
+        const char* env_ls = getenv("PPE_LATE_SLICE");
+        if (env_ls && atoll(env_ls) >= 1024) ctx->late_slice = atoll(env_ls);
         const char* env_k2c = getenv("PPE_DEEP_WALKER");
         if (env_k2c) ctx->tuning.deep_walker = env_k2c[0] == '1';
         ctx->tuning = clamp_tuning(ctx->tuning);
@@ -410,6 +418,7 @@ void ppe_destroy(ppe_ctx* ctx) {
     cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_prepared); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
     cudaFree(ctx->d_work); cudaFree(ctx->d_heavy); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
+    if (ctx->d_patch) cudaFree(ctx->d_patch);
     cudaFree(ctx->d_sx); cudaFree(ctx->d_sy); cudaFree(ctx->d_sh); cudaFree(ctx->d_stage); cudaFree(ctx->d_keep);
     cudaFree(ctx->d_blockcnt); cudaFree(ctx->d_verts); cudaFree(ctx->d_xedges); cudaFree(ctx->d_xresults);
     cudaFree(ctx->d_children); cudaFree(ctx->d_xints);
@@ -720,6 +729,92 @@ int ppe_best_copy_device(ppe_ctx* ctx, void* d_dst16, int64_t index_base, void* 
     return PPE_OK;
 }
 
+// Large host-buffer batches when K2t is on.  The copies of a 2^20-edge batch (176 B in, 208 B out per edge) take about as
+// long as its kernels, and slicing the WHOLE kernel sequence makes every slice end on its own tail of survey-line edges.
+// So only the uniform part is sliced: K2a + K2t of slice k run while slice k + 1 arrives and the results of slice k - 1
+// leave -- 95 % of the records are final after K2t.  K2b then runs ONCE over the heavy list of the whole batch, and the
+// records it wrote (5 %) are scattered by a kernel straight into the caller's array when that is mapped pinned memory, or
+// packed, copied and scattered by the host when it is pageable.
+static int grow_pinned(ppe_ctx* ctx, void** p, size_t* cap, size_t need);
+static int batch_pipelined(ppe_ctx* ctx, WorldD& w, int64_t n, const ppe_edge* edges, ppe_edge_result* results, int64_t slice) {
+    const int64_t n_slices = (n + slice - 1) / slice;
+    int rc = grow(ctx, &ctx->d_prepared, &ctx->cap_prepared, (size_t)n * prepared_edge_bytes());
+    if (rc != PPE_OK) return rc;
+    rc = grow(ctx, &ctx->d_heavy, &ctx->cap_heavy, 2 * (size_t)n);
+    if (rc != PPE_OK) return rc;
+    // can a kernel write into `results`?
+    ppe_edge_result* mapped = nullptr;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, results) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            mapped = reinterpret_cast<ppe_edge_result*>(attr.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        PPE_CUDA(ctx, cudaMemsetAsync(ctx->d_out_count, 0, sizeof(unsigned long long), ctx->stream_in));
+        PPE_CUDA(ctx, cudaMemsetAsync(ctx->d_work, 0, 2 * sizeof(unsigned long long), ctx->stream_in));
+        for (int64_t k = 0; k < n_slices; k++) {
+            const int64_t lo = k * slice, cnt = (lo + slice <= n) ? slice : n - lo;
+            ppe_ctx::Lane& ln = ctx->lanes[k & 1];
+            PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_edges + lo, edges + lo, (size_t)cnt * sizeof(ppe_edge), cudaMemcpyHostToDevice, ctx->stream_in));
+            PPE_CUDA(ctx, cudaEventRecord(ctx->ev_in[k], ctx->stream_in));
+            PPE_CUDA(ctx, cudaStreamWaitEvent(ln.stream, ctx->ev_in[k], 0));
+            int launches = 0;
+            PPE_CUDA(ctx, launch_prepare_and_walk(w, n, lo, cnt, ctx->d_edges, ctx->d_prepared, ctx->d_results, ctx->d_work, ctx->d_heavy,
+                                                  ln.stream, ctx->tuning, &launches));
+            PPE_CUDA(ctx, cudaEventRecord(ctx->ev_k2[k], ln.stream));
+            ctx->launches += launches;
+            PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_out, ctx->ev_k2[k], 0));
+            PPE_CUDA(ctx, cudaMemcpyAsync(results + lo, ctx->d_results + lo, (size_t)cnt * sizeof(ppe_edge_result), cudaMemcpyDeviceToHost, ctx->stream_out));
+            PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_k2[k], 0));
+        }
+        PPE_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->stream_out));
+        int blocks = 1, launches = 0;
+        PPE_CUDA(ctx, launch_heavy_and_best(w, n, ctx->d_edges, ctx->d_prepared, ctx->d_results, ctx->d_work, ctx->d_heavy, ctx->d_block_best,
+                                            ctx->max_blocks, ctx->sm_count, ctx->stream, &blocks, &launches));
+        PPE_CUDA(ctx, launch_best_final(ctx->d_block_best, blocks, ctx->d_best, 0, false, ctx->stream));
+        ctx->launches += launches + 1;
+        PPE_CUDA(ctx, cudaMemcpyAsync(&ctx->last_out_count, ctx->d_out_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        // K2b's records overwrite what the slice copies brought: after the last of those copies
+        PPE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_done[0], 0));
+        if (mapped) {
+            PPE_CUDA(ctx, launch_patch_results(ctx->d_results, ctx->d_heavy, ctx->d_work, n, mapped, nullptr, ctx->sm_count, ctx->stream));
+            ctx->launches += 1;
+            PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            unsigned int counts[2] = {0, 0};
+            PPE_CUDA(ctx, cudaMemcpyAsync(counts, ctx->d_work + 1, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
+            PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const size_t m = (size_t)counts[0] + counts[1];
+            if (m > 0) {
+                const size_t rec_bytes = m * sizeof(ppe_edge_result), bytes = rec_bytes + m * sizeof(unsigned int);
+                rc = grow(ctx, &ctx->d_patch, &ctx->cap_patch, bytes);
+                if (rc != PPE_OK) return rc;
+                rc = grow_pinned(ctx, &ctx->h_pinned, &ctx->cap_pinned, bytes);
+                if (rc != PPE_OK) return rc;
+                unsigned int* d_idx = reinterpret_cast<unsigned int*>(ctx->d_patch + rec_bytes);
+                PPE_CUDA(ctx, launch_patch_results(ctx->d_results, ctx->d_heavy, ctx->d_work, n, reinterpret_cast<ppe_edge_result*>(ctx->d_patch),
+                                                   d_idx, ctx->sm_count, ctx->stream));
+                ctx->launches += 1;
+                PPE_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_patch, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                const ppe_edge_result* rec = reinterpret_cast<const ppe_edge_result*>(ctx->h_pinned);
+                const unsigned int* idx = reinterpret_cast<const unsigned int*>(static_cast<const unsigned char*>(ctx->h_pinned) + rec_bytes);
+                for (size_t i = 0; i < m; i++) results[idx[i]] = rec[i];
+            }
+        }
+        PPE_CUDA(ctx, cudaStreamSynchronize(ctx->stream_out));
+        if (ctx->last_out_count <= ctx->out_cap) break;
+        // the ribbons-after pool was too small for this batch: grow it and run the batch again
+        rc = ensure_pool(ctx, (size_t)(ctx->last_out_count + ctx->last_out_count / 4 + 1024));
+        if (rc != PPE_OK) return rc;
+        rc = make_world(ctx, &w);
+        if (rc != PPE_OK) return rc;
+    }
+    return PPE_OK;
+}
+
 int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge_result* results) {
     if (!ctx || n < 0 || (n > 0 && (!edges || !results))) return fail(ctx, PPE_ERR_INVALID, "ppe_true_cost_batch: bad arguments");
     PPE_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -735,6 +830,25 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
     int rc = make_world(ctx, &w);
     if (rc != PPE_OK) return rc;
     ctx->out_downloaded = false;
+    if (ctx->thread_walker && !ctx->tuning.deep_walker && ctx->late_k2b && n >= 4 * ctx->late_slice) {
+        const int64_t n_slices = (n + ctx->late_slice - 1) / ctx->late_slice;
+        while ((int64_t)ctx->ev_in.size() < n_slices) {
+            cudaEvent_t a, b, c;
+            PPE_CUDA(ctx, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            PPE_CUDA(ctx, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            PPE_CUDA(ctx, cudaEventCreateWithFlags(&c, cudaEventDisableTiming));
+            ctx->ev_in.push_back(a);
+            ctx->ev_k2.push_back(b);
+            ctx->ev_done.push_back(c);
+        }
+        rc = batch_pipelined(ctx, w, n, edges, results, ctx->late_slice);
+        if (rc != PPE_OK) return rc;
+        ctx->last_count = n;
+        ctx->have_batch = true;
+        ctx->last_was_expand = false;
+        ctx->out_downloaded = false;
+        return PPE_OK;
+    }
     // Slices of the batch flow through the streams: H2D of slice k + 1 (copy engine), the kernels of slices k and
     // k - 1 (two lanes) and D2H of finished slices (second copy engine) run concurrently; K3 accumulates the best
     // record slice by slice on the context stream.  Small batches are one slice.

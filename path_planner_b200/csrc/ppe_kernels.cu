@@ -1769,10 +1769,11 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
 }
 
 __global__ void __launch_bounds__(128)
-k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edge* __restrict__ edges,
-                const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
-                unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count, const int dirty_budget,
-                const int cp_budget) {
+k2t_thread_walk(const __grid_constant__ WorldD w, const long long first, const long long n, const long long list_n,
+                const ppe_edge* __restrict__ edges, const PreparedEdge* __restrict__ prepared,
+                ppe_edge_result* __restrict__ results, unsigned int* __restrict__ heavy_list,
+                unsigned int* __restrict__ heavy_count, const int dirty_budget, const int cp_budget) {
+    // edges [first, n) of the batch; the heavy list belongs to the whole batch (2 * list_n slots)
     extern __shared__ double4 smem4[];
     ObstacleD* s_obs = reinterpret_cast<ObstacleD*>(smem4);
     {
@@ -1790,9 +1791,9 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long n, const ppe_e
         tile_stage(w, s_tile, &s_tile_bar);
         tile = s_tile;
     }
-    const long long ei = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ei = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (ei >= n) return;
-    thread_walk<false>(w, n, ei, edges, prepared, results, heavy_list, heavy_count, dirty_budget, cp_budget, s_obs, tile);
+    thread_walk<false>(w, list_n, ei, edges, prepared, results, heavy_list, heavy_count, dirty_budget, cp_budget, s_obs, tile);
 }
 
 // K2c: one thread per edge of the FRONT heavy list (the edges K2t caught covering a ribbon)
@@ -2080,8 +2081,8 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
             if (e != cudaSuccess) return e;
         }
         const int dirty_budget = tuning.dirty_budget, cp_budget = tuning.cp_budget;
-        k2t_thread_walk<<<(unsigned)((n + 127) / 128), 128, smem_t, stream>>>(world, (long long)n, edges, prepared, results, heavy_list,
-                                                                             heavy_count, dirty_budget, cp_budget);
+        k2t_thread_walk<<<(unsigned)((n + 127) / 128), 128, smem_t, stream>>>(world, 0ll, (long long)n, (long long)n, edges, prepared,
+                                                                             results, heavy_list, heavy_count, dirty_budget, cp_budget);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         launches++;
@@ -2117,6 +2118,77 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
     launches++;
     *blocks_out = (int)blocks;
     if (launches_out) *launches_out = launches;
+    return cudaGetLastError();
+}
+
+// ---- host-buffer pipeline (ppe_true_cost_batch): K2a + K2t slice by slice while the copies run, K2b once ------------------------
+// K2a + K2t over the edges [first, first + cnt) of a batch of n_total edges (all pointers are the batch's arrays); what K2t
+// leaves behind is appended to the batch's heavy list.  `counters` must have been zeroed ahead of the first slice.
+cudaError_t launch_prepare_and_walk(const WorldD& world, int64_t n_total, int64_t first, int64_t cnt, const ppe_edge* edges,
+                                    void* prepared_scratch, ppe_edge_result* results, unsigned long long* counters,
+                                    unsigned int* heavy_list, cudaStream_t stream, K2Tuning tuning, int* launches_out) {
+    PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
+    k2a_prepare<<<(unsigned)((cnt + 127) / 128), 128, 0, stream>>>(world.cfg, world.dt, world.horizon_end, (long long)cnt, edges + first,
+                                                                  prepared + first);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
+    const size_t smem_t = (size_t)world.n_obs * sizeof(ObstacleD) +
+                          (world.tile_on ? (size_t)2 * world.tile_rows * world.tile_words * sizeof(uint32_t) : 0);
+    if (smem_t > 32 * 1024) {
+        e = cudaFuncSetAttribute(k2t_thread_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t);
+        if (e != cudaSuccess) return e;
+    }
+    k2t_thread_walk<<<(unsigned)((cnt + 127) / 128), 128, smem_t, stream>>>(world, (long long)first, (long long)(first + cnt),
+                                                                           (long long)n_total, edges, prepared, results, heavy_list,
+                                                                           heavy_count, tuning.dirty_budget, tuning.cp_budget);
+    if (launches_out) *launches_out = 2;
+    return cudaGetLastError();
+}
+
+// K2b over the batch's heavy list, then K3a over all results
+cudaError_t launch_heavy_and_best(const WorldD& world, int64_t n_total, const ppe_edge* edges, void* prepared_scratch,
+                                  ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
+                                  BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, int* blocks_out,
+                                  int* launches_out) {
+    PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
+    unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
+    cudaError_t e = launch_k2<kWarpsNarrow>(world, n_total, edges, prepared, results, counters, heavy_list, heavy_count, 1, max_blocks,
+                                            sm_count, stream);
+    if (e != cudaSuccess) return e;
+    long long blocks = (n_total + 255) / 256;
+    if (blocks > 1024) blocks = 1024;
+    if (blocks > max_blocks) blocks = max_blocks;
+    k3_best_scan<<<(unsigned)blocks, 256, 0, stream>>>(results, (long long)n_total, block_best);
+    *blocks_out = (int)blocks;
+    if (launches_out) *launches_out = 2;
+    return cudaGetLastError();
+}
+
+// The records K2b wrote, one warp per record: to their places in `dst` (the caller's result array, mapped pinned host
+// memory: a scatter over PCIe), or (compact_idx != nullptr) packed into dst[0 .. count) with their edge indices beside them.
+static_assert(sizeof(ppe_edge_result) % 16 == 0 && sizeof(ppe_edge_result) / 16 <= 32, "k_patch_results copies 16 B per lane");
+__global__ void __launch_bounds__(256)
+k_patch_results(const ppe_edge_result* __restrict__ results, const unsigned int* __restrict__ heavy_list,
+                const unsigned int* __restrict__ heavy_count, const long long n, ppe_edge_result* __restrict__ dst,
+                unsigned int* __restrict__ compact_idx) {
+    constexpr int kQuads = (int)(sizeof(ppe_edge_result) / 16);
+    const unsigned int n_front = heavy_count[0], total = n_front + heavy_count[1];
+    const int lane = threadIdx.x & 31;
+    const unsigned int warps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < total; k += warps) {
+        const unsigned int ei = k < n_front ? heavy_list[k] : heavy_list[2 * n - 1 - (k - n_front)];
+        const uint4* src = reinterpret_cast<const uint4*>(results + ei);
+        uint4* out = reinterpret_cast<uint4*>(dst + (compact_idx ? k : ei));
+        if (lane < kQuads) out[lane] = src[lane];
+        if (compact_idx && lane == 0) compact_idx[k] = ei;
+    }
+}
+
+cudaError_t launch_patch_results(const ppe_edge_result* results, const unsigned int* heavy_list, const unsigned long long* counters,
+                                 int64_t n_total, ppe_edge_result* dst, unsigned int* compact_idx, int sm_count, cudaStream_t stream) {
+    const unsigned int* heavy_count = reinterpret_cast<const unsigned int*>(counters + 1);
+    k_patch_results<<<(unsigned)(sm_count * 4), 256, 0, stream>>>(results, heavy_list, heavy_count, (long long)n_total, dst, compact_idx);
     return cudaGetLastError();
 }
 

@@ -116,6 +116,17 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
                                      ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
                                      BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, bool reset_pool,
                                      K2Tuning tuning, int* blocks_out, int* launches_out);
+// host-buffer pipeline of ppe_true_cost_batch: K2a + K2t per slice of the batch, K2b + K3a once, then the K2b records
+// to the caller's array (see ppe_kernels.cu)
+cudaError_t launch_prepare_and_walk(const WorldD& world, int64_t n_total, int64_t first, int64_t cnt, const ppe_edge* edges,
+                                    void* prepared_scratch, ppe_edge_result* results, unsigned long long* counters,
+                                    unsigned int* heavy_list, cudaStream_t stream, K2Tuning tuning, int* launches_out);
+cudaError_t launch_heavy_and_best(const WorldD& world, int64_t n_total, const ppe_edge* edges, void* prepared_scratch,
+                                  ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
+                                  BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, int* blocks_out,
+                                  int* launches_out);
+cudaError_t launch_patch_results(const ppe_edge_result* results, const unsigned int* heavy_list, const unsigned long long* counters,
+                                 int64_t n_total, ppe_edge_result* dst, unsigned int* compact_idx, int sm_count, cudaStream_t stream);
 cudaError_t launch_best_final(const BestD* block_best, int blocks, BestD* best, int64_t index_base, bool accumulate,
                               cudaStream_t stream);
 // *dst = {src->f, src->idx + index_base}: the NCCL send record of a rank that holds edges [index_base, ...)

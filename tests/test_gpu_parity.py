@@ -272,3 +272,44 @@ def test_deep_thread_walker_matches_oracle(oracle):
         got, want = _check_batch(eng, oracle, world, edges)
         deep += int(((got["reserved"] >> 25) & 1).sum())
     assert deep > 0
+
+
+@pytest.mark.parametrize("name,near,n", [("c2", 0.6, 9000), ("c5", 0.3, 5000)])
+def test_host_buffer_pipeline_matches_oracle(oracle, name, near, n):
+    """Large host-buffer batches run K2a + K2t slice by slice under the copies and K2b once at the end, whose records reach the
+    caller's array by a scatter kernel (pinned, mapped memory) or a packed copy + host scatter (pageable).  Forced here with a
+    small slice (PPE_LATE_SLICE, read at ppe_create): both variants must give the oracle's records, the ribbons-after pool
+    and the K3 record, and must agree with the one-launch-group path byte for byte."""
+    import ctypes as C
+    import os
+    import torch
+    os.environ["PPE_LATE_SLICE"] = "1024"
+    try:
+        eng = EdgeEngine(0)
+    finally:
+        os.environ.pop("PPE_LATE_SLICE", None)
+    world = synth.WORLDS[name]()
+    edges = synth.make_edges(world, n, seed=33, near_ribbons=near)
+    launches0 = eng.launch_count()
+    got, want = _check_batch(eng, oracle, world, edges)  # pageable numpy buffers
+    slices = (n + 1023) // 1024
+    assert eng.launch_count() - launches0 >= 2 * slices + 3, "the sliced pipeline did not run"
+    assert int(((got["reserved"] >> 24) & 1).sum()) < n, "no edge went to K2b: the scatter was not exercised"
+    # pinned buffers: K2b's records are written into the caller's array by the scatter kernel
+    h_edges = torch.from_numpy(edges.view(np.uint8).reshape(n, -1).copy()).pin_memory()
+    h_res = torch.zeros((n, abi.RESULT_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
+    rc = eng._lib.ppe_true_cost_batch(eng._ctx, n, C.c_void_p(h_edges.data_ptr()), C.c_void_p(h_res.data_ptr()))
+    assert rc == 0
+    pinned = h_res.numpy().view(abi.RESULT_DTYPE).reshape(n)
+    # the ribbons-after pool is filled in whatever order the warps finish: offsets differ run to run, nothing else may
+    a, b = pinned.copy(), got.copy()
+    a["ribbons_offset"] = 0
+    b["ribbons_offset"] = 0
+    assert a.tobytes() == b.tobytes()
+    # and the one-launch-group path (default slice: a batch this small is not pipelined)
+    ref = EdgeEngine(0)
+    sid = world.upload(ref)
+    assert sid == edges["ribbon_set"][0]
+    c = ref.true_cost_batch(edges)
+    c["ribbons_offset"] = 0
+    assert c.tobytes() == b.tobytes()

@@ -181,7 +181,7 @@ int ppe_dubins_batch(ppe_ctx* ctx, int64_t n, const double* q0, const double* q1
  * kernels of different slices overlap; pinned host buffers make the copies asynchronous.
  * Environment knobs read at ppe_create (tuning / testing only): PPE_THREAD_WALKER=0 evaluates every
  * edge with the warp walker K2b instead of K2t + K2b; PPE_K2T_DIRTY=<n> non-clean chunks a K2t
- * thread may evaluate before handing the edge to K2b (default 2). */
+ * warp may evaluate for one edge before handing it to K2b (default 64 = all). */
 int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge_result* results);
 /* Ribbons-after of edge `edge_index` of the last batch (4 doubles per ribbon, list order).
  * Returns the number of ribbons (<= cap written) or a negative status. */

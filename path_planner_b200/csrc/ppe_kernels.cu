@@ -1258,23 +1258,36 @@ __device__ void process_edge(const WorldD& w, const WorldD* ws, const ppe_edge* 
 // to "would it change anything?") and the check-point budget is not exceeded.  Anything else (a cover that splits or
 // erases a ribbon, coverage already complete, a non-OK status, unusual time scales) puts the edge on the heavy list and
 // the warp walker K2b evaluates it from scratch; both paths produce the same bits.
-constexpr int kThreadDirtyCap = 8;    // upper limit of K2Tuning::dirty_budget (size of the per-thread mask array)
+constexpr int kThreadDirtyCap = 64;   // upper limit of K2Tuning::dirty_budget (size of the per-thread mask array): every chunk of an edge
+constexpr int kDeepDirtyBudget = 8;   // K2c evaluates its dirty chunks sample by sample in the edge's own thread
 
-struct SeqTime { // cursor over the prepared run table
+struct SeqTime { // cursor over the prepared run table; the current run [lo, hi) and its coefficients stay in registers
     const PreparedEdge* p;
-    int r;
+    int r, n_runs, lo, hi;
+    double base, D;
+    __device__ __forceinline__ explicit SeqTime(const PreparedEdge* prep) : p(prep), r(0), n_runs(prep->n_runs) { load(); }
+    __device__ __forceinline__ void load() {
+        lo = p->run_i0[r];
+        hi = r + 1 < n_runs ? p->run_i0[r + 1] : INT_MAX;
+        base = p->run_base[r];
+        D = p->run_D[r];
+    }
     __device__ __forceinline__ double at(int i) {
-        while (r + 1 < p->n_runs && i >= p->run_i0[r + 1]) r++;
-        while (r > 0 && i < p->run_i0[r]) r--;
-        return p->run_base[r] + (double)(i - p->run_i0[r]) * p->run_D[r];
+        if (i >= hi || (i < lo && r > 0)) { // the run with run_i0[r] <= i < run_i0[r + 1], clamped to the table
+            while (r + 1 < n_runs && i >= p->run_i0[r + 1]) r++;
+            while (r > 0 && i < p->run_i0[r]) r--;
+            load();
+        }
+        return base + (double)(i - lo) * D;
     }
 };
 
 // minDistanceFrom + "would cover(x, y, strict) change the list?" over the parent's ribbons, in place
+// (`any_short`: the per-set invariant "some ribbon is short enough for cover() to erase it wherever the point is")
 __device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib, int nr, double x, double y, double W, bool tame,
-                                                 bool* would_change) {
+                                                 bool any_short, bool* would_change) {
     double mn = DBL_MAX;
-    bool inside = false, change = false;
+    bool inside = false, change = any_short;
 #pragma unroll 1
     for (int r = 0; r < nr; r++) {
         const RibbonD rb = load_ribbon(rib + r);
@@ -1289,7 +1302,7 @@ __device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib
             }
         }
         // cover leaves a ribbon as it is iff it is not (strictly) contained and not already short enough to erase
-        change = change || contained || ribbon_covered(rb, true, W);
+        change = change || contained;
         const double dStart = point_distance_sq(rb.sx, rb.sy, x, y);
         const double dEnd = point_distance_sq(rb.ex, rb.ey, x, y);
         mn = fmin(fmin(mn, dEnd), dStart); // squared
@@ -1464,23 +1477,28 @@ template <bool kDeep>
 __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, const long long ei, const ppe_edge* __restrict__ edges,
                                             const PreparedEdge* __restrict__ prepared, ppe_edge_result* __restrict__ results,
                                             unsigned int* __restrict__ heavy_list, unsigned int* __restrict__ heavy_count,
-                                            const int dirty_budget, const int cp_budget, const ObstacleD* s_obs, const uint32_t* tile) {
+                                            const int dirty_budget, const int cp_budget, const ObstacleD* s_obs, const uint32_t* tile,
+                                            const bool live) {
+    // `live` = false (K2t only): a lane of the batch's last warp without an edge of its own -- `ei` then names some valid
+    // edge that is only read; the lane takes part in the warp-cooperative phase B and writes nothing.
     const ppe_edge* edge = edges + ei;
     const PreparedEdge* prep = prepared + ei;
     const double* pe = prep->v;
     const ppe_config& cfg = w.cfg;
     const double W = cfg.ribbon_width, inc = cfg.collision_checking_increment, dt = w.dt;
 
-    if (pe[kStatus] == (double)PPE_EDGE_SKIPPED) { // empty slot of a frontier batch: nothing to evaluate
+    bool skipped = false;
+    if (live && pe[kStatus] == (double)PPE_EDGE_SKIPPED) { // empty slot of a frontier batch: nothing to evaluate
         ppe_edge_result* r = results + ei;
         memset(r, 0, sizeof *r);
         r->ribbons_offset = -1;
         r->status = PPE_EDGE_SKIPPED;
-        return;
+        if (kDeep) return;
+        skipped = true; // K2t: the lane stays for phase B
     }
     // ---- is this edge simple at all? -------------------------------------------------------------------------------
     const int set = edge->ribbon_set;
-    bool heavy = !(set >= 0 && set < w.n_sets) || pe[kStatus] != 0.0 || pe[kSampleFault] != 0.0 || prep->n_runs <= 0;
+    bool heavy = !live || skipped || !(set >= 0 && set < w.n_sets) || pe[kStatus] != 0.0 || pe[kSampleFault] != 0.0 || prep->n_runs <= 0;
     int nr = 0;
     double cct = -1;
     const double4* rib = nullptr;
@@ -1492,7 +1510,9 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     }
     bool tame = fabs(pe[kX0]) + fabs(pe[kLength]) < 1e7 && fabs(pe[kY0]) + fabs(pe[kLength]) < 1e7 && fabs(edge->src[0]) < 1e7 &&
                 fabs(edge->src[1]) < 1e7;
+    bool any_short = true;
     if (!heavy) {
+        any_short = (w.set_tame[set] & 2) != 0;
         tame = tame && (w.set_tame[set] & 1) != 0;
         // K2c keeps the ribbons' structure: a list holding a ribbon short enough for cover() to erase it wherever the
         // point is, or coordinates beyond the bounding-box shortcut's range, is the warp walker's
@@ -1523,11 +1543,17 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     heavy = heavy || n_valid < 0 || n_valid > 64 * kChunk;
 
     // The walk is organised in phases that keep the 32 edges of a warp on the same instructions: every thread probes
-    // ALL its chunks first (uniform, cheap); then the few chunks that were not proved clean are evaluated sample by
-    // sample -- thread k's j-th such chunk runs in lockstep with every other thread's j-th, instead of the whole warp
-    // waiting whenever any one of its threads meets a dirty chunk; then the check-points; then the tail.
+    // ALL its chunks first (uniform, cheap); then the few chunks that were not proved clean are evaluated -- K2t: by the
+    // whole warp, lane i = sample i of the chunk, one (edge, chunk) item after the other; K2c: sample by sample in the
+    // edge's own thread -- then the check-points; then the tail.
+    SeqTime tm(prep);
+    unsigned long long dirty = 0;      // bit c: chunk c must be evaluated
+    unsigned long long dmask[kThreadDirtyCap]; // its candidate obstacles, in order of appearance
+    int n_dirty = 0;
+    bool more_dirty = false;
+    int n_exec = n_valid;      // samples that run the full loop body
+    bool blocked_exit = false;
     if (!heavy) {
-        SeqTime tm{prep, 0};
         const double rad_max = 0.5 * kChunk * inc * 1.001 + 1e-6;
         // obstacles that can matter anywhere on this edge
         unsigned long long edge_mask = w.n_obs >= 64 ? ~0ull : ((1ull << w.n_obs) - 1ull);
@@ -1546,10 +1572,6 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
 
         // ---- phase A: probe every chunk (the last one over its valid samples only) -------------------------------------
         const int n_chunks = (n_valid + kChunk - 1) / kChunk;
-        unsigned long long dirty = 0;      // bit c: chunk c must be evaluated
-        unsigned long long dmask[kThreadDirtyCap]; // its candidate obstacles, in order of appearance
-        int n_dirty = 0;
-        bool more_dirty = false;
 #pragma unroll 1
         for (int c = 0; c < n_chunks; c++) {
             const int c0 = c * kChunk;
@@ -1564,12 +1586,73 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
                 dmask[n_dirty++] = om;
             }
         }
+    }
 
-        // ---- phase B: the dirty chunks, sample by sample, in order (Edge.cpp:126-151) until the loop would stop --------------
-        int n_exec = n_valid;      // samples that run the full loop body
-        bool blocked_exit = false;
-        if (!heavy) {
-            tm.r = 0;
+    // ---- phase B: the dirty chunks in order (Edge.cpp:126-151) until the loop would stop -------------------------------------
+    if (!kDeep) {
+        // K2t: the warp takes the (edge, chunk) items of its 32 threads one after the other, lane i evaluating sample i of
+        // the chunk -- 32 samples in the time one thread needs for one.  Every lane of the warp gets here (live or not,
+        // simple or not); the owner of an item keeps its outcome, in the order the sequential loop would have met it.
+        const int lane = threadIdx.x & 31;
+        unsigned long long todo = dirty;
+#pragma unroll 1
+        for (int j = 0; j < dirty_budget; j++) {
+            const bool want = !heavy && n_exec == n_valid && j < n_dirty;
+            unsigned pending = __ballot_sync(kFull, want);
+            const int c_own = want ? __ffsll((long long)todo) - 1 : 0;
+            const unsigned long long om_own = want ? dmask[j] : 0ull;
+            while (pending) {
+                const int b = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const PreparedEdge* pp = reinterpret_cast<const PreparedEdge*>(shfl_u64((unsigned long long)prep, b));
+                const unsigned long long omask = shfl_u64(om_own, b);
+                const int c0 = __shfl_sync(kFull, c_own, b) * kChunk;
+                const int nv = __shfl_sync(kFull, n_valid, b);
+                const int last = (c0 + kChunk - 1 < nv - 1) ? c0 + kChunk - 1 : nv - 1;
+                const int i = c0 + lane;
+                const bool valid = i <= last;
+                double x = 0, y = 0, ang = 0, pen = 0;
+                bool in_time = true, sample_ok = true, blocked = false;
+                if (valid) {
+                    SeqTime tb(pp);
+                    const double t_i = tb.at(i);
+                    sample_ok = pose_eval(pp->v, t_i, &x, &y, &ang, &in_time);
+                    if (in_time && sample_ok) {
+                        blocked = map_blocked(w, x, y, tile);                                     // Edge.cpp:144-147
+                        if (!blocked && w.obs_kind != kObsNone && w.n_obs > 0 && omask != 0)
+                            pen = collision_exists(w.obs_kind, w.n_obs, s_obs, omask, true, x, y, t_i) * cfg.collision_penalty_factor;
+                    }
+                }
+                const unsigned m_nit = __ballot_sync(kFull, valid && !in_time);                   // sample() throws, Edge.cpp:126-133
+                const unsigned m_bad = __ballot_sync(kFull, valid && in_time && !sample_ok);      // stale-pose corner: warp walker
+                const unsigned m_blk = __ballot_sync(kFull, valid && in_time && sample_ok && blocked);
+                const unsigned m_stop = m_nit | m_bad | m_blk;
+                const int s_stop = m_stop ? __ffs(m_stop) - 1 : 0;
+                const int limit = m_stop ? s_stop : last - c0 + 1; // samples [c0, c0 + limit) run the full loop body
+                double acc = __shfl_sync(kFull, penalty, b);      // the penalty sum, in sample order
+                if (__any_sync(kFull, lane < limit && pen != 0.0)) {
+                    for (int q = 0; q < limit; q++) acc += __shfl_sync(kFull, pen, q);
+                }
+                const double sx_ = __shfl_sync(kFull, x, s_stop), sy_ = __shfl_sync(kFull, y, s_stop), sa_ = __shfl_sync(kFull, ang, s_stop);
+                if (lane == b) {
+                    penalty = acc;
+                    todo &= todo - 1;
+                    if (m_stop) {
+                        const unsigned bit = 1u << s_stop;
+                        if (m_bad & bit) {
+                            heavy = true;
+                        } else {
+                            infeasible = true;
+                            n_exec = c0 + s_stop;
+                            if (m_blk & bit) { blocked_exit = true; P_x = sx_; P_y = sy_; P_h = heading_of(sa_); } // `intermediate` holds the blocked sample
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!heavy) {
+        if (kDeep) {
             int j = 0;
             unsigned long long todo = dirty;
 #pragma unroll 1
@@ -1598,6 +1681,8 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
                         penalty += collision_exists(w.obs_kind, w.n_obs, s_obs, omask, true, x, y, t_i) * cfg.collision_penalty_factor;
                 }
             }
+        }
+        {
             // per-sample work beyond the budget belongs to the warp walker (lanes = samples)
             if (more_dirty && n_exec == n_valid) heavy = true;
             n_samples = n_exec + (infeasible && n_exec < n_valid ? 1 : 0); // the breaking iteration was entered
@@ -1638,7 +1723,7 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
                 double toCover;
                 if (!kDeep) {
                     bool would_change;
-                    toCover = seq_checkpoint(rib, nr, x, y, W, tame, &would_change);
+                    toCover = seq_checkpoint(rib, nr, x, y, W, tame, any_short, &would_change);
                     if (do_cover && would_change) { long_run = true; heavy = true; break; }
                 } else {
                     const int c = idx / kChunk;
@@ -1678,7 +1763,7 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
             if (!heavy && (cov || lastHeading == P_h)) {
                 if (!kDeep) {
                     bool would_change;
-                    seq_checkpoint(rib, nr, P_x, P_y, W, tame, &would_change);
+                    seq_checkpoint(rib, nr, P_x, P_y, W, tame, any_short, &would_change);
                     if (would_change) heavy = true;
                 } else { // the final cover at `intermediate` (Edge.cpp:182-184)
                     int rel[kDeepRelCap];
@@ -1691,6 +1776,7 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     }
 
     if (heavy) {
+        if (!live || skipped) return;
         // The heavy list is filled from both ends: edges that were caught covering a ribbon (they tend to run along
         // it for hundreds of check-points, milliseconds of strictly sequential work) from the front, the rest from
         // the back.  K2b takes the front first, so the longest items start first and the batch does not end on one.
@@ -1768,7 +1854,10 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     r->reserved = (n_culled & 0xffffff) | (1 << 24) | (kDeep ? (1 << 25) : 0);
 }
 
-__global__ void __launch_bounds__(128)
+#ifndef PPE_K2T_BLOCKS_PER_SM
+#define PPE_K2T_BLOCKS_PER_SM 5 // 5 x 128 threads: at most 102 registers per thread
+#endif
+__global__ void __launch_bounds__(128, PPE_K2T_BLOCKS_PER_SM)
 k2t_thread_walk(const __grid_constant__ WorldD w, const long long first, const long long n, const long long list_n,
                 const ppe_edge* __restrict__ edges, const PreparedEdge* __restrict__ prepared,
                 ppe_edge_result* __restrict__ results, unsigned int* __restrict__ heavy_list,
@@ -1792,8 +1881,10 @@ k2t_thread_walk(const __grid_constant__ WorldD w, const long long first, const l
         tile = s_tile;
     }
     const long long ei = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (ei >= n) return;
-    thread_walk<false>(w, list_n, ei, edges, prepared, results, heavy_list, heavy_count, dirty_budget, cp_budget, s_obs, tile);
+    if (ei - (threadIdx.x & 31) >= n) return; // the whole warp lies beyond the range
+    // phase B of the walk is warp-cooperative: the lanes beyond the last edge stay, reading (never writing) edge n - 1
+    const bool live = ei < n;
+    thread_walk<false>(w, list_n, live ? ei : n - 1, edges, prepared, results, heavy_list, heavy_count, dirty_budget, cp_budget, s_obs, tile, live);
 }
 
 // K2c: one thread per edge of the FRONT heavy list (the edges K2t caught covering a ribbon)
@@ -1812,7 +1903,7 @@ k2c_deep_walk(const __grid_constant__ WorldD w, const long long n, const ppe_edg
     __syncthreads();
     const unsigned int n_front = heavy_count[0];
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_front; k += gridDim.x * blockDim.x)
-        thread_walk<true>(w, n, (long long)heavy_list[k], edges, prepared, results, heavy_list, heavy_count, dirty_budget, 0, s_obs, nullptr);
+        thread_walk<true>(w, n, (long long)heavy_list[k], edges, prepared, results, heavy_list, heavy_count, dirty_budget, 0, s_obs, nullptr, true);
 }
 
 // K2a: one thread per edge
@@ -2095,7 +2186,7 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
             long long cblocks = (n + 127) / 128;
             if (cblocks > (long long)sm_count * 8) cblocks = (long long)sm_count * 8;
             k2c_deep_walk<<<(unsigned)cblocks, 128, smem_c, stream>>>(world, (long long)n, edges, prepared, results, heavy_list, heavy_count,
-                                                                     kThreadDirtyCap);
+                                                                     kDeepDirtyBudget);
             e = cudaGetLastError();
             if (e != cudaSuccess) return e;
             launches++;

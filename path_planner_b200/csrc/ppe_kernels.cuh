@@ -72,7 +72,7 @@ struct BestD {
 
 // K2t hand-over budgets (measured best on C2 / C3 / C5; PPE_K2T_DIRTY / PPE_K2T_CPS override them per context)
 struct K2Tuning {
-    int dirty_budget = 2; // non-clean chunks a K2t thread evaluates sample by sample before handing the edge to K2b
+    int dirty_budget = 64; // non-clean chunks of an edge that K2t evaluates (warp-cooperatively) before handing the edge to K2b
     int cp_budget = 6;    // ribbon check-points a K2t thread walks
     int deep_walker = 0;  // K2c: thread-per-edge walk of the edges K2t caught covering a ribbon (PPE_DEEP_WALKER=1; measured
                           // slower than handing them to K2b -- DESIGN.md section 4.5 -- so off by default)

@@ -384,11 +384,17 @@ PPE_HD bool ribbon_covered(const RibbonD& r, bool strict, double W) { // Ribbon.
     const double minLength = 2 * W;
     return ribbon_sqlen(r) < minLength * minLength / (strict ? 2.0 * 2.0 : 1.0);
 }
+// num / den.  A zero numerator over a positive denominator is the numerator itself (the sign of the zero included); it is
+// returned without dividing because CUDA's fp64 division leaves its inline sequence for numerators that small and calls a
+// ~100-instruction routine -- and an axis-aligned ribbon produces one such quotient in every projection (ncu, round 2:
+// 16 % of the warp walker's instructions were that routine).
+PPE_HD double div_zero_aware(double num, double den) { return (num == 0.0 && den > 0.0) ? num : num / den; }
+
 PPE_HD void ribbon_projection(const RibbonD& r, double x, double y, double* px, double* py) { // Ribbon.cpp:72-78
     const double squaredL = ribbon_sqlen(r);
     const double dot = (x - r.sx) * (r.ex - r.sx) + (y - r.sy) * (r.ey - r.sy);
-    const double projectedX = (r.ex - r.sx) * dot / squaredL;
-    const double projectedY = (r.ey - r.sy) * dot / squaredL;
+    const double projectedX = div_zero_aware((r.ex - r.sx) * dot, squaredL);
+    const double projectedY = div_zero_aware((r.ey - r.sy) * dot, squaredL);
     *px = projectedX + r.sx;
     *py = projectedY + r.sy;
 }
@@ -398,7 +404,7 @@ PPE_HD bool ribbon_contains_projection(const RibbonD& r, double px, double py) {
              ((py - r.sy < -tol && py - r.ey < -tol) || (py - r.sy > tol && py - r.ey > tol)));
 }
 PPE_HD double ribbon_distance(const RibbonD& r, double x, double y) { // Ribbon.h:118-121
-    return (fabs((r.ey - r.sy) * x - (r.ex - r.sx) * y + r.ex * r.sy - r.ey * r.sx)) / sqrt(ribbon_sqlen(r));
+    return div_zero_aware(fabs((r.ey - r.sy) * x - (r.ex - r.sx) * y + r.ex * r.sy - r.ey * r.sx), sqrt(ribbon_sqlen(r)));
 }
 PPE_HD bool ribbon_contains(const RibbonD& r, double x, double y, double px, double py, bool strict, double W) { // Ribbon.cpp:39-43
     if (!ribbon_contains_projection(r, px, py)) return false;

@@ -16,8 +16,9 @@ for wl in c5 c2; do
        $B --workload $wl > $OUT/${TAG}_ncu_${k}_${wl}.log 2>&1; echo "ncu full $k $wl rc=$?"
   done
 done
+# (TILEAB_MODES= skips it)
 # N2 A/B: the thread walker on the frontier-shaped batch, look-ups from L2 (__ldg) vs the shared-memory tile
-for mode in ldg smem_tile; do
+for mode in ${TILEAB_MODES-ldg smem_tile}; do
   envs=""; [ $mode = smem_tile ] && envs="PPE_MAP_TILE=1"
   timeout 900 env $envs ncu --set full --clock-control none --import-source on -k regex:k2t_thread_walk -s 3 -c 1 -o $OUT/${TAG}_k2t_tileab_${mode} -f \
      python tools/map_tile_ab.py $mode c4 > $OUT/${TAG}_ncu_tileab_${mode}.log 2>&1; echo "ncu tile A/B $mode rc=$?"

@@ -75,6 +75,9 @@ struct ppe_ctx {
     size_t uploaded_ribbons = 0, uploaded_sets = 0; // the pool is append-only: only the tail is copied
     int max_set = 0;
     double4* d_ribbons = nullptr;
+    double4* d_boxes = nullptr;    // per ribbon of the pool: bounding box grown by the ribbon width (WorldD::boxes)
+    size_t cap_boxes = 0, uploaded_boxes = 0;
+    std::vector<double> h_boxes;
     int* d_off = nullptr;
     int* d_cnt = nullptr;
     double* d_cct = nullptr;
@@ -216,10 +219,31 @@ int upload_sets(ppe_ctx* ctx) {
             ctx->h_tame[k] = (ctx->h_tame[k] & 1) | (any_short ? 2 : 0);
         }
         ctx->uploaded_sets = 0;
+        ctx->uploaded_boxes = 0; // the boxes are grown by the width
     }
     const size_t r0 = ctx->uploaded_ribbons, s0 = ctx->uploaded_sets;
     int rc = grow_keep(ctx, &ctx->d_ribbons, &ctx->cap_ribbons, nr + 1, r0, 1024);
     if (rc != PPE_OK) return rc;
+    {
+        // the box ribbon_may_contain (ppe_kernels.cu) compares a point with: the segment's bounding box grown by the ribbon
+        // width and the shortcut's margin -- the same IEEE operations the kernel used to repeat per ribbon and check-point
+        if (ctx->uploaded_boxes > nr || ctx->uploaded_boxes > r0) ctx->uploaded_boxes = 0;
+        const size_t b0 = ctx->uploaded_boxes;
+        ctx->h_boxes.resize(nr * 4);
+        const double grow = ctx->cfg.ribbon_width * (1 + 1e-9) + 1e-3;
+        for (size_t i = b0; i < nr; i++) {
+            const double* r = ctx->h_ribbons.data() + 4 * i;
+            double* b = ctx->h_boxes.data() + 4 * i;
+            b[0] = fmin(r[0], r[2]) - grow; b[1] = fmax(r[0], r[2]) + grow;
+            b[2] = fmin(r[1], r[3]) - grow; b[3] = fmax(r[1], r[3]) + grow;
+        }
+        rc = grow_keep(ctx, &ctx->d_boxes, &ctx->cap_boxes, nr + 1, b0, 1024);
+        if (rc != PPE_OK) return rc;
+        if (nr > b0)
+            PPE_CUDA(ctx, cudaMemcpyAsync(ctx->d_boxes + b0, ctx->h_boxes.data() + 4 * b0, (nr - b0) * 4 * sizeof(double),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+        ctx->uploaded_boxes = nr;
+    }
     {
         size_t c1 = ctx->cap_sets, c2 = ctx->cap_sets, c3 = ctx->cap_sets, c4 = ctx->cap_sets, c5 = ctx->cap_sets;
         rc = grow_keep(ctx, &ctx->d_off, &c1, ns + 1, s0, 64);
@@ -333,6 +357,7 @@ int make_world(ppe_ctx* ctx, WorldD* w) {
     w->obs_kind = ctx->n_obs > 0 ? ctx->obs_kind : kObsNone;
     w->n_obs = ctx->obs_kind == kObsNone ? 0 : ctx->n_obs;
     w->ribbons = ctx->d_ribbons;
+    w->boxes = ctx->d_boxes;
     w->set_offset = ctx->d_off;
     w->set_count = ctx->d_cnt;
     w->set_cct = ctx->d_cct;
@@ -386,6 +411,8 @@ int ppe_create(int device, ppe_ctx** out) {
         if (env_cp && atoi(env_cp) > 0) ctx->tuning.cp_budget = atoi(env_cp);
         const char* env_d = getenv("PPE_K2T_DIRTY");  // tuning knob: non-clean chunks a K2t thread may evaluate
         if (env_d) ctx->tuning.dirty_budget = atoi(env_d);
+        const char* env_k2b = getenv("PPE_K2B_CTAS");  // tuning knob: K2b CTAs per SM
+        if (env_k2b) ctx->tuning.k2b_ctas_per_sm = atoi(env_k2b);
         const char* env_late = getenv("PPE_LATE_K2B");
         if (env_late) ctx->late_k2b = atoi(env_late) != 0;
         const char* env_ls = getenv("PPE_LATE_SLICE");
@@ -414,7 +441,7 @@ void ppe_destroy(ppe_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_map); cudaFree(ctx->d_safe); cudaFree(ctx->d_safe_tmp); cudaFree(ctx->d_obs);
-    cudaFree(ctx->d_ribbons); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct); cudaFree(ctx->d_sumlen); cudaFree(ctx->d_tame);
+    cudaFree(ctx->d_ribbons); cudaFree(ctx->d_boxes); cudaFree(ctx->d_off); cudaFree(ctx->d_cnt); cudaFree(ctx->d_cct); cudaFree(ctx->d_sumlen); cudaFree(ctx->d_tame);
     cudaFree(ctx->d_edges); cudaFree(ctx->d_results); cudaFree(ctx->d_prepared); cudaFree(ctx->d_dub); cudaFree(ctx->d_dubi);
     cudaFree(ctx->d_out_ribbons); cudaFree(ctx->d_out_count);
     cudaFree(ctx->d_work); cudaFree(ctx->d_heavy); cudaFree(ctx->d_block_best); cudaFree(ctx->d_best);
@@ -606,6 +633,7 @@ int ppe_clear_ribbon_sets(ppe_ctx* ctx) {
     ctx->h_ribbons.clear(); ctx->h_off.clear(); ctx->h_cnt.clear(); ctx->h_cct.clear(); ctx->h_sumlen.clear(); ctx->h_tame.clear();
     ctx->max_set = 0;
     ctx->uploaded_ribbons = ctx->uploaded_sets = 0;
+    ctx->uploaded_boxes = 0;
     ctx->sets_dirty = true;
     ctx->have_batch = false;
     return PPE_OK;
@@ -772,7 +800,7 @@ static int batch_pipelined(ppe_ctx* ctx, WorldD& w, int64_t n, const ppe_edge* e
         PPE_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], ctx->stream_out));
         int blocks = 1, launches = 0;
         PPE_CUDA(ctx, launch_heavy_and_best(w, n, ctx->d_edges, ctx->d_prepared, ctx->d_results, ctx->d_work, ctx->d_heavy, ctx->d_block_best,
-                                            ctx->max_blocks, ctx->sm_count, ctx->stream, &blocks, &launches));
+                                            ctx->max_blocks, ctx->sm_count, ctx->stream, ctx->tuning, &blocks, &launches));
         PPE_CUDA(ctx, launch_best_final(ctx->d_block_best, blocks, ctx->d_best, 0, false, ctx->stream));
         ctx->launches += launches + 1;
         PPE_CUDA(ctx, cudaMemcpyAsync(&ctx->last_out_count, ctx->d_out_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1284,15 +1284,18 @@ struct SeqTime { // cursor over the prepared run table; the current run [lo, hi)
 
 // minDistanceFrom + "would cover(x, y, strict) change the list?" over the parent's ribbons, in place
 // (`any_short`: the per-set invariant "some ribbon is short enough for cover() to erase it wherever the point is")
-__device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib, int nr, double x, double y, double W, bool tame,
-                                                 bool any_short, bool* would_change) {
+// `box`: the grown bounding boxes of the same ribbons (WorldD::boxes), what ribbon_may_contain would compute
+__device__ __forceinline__ double seq_checkpoint(const double4* __restrict__ rib, const double4* __restrict__ box, int nr, double x, double y,
+                                                 double W, bool tame, bool any_short, bool* would_change) {
     double mn = DBL_MAX;
     bool inside = false, change = any_short;
 #pragma unroll 1
     for (int r = 0; r < nr; r++) {
         const RibbonD rb = load_ribbon(rib + r);
+        const double4 bx = box[r];
         bool contained = false;
-        if (ribbon_may_contain(rb, x, y, W, tame)) {
+        const bool outside = x < bx.x || x > bx.y || y < bx.z || y > bx.w;
+        if (!(outside && tame)) {
             double px, py;
             ribbon_projection(rb, x, y, &px, &py);
             if (ribbon_contains_projection(rb, px, py)) {
@@ -1502,10 +1505,12 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
     int nr = 0;
     double cct = -1;
     const double4* rib = nullptr;
+    const double4* box = nullptr;
     if (!heavy) {
         nr = w.set_count[set];
         cct = w.set_cct[set];
         rib = w.ribbons + w.set_offset[set];
+        box = w.boxes + w.set_offset[set];
         heavy = nr <= 0 || nr > w.ribbon_cap; // coverage already complete: every sample is a check-point (warp walker)
     }
     bool tame = fabs(pe[kX0]) + fabs(pe[kLength]) < 1e7 && fabs(pe[kY0]) + fabs(pe[kLength]) < 1e7 && fabs(edge->src[0]) < 1e7 &&
@@ -1723,7 +1728,7 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
                 double toCover;
                 if (!kDeep) {
                     bool would_change;
-                    toCover = seq_checkpoint(rib, nr, x, y, W, tame, any_short, &would_change);
+                    toCover = seq_checkpoint(rib, box, nr, x, y, W, tame, any_short, &would_change);
                     if (do_cover && would_change) { long_run = true; heavy = true; break; }
                 } else {
                     const int c = idx / kChunk;
@@ -1763,7 +1768,7 @@ __device__ __forceinline__ void thread_walk(const WorldD& w, const long long n, 
             if (!heavy && (cov || lastHeading == P_h)) {
                 if (!kDeep) {
                     bool would_change;
-                    seq_checkpoint(rib, nr, P_x, P_y, W, tame, any_short, &would_change);
+                    seq_checkpoint(rib, box, nr, P_x, P_y, W, tame, any_short, &would_change);
                     if (would_change) heavy = true;
                 } else { // the final cover at `intermediate` (Edge.cpp:182-184)
                     int rel[kDeepRelCap];
@@ -2122,7 +2127,8 @@ size_t prepared_edge_bytes() { return sizeof(PreparedEdge); }
 template <int kW>
 static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edges, const PreparedEdge* prepared,
                              ppe_edge_result* results, unsigned long long* work_counter, const unsigned int* heavy_list,
-                             const unsigned int* heavy_count, int front_too, int max_blocks, int sm_count, cudaStream_t stream) {
+                             const unsigned int* heavy_count, int front_too, int max_blocks, int sm_count, cudaStream_t stream,
+                             int ctas_per_sm) {
     const size_t smem = k2_smem_bytes(kW, world.ribbon_cap, world.n_obs);
     cudaError_t e;
     if (smem > 32 * 1024) { // per device and per function (static + dynamic must fit): set it whenever it may be needed
@@ -2133,6 +2139,7 @@ static cudaError_t launch_k2(const WorldD& world, int64_t n, const ppe_edge* edg
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_true_cost<kW>, kW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    if (ctas_per_sm > 0 && per_sm > ctas_per_sm) per_sm = ctas_per_sm;
     // persistent grid: a multiple of the SM count, never more warps than edges
     long long blocks = (long long)sm_count * per_sm;
     const long long needed = (n + kW - 1) / kW;
@@ -2197,9 +2204,9 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
 #define PPE_K2_FORCE_NARROW 1
 #endif
     if (!PPE_K2_FORCE_NARROW && k2_smem_bytes(kWarpsWide, world.ribbon_cap, world.n_obs) <= 190 * 1024)
-        e = launch_k2<kWarpsWide>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, front_too, max_blocks, sm_count, stream);
+        e = launch_k2<kWarpsWide>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, front_too, max_blocks, sm_count, stream, tuning.k2b_ctas_per_sm);
     else
-        e = launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, front_too, max_blocks, sm_count, stream);
+        e = launch_k2<kWarpsNarrow>(world, n, edges, prepared, results, counters, heavy_list, heavy_count, front_too, max_blocks, sm_count, stream, tuning.k2b_ctas_per_sm);
     if (e != cudaSuccess) return e;
     launches++;
     long long blocks = (n + 255) / 256;
@@ -2240,12 +2247,12 @@ cudaError_t launch_prepare_and_walk(const WorldD& world, int64_t n_total, int64_
 // K2b over the batch's heavy list, then K3a over all results
 cudaError_t launch_heavy_and_best(const WorldD& world, int64_t n_total, const ppe_edge* edges, void* prepared_scratch,
                                   ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
-                                  BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, int* blocks_out,
-                                  int* launches_out) {
+                                  BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, K2Tuning tuning,
+                                  int* blocks_out, int* launches_out) {
     PreparedEdge* prepared = reinterpret_cast<PreparedEdge*>(prepared_scratch);
     unsigned int* heavy_count = reinterpret_cast<unsigned int*>(counters + 1);
     cudaError_t e = launch_k2<kWarpsNarrow>(world, n_total, edges, prepared, results, counters, heavy_list, heavy_count, 1, max_blocks,
-                                            sm_count, stream);
+                                            sm_count, stream, tuning.k2b_ctas_per_sm);
     if (e != cudaSuccess) return e;
     long long blocks = (n_total + 255) / 256;
     if (blocks > 1024) blocks = 1024;

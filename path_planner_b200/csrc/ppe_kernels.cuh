@@ -50,6 +50,7 @@ struct WorldD {
     int obs_kind, n_obs;
     // interned ribbon sets (RibbonManager state of parent vertices)
     const double4* ribbons;     // pool: sx, sy, ex, ey
+    const double4* boxes;       // per ribbon of the pool: x_lo, x_hi, y_lo, y_hi of its bounding box grown by the ribbon width + margin
     const int* set_offset;
     const int* set_count;
     const double* set_cct;      // coverageCompletedTime
@@ -74,6 +75,7 @@ struct BestD {
 struct K2Tuning {
     int dirty_budget = 64; // non-clean chunks of an edge that K2t evaluates (warp-cooperatively) before handing the edge to K2b
     int cp_budget = 6;    // ribbon check-points a K2t thread walks
+    int k2b_ctas_per_sm = 0; // K2b CTAs (4 warps each) resident per SM; 0 = as many as fit (4).  PPE_K2B_CTAS
     int deep_walker = 0;  // K2c: thread-per-edge walk of the edges K2t caught covering a ribbon (PPE_DEEP_WALKER=1; measured
                           // slower than handing them to K2b -- DESIGN.md section 4.5 -- so off by default)
 };
@@ -123,8 +125,8 @@ cudaError_t launch_prepare_and_walk(const WorldD& world, int64_t n_total, int64_
                                     unsigned int* heavy_list, cudaStream_t stream, K2Tuning tuning, int* launches_out);
 cudaError_t launch_heavy_and_best(const WorldD& world, int64_t n_total, const ppe_edge* edges, void* prepared_scratch,
                                   ppe_edge_result* results, unsigned long long* counters, unsigned int* heavy_list,
-                                  BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, int* blocks_out,
-                                  int* launches_out);
+                                  BestD* block_best, int max_blocks, int sm_count, cudaStream_t stream, K2Tuning tuning,
+                                  int* blocks_out, int* launches_out);
 cudaError_t launch_patch_results(const ppe_edge_result* results, const unsigned int* heavy_list, const unsigned long long* counters,
                                  int64_t n_total, ppe_edge_result* dst, unsigned int* compact_idx, int sm_count, cudaStream_t stream);
 cudaError_t launch_best_final(const BestD* block_best, int blocks, BestD* best, int64_t index_base, bool accumulate,

@@ -2166,7 +2166,9 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
         if (e != cudaSuccess) return e;
     }
     int launches = 0;
-    k2a_prepare<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(world.cfg, world.dt, world.horizon_end, (long long)n, edges, prepared);
+    // thread-per-edge kernels: a frontier batch (a few thousand edges) in 128-thread CTAs would occupy a fraction of the SMs
+    const int bt = n < (int64_t)sm_count * 128 ? 32 : 128;
+    k2a_prepare<<<(unsigned)((n + bt - 1) / bt), bt, 0, stream>>>(world.cfg, world.dt, world.horizon_end, (long long)n, edges, prepared);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     launches++;
@@ -2179,7 +2181,7 @@ cudaError_t launch_true_cost_kernels(const WorldD& world, int64_t n, const ppe_e
             if (e != cudaSuccess) return e;
         }
         const int dirty_budget = tuning.dirty_budget, cp_budget = tuning.cp_budget;
-        k2t_thread_walk<<<(unsigned)((n + 127) / 128), 128, smem_t, stream>>>(world, 0ll, (long long)n, (long long)n, edges, prepared,
+        k2t_thread_walk<<<(unsigned)((n + bt - 1) / bt), bt, smem_t, stream>>>(world, 0ll, (long long)n, (long long)n, edges, prepared,
                                                                              results, heavy_list, heavy_count, dirty_budget, cp_budget);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;

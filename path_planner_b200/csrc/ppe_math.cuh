@@ -388,7 +388,17 @@ PPE_HD bool ribbon_covered(const RibbonD& r, bool strict, double W) { // Ribbon.
 // returned without dividing because CUDA's fp64 division leaves its inline sequence for numerators that small and calls a
 // ~100-instruction routine -- and an axis-aligned ribbon produces one such quotient in every projection (ncu, round 2:
 // 16 % of the warp walker's instructions were that routine).
-PPE_HD double div_zero_aware(double num, double den) { return (num == 0.0 && den > 0.0) ? num : num / den; }
+// (The compiler turns a guarded division into an unconditional one plus a select, so the guard is put on the OPERAND: the
+// division that is executed in the zero case is 1 / den, which stays on the inline path.)
+PPE_HD double div_zero_aware(double num, double den) {
+    const bool zero_case = (num == 0.0) && (den > 0.0);
+    double safe = zero_case ? 1.0 : num;
+#ifdef __CUDA_ARCH__
+    asm volatile("" : "+d"(safe)); // opaque: otherwise the select is dropped again (its result is unused in the zero case)
+#endif
+    const double q = safe / den;
+    return zero_case ? num : q;
+}
 
 PPE_HD void ribbon_projection(const RibbonD& r, double x, double y, double* px, double* py) { // Ribbon.cpp:72-78
     const double squaredL = ribbon_sqlen(r);

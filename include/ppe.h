@@ -176,12 +176,15 @@ int ppe_dubins_batch(ppe_ctx* ctx, int64_t n, const double* q0, const double* q1
                      int32_t* type, double* param, double* length, int32_t* err);
 
 /* ---- K2: batched true cost = Edge::computeTrueCost ---------------------------------------- */
-/* Host buffers; H2D / D2H copies are part of the call.  Batches above ~390 k edges are pipelined in
- * 262 144-edge slices (PPE_SLICE_EDGES) over two kernel lanes and two copy streams, so copies and
- * kernels of different slices overlap; pinned host buffers make the copies asynchronous.
- * Environment knobs read at ppe_create (tuning / testing only): PPE_THREAD_WALKER=0 evaluates every
- * edge with the warp walker K2b instead of K2t + K2b; PPE_K2T_DIRTY=<n> non-clean chunks a K2t
- * warp may evaluate for one edge before handing it to K2b (default 64 = all). */
+/* Host buffers; H2D / D2H copies are part of the call.  Batches of 2^19 edges and more are pipelined: the edges travel in
+ * 131 072-edge slices (PPE_LATE_SLICE), K2a + K2t of a slice run while the next slice arrives and the previous slice's
+ * records leave, K2b runs once over the heavy list of the whole batch and its records are scattered into `results` by a
+ * kernel when `results` is pinned, mapped memory (cudaHostAlloc / cudaHostRegister) or by the host when it is pageable.
+ * Pinned buffers also make the slice copies asynchronous.  Smaller batches: one H2D, one launch group, one D2H.
+ * Environment knobs read at ppe_create (tuning / testing only): PPE_THREAD_WALKER=0 evaluates every edge with the warp
+ * walker K2b instead of K2t + K2b; PPE_K2T_DIRTY=<n> non-clean chunks of one edge a K2t warp evaluates before handing
+ * the edge to K2b (default 64 = all); PPE_K2T_CPS=<n> ribbon check-points a K2t thread walks (default 6);
+ * PPE_K2B_CTAS=<n> K2b CTAs per SM; PPE_LATE_K2B=0 slices the whole kernel sequence instead (the round-1 pipeline). */
 int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge_result* results);
 /* Ribbons-after of edge `edge_index` of the last batch (4 doubles per ribbon, list order).
  * Returns the number of ribbons (<= cap written) or a negative status. */

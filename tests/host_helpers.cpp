@@ -65,6 +65,17 @@ void hh_cr_acos(int64_t n, const double* x, double* out) {
     for (int64_t i = 0; i < n; i++) out[i] = cr_acos(x[i]);
 }
 
+// div_zero_aware (ppe_math.cuh) element-wise, and Ribbon::getProjection through it (4 doubles per ribbon: sx sy ex ey)
+void hh_div_zero_aware(int64_t n, const double* num, const double* den, double* out) {
+    for (int64_t i = 0; i < n; i++) out[i] = div_zero_aware(num[i], den[i]);
+}
+void hh_ribbon_projection(int64_t n, const double* ribbons, const double* x, const double* y, double* px, double* py) {
+    for (int64_t i = 0; i < n; i++) {
+        const RibbonD r = {ribbons[4 * i], ribbons[4 * i + 1], ribbons[4 * i + 2], ribbons[4 * i + 3]};
+        ribbon_projection(r, x[i], y[i], &px[i], &py[i]);
+    }
+}
+
 // the platform libm (glibc on the reference's x86-64 build), element-wise, for agreement statistics
 void hh_libm_sincos(int64_t n, const double* x, double* s, double* c) {
     for (int64_t i = 0; i < n; i++) { s[i] = sin(x[i]); c[i] = cos(x[i]); }

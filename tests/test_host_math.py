@@ -172,3 +172,34 @@ def test_cr_functions_are_correctly_rounded_and_agree_with_glibc(host_helpers):
         assert err(o[i], mp.atan2(mp.mpf(float(y[i])), mp.mpf(float(xx[i])))) <= 0.5000001
     for i in np.concatenate([rng.integers(0, n, 300), np.flatnonzero(oa != ga)[:50]]):
         assert err(oa[i], mp.acos(mp.mpf(float(a[i])))) <= 0.5000001
+
+
+def test_zero_aware_division_is_the_ieee_quotient(host_helpers):
+    """`div_zero_aware` (the guard that keeps exact-zero numerators away from CUDA's out-of-line division routine) returns
+    the IEEE quotient's bits for every operand class, signs of zero included; `ribbon_projection` through it equals
+    Ribbon::getProjection (Ribbon.cpp:72-78) written with plain divisions, axis-aligned ribbons included."""
+    rng = np.random.default_rng(9)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 5e-324, -5e-324, 1e-310, 1e308, -1e308, np.inf, -np.inf, np.nan, 3.5, -2.25e-200])
+    num = np.concatenate([np.repeat(special, len(special)), rng.normal(0, 1e3, 4000), np.zeros(500), -np.zeros(500)])
+    den = np.concatenate([np.tile(special, len(special)), rng.normal(0, 1e3, 4000), rng.uniform(1e-3, 1e6, 500), rng.uniform(1e-3, 1e6, 500)])
+    out = np.zeros(len(num))
+    host_helpers.hh_div_zero_aware(C.c_int64(len(num)), abi.dptr(num), abi.dptr(den), abi.dptr(out))
+    with np.errstate(all="ignore"):
+        want = num / den
+    ok = ~np.isnan(want)
+    assert np.array_equal(np.isnan(out), np.isnan(want))
+    assert np.array_equal(out[ok].view(np.int64), want[ok].view(np.int64))
+    n = 6000
+    rib = rng.uniform(-500, 500, (n, 4))
+    rib[:2000, 2] = rib[:2000, 0]  # vertical ribbons: (ex - sx) * dot is an exact zero
+    rib[2000:4000, 3] = rib[2000:4000, 1]  # horizontal ones
+    rib = np.ascontiguousarray(rib)
+    x, y = rng.uniform(-500, 500, n), rng.uniform(-500, 500, n)
+    px, py = np.zeros(n), np.zeros(n)
+    host_helpers.hh_ribbon_projection(C.c_int64(n), abi.dptr(rib), abi.dptr(x), abi.dptr(y), abi.dptr(px), abi.dptr(py))
+    sx, sy, ex, ey = rib.T
+    sq = (ex - sx) * (ex - sx) + (ey - sy) * (ey - sy)
+    dot = (x - sx) * (ex - sx) + (y - sy) * (ey - sy)
+    wx = (ex - sx) * dot / sq + sx
+    wy = (ey - sy) * dot / sq + sy
+    assert np.array_equal(px.view(np.int64), wx.view(np.int64)) and np.array_equal(py.view(np.int64), wy.view(np.int64))

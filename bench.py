@@ -321,6 +321,12 @@ def ncu_metrics(workload, n):
         for rec in t.get("captures", []):
             if rec.get("workload") == workload and rec.get("edges") == n:
                 return rec
+        for rec in t.get("captures", []):  # a shard of the captured batch (--gpus N): the pipe share carries over, bytes scale with n
+            if rec.get("workload") == workload and rec.get("edges") and n < rec["edges"]:
+                out = dict(rec)
+                out["dram_bytes"] = rec["dram_bytes"] * n / rec["edges"] if rec.get("dram_bytes") is not None else None
+                out["source"] = "%s; scaled from the %d-edge capture to this rank's %d edges" % (rec.get("source", ""), rec["edges"], n)
+                return out
     except (OSError, ValueError):
         pass
     return {}

@@ -313,3 +313,23 @@ def test_host_buffer_pipeline_matches_oracle(oracle, name, near, n):
     c = ref.true_cost_batch(edges)
     c["ribbons_offset"] = 0
     assert c.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("pipeline", ["late-k2b", "sliced-whole"])
+def test_ribbons_after_pool_overflow_is_retried(oracle, pipeline):
+    """The ribbons-after pool is bump-allocated; a batch that outgrows it is run again with a larger pool (both host-buffer
+    pipelines, forced here with a 64-ribbon pool and small slices).  The caller sees the oracle's records and lists."""
+    import os
+    env = {"PPE_RIBBON_POOL": "64", "PPE_LATE_SLICE": "1024", "PPE_SLICE_EDGES": "1024"}
+    if pipeline == "sliced-whole":
+        env["PPE_LATE_K2B"] = "0"
+    os.environ.update(env)
+    try:
+        eng = EdgeEngine(0)
+        world = synth.WORLDS["c2"]()
+        edges = synth.make_edges(world, 6000, seed=44, near_ribbons=0.6)
+        got, want = _check_batch(eng, oracle, world, edges)
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
+    assert int(want["ribbons_changed"].sum()) * 5 > 64, "the batch does not overflow a 64-ribbon pool"

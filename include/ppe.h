@@ -176,8 +176,8 @@ int ppe_dubins_batch(ppe_ctx* ctx, int64_t n, const double* q0, const double* q1
                      int32_t* type, double* param, double* length, int32_t* err);
 
 /* ---- K2: batched true cost = Edge::computeTrueCost ---------------------------------------- */
-/* Host buffers; H2D / D2H copies are part of the call.  Batches of 2^19 edges and more are pipelined: the edges travel in
- * 131 072-edge slices (PPE_LATE_SLICE), K2a + K2t of a slice run while the next slice arrives and the previous slice's
+/* Host buffers; H2D / D2H copies are part of the call.  Batches of 2^16 edges and more are pipelined: the edges travel in
+ * slices of an eighth of the batch (16 Ki .. 128 Ki edges; PPE_LATE_SLICE fixes the size), K2a + K2t of a slice run while the next slice arrives and the previous slice's
  * records leave, K2b runs once over the heavy list of the whole batch and its records are scattered into `results` by a
  * kernel when `results` is pinned, mapped memory (cudaHostAlloc / cudaHostRegister) or by the host when it is pageable.
  * Pinned buffers also make the slice copies asynchronous.  Smaller batches: one H2D, one launch group, one D2H.

@@ -105,7 +105,8 @@ struct ppe_ctx {
     size_t cap_patch = 0;
     bool thread_walker = true;            // PPE_THREAD_WALKER=0: the warp walker evaluates every edge
     bool late_k2b = true;                 // PPE_LATE_K2B=0: slice the whole kernel sequence of host-buffer batches (A/B)
-    int64_t late_slice = 131072;          // PPE_LATE_SLICE: edges per slice of the late-K2b pipeline
+    int64_t late_slice = 131072;          // PPE_LATE_SLICE: edges per slice of the late-K2b pipeline (default: n / 8, 16 Ki .. 128 Ki)
+    bool late_slice_fixed = false;
     K2Tuning tuning;                      // PPE_K2T_DIRTY / PPE_K2T_CPS, read at ppe_create
     BestD* d_block_best = nullptr;
     BestD* d_best = nullptr;
@@ -416,7 +417,7 @@ int ppe_create(int device, ppe_ctx** out) {
         const char* env_late = getenv("PPE_LATE_K2B");
         if (env_late) ctx->late_k2b = atoi(env_late) != 0;
         const char* env_ls = getenv("PPE_LATE_SLICE");
-        if (env_ls && atoll(env_ls) >= 1024) ctx->late_slice = atoll(env_ls);
+        if (env_ls && atoll(env_ls) >= 1024) { ctx->late_slice = atoll(env_ls); ctx->late_slice_fixed = true; }
         const char* env_k2c = getenv("PPE_DEEP_WALKER");
         if (env_k2c) ctx->tuning.deep_walker = env_k2c[0] == '1';
         ctx->tuning = clamp_tuning(ctx->tuning);
@@ -858,8 +859,16 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
     int rc = make_world(ctx, &w);
     if (rc != PPE_OK) return rc;
     ctx->out_downloaded = false;
-    if (ctx->thread_walker && !ctx->tuning.deep_walker && ctx->late_k2b && n >= 4 * ctx->late_slice) {
-        const int64_t n_slices = (n + ctx->late_slice - 1) / ctx->late_slice;
+    // slice size of the late-K2b pipeline: an eighth of the batch (so that a shard of a batch split over several GPUs is
+    // pipelined like the whole batch is on one), between 16 Ki and 128 Ki edges; PPE_LATE_SLICE fixes it
+    int64_t late_slice = ctx->late_slice;
+    if (!ctx->late_slice_fixed) {
+        late_slice = ((n / 8 + 4095) / 4096) * 4096;
+        if (late_slice < 16384) late_slice = 16384;
+        if (late_slice > 131072) late_slice = 131072;
+    }
+    if (ctx->thread_walker && !ctx->tuning.deep_walker && ctx->late_k2b && n >= 4 * late_slice) {
+        const int64_t n_slices = (n + late_slice - 1) / late_slice;
         while ((int64_t)ctx->ev_in.size() < n_slices) {
             cudaEvent_t a, b, c;
             PPE_CUDA(ctx, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -869,7 +878,7 @@ int ppe_true_cost_batch(ppe_ctx* ctx, int64_t n, const ppe_edge* edges, ppe_edge
             ctx->ev_k2.push_back(b);
             ctx->ev_done.push_back(c);
         }
-        rc = batch_pipelined(ctx, w, n, edges, results, ctx->late_slice);
+        rc = batch_pipelined(ctx, w, n, edges, results, late_slice);
         if (rc != PPE_OK) return rc;
         ctx->last_count = n;
         ctx->have_batch = true;

@@ -23,9 +23,9 @@ struct ppe_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    // host-buffer batches are pipelined in slices: H2D, kernels and D2H of different slices overlap, and the
-    // kernels of consecutive slices run on two alternating lanes so that the tail of one slice (a few edges that
-    // spend their whole length on a ribbon) overlaps the bulk of the next
+    // host-buffer batches are pipelined in slices (batch_pipelined): H2D, K2a + K2t and D2H of different slices overlap,
+    // consecutive slices alternating between two kernel lanes; K2b runs once per batch on `stream`.  (PPE_LATE_K2B=0: the
+    // round-1 pipeline, the whole kernel sequence per slice, each lane with its own scratch.)
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     struct Lane {
         cudaStream_t stream = nullptr;
